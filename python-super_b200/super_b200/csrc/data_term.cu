@@ -1,0 +1,368 @@
+// Projective point-to-plane data term of the LM solver: fused
+//   warp -> project -> validity -> bilinear(+gradient) -> residual -> 28-entry Jacobian row
+//   -> J^T J / J^T r accumulation
+// replacing DataLoss.prepare/forward + LossTool.* + torch.sparse.mm
+// (/root/reference/super/loss.py:106-290, /root/reference/super/utils.py:17-71,
+//  /root/reference/utils/utils.py:161-184).
+//
+// Reduction design (DESIGN.md "J^T J assembly"): surfels are visited in kNN-tuple-sorted order, so a
+// warp's 32 surfels almost always share the same 4 ED nodes.  Each lane computes its own row
+// [j_0..j_27 | r | 0 0 0]; the warp stages the 32x32 panel in shared memory (column-major, stride 36
+// doubles: conflict-free) and accumulates the 32x32 Gram matrix  S += panel^T panel  with FP64 tensor
+// core MMAs (mma.sync m8n8k4 f64, 10 upper-triangular 8x8 tiles).  S[0:28,0:28] is the 4x4 grid of
+// 7x7 node-pair blocks, S[0:28,28] is J^T r and S[28,28] is sum r^2.  The accumulator is flushed with
+// one f64 atomic per entry only when the node tuple changes.  No 3 400-op ATen chain, no COO
+// Jacobian, no SpGEMM.
+#include "common.cuh"
+
+namespace {
+
+struct DataArgs {
+    const double* points;   // (N,3) f64
+    const int* knn_idx;     // (N,4) i32
+    const double* knn_w;    // (N,4) f64
+    const int* order;       // (N,) tuple-sorted surfel ids or nullptr (natural order)
+    int n_cap;
+    const int* n_dev;
+    const double* ed_points;  // (J,3)
+    const double* beta;       // (J,7)
+    int J;
+    const float4* vmap;  // (P,) new-frame vertex map, w = 1 valid / 0 invalid
+    const float4* nmap;  // (P,) new-frame normal map
+    Cam cam;
+    double lambda;
+};
+
+struct Eval {
+    int idx[SB_KNN];
+    int flv, cev, flu, ceu;
+    double r;
+};
+
+// Per-surfel evaluation.  Returns true when the surfel has a valid projective correspondence
+// (the reference's valid_pair & intrpl_valid, loss.py:229-246).  jrow: 28 doubles when GRAD.
+template <bool GRAD>
+__device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, double* jrow, int jstride) {
+    const double* pp = a.points + 3 * (size_t)i;
+    V3 p = v3(pp[0], pp[1], pp[2]);
+    const int4 id4 = *reinterpret_cast<const int4*>(a.knn_idx + 4 * (size_t)i);
+    ev.idx[0] = id4.x; ev.idx[1] = id4.y; ev.idx[2] = id4.z; ev.idx[3] = id4.w;
+    const double2 w01 = *reinterpret_cast<const double2*>(a.knn_w + 4 * (size_t)i);
+    const double2 w23 = *reinterpret_cast<const double2*>(a.knn_w + 4 * (size_t)i + 2);
+    double w[SB_KNN] = {w01.x, w01.y, w23.x, w23.y};
+
+    V3 T = v3(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < SB_KNN; ++k) {
+        const double* g = a.ed_points + 3 * ev.idx[k];
+        const double* b = a.beta + 7 * ev.idx[k];
+        V3 gk = v3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+        V3 cpk;
+        V3 tv = quat_rot_ref(v3(subr(p.x, gk.x), subr(p.y, gk.y), subr(p.z, gk.z)), __ldg(b),
+                             v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3)), cpk);
+        tv.x = addr(addr(tv.x, __ldg(b + 4)), gk.x);
+        tv.y = addr(addr(tv.y, __ldg(b + 5)), gk.y);
+        tv.z = addr(addr(tv.z, __ldg(b + 6)), gk.z);
+        if (k == 0) {
+            T = v3(mulr(w[k], tv.x), mulr(w[k], tv.y), mulr(w[k], tv.z));
+        } else {
+            T.x = addr(T.x, mulr(w[k], tv.x));
+            T.y = addr(T.y, mulr(w[k], tv.y));
+            T.z = addr(T.z, mulr(w[k], tv.z));
+        }
+    }
+    double u, v;
+    project_ref(T, a.cam, u, v);
+    if (!(fabs(u) < 1e9 && fabs(v) < 1e9)) return false;
+    const int H = a.cam.H, W = a.cam.W;
+    const long long P = (long long)H * W;
+    long long coords = round_ll(v) * W + round_ll(u);
+    if (coords < 0 || coords >= P) return false;
+    if (a.vmap[coords].w == 0.f) return false;
+
+    double fv = floor(v), cv = ceil(v), fu = floor(u), cu = ceil(u);
+    int iy[2] = {(int)fv, (int)cv}, ix[2] = {(int)fu, (int)cu};
+    ev.flv = iy[0]; ev.cev = iy[1]; ev.flu = ix[0]; ev.ceu = ix[1];
+    if (iy[0] < 0 || iy[1] >= H || ix[0] < 0 || ix[1] >= W) return false;
+    double dy[2] = {fv - v, cv - v}, dx[2] = {fu - u, cu - u};
+    double wy[2] = {fmax(1.0 - fabs(dy[0]), 0.0), fmax(1.0 - fabs(dy[1]), 0.0)};
+    double wx[2] = {fmax(1.0 - fabs(dx[0]), 0.0), fmax(1.0 - fabs(dx[1]), 0.0)};
+    V3 o = v3(0, 0, 0), n = v3(0, 0, 0);
+    V3 o_u = v3(0, 0, 0), o_v = v3(0, 0, 0), n_u = v3(0, 0, 0), n_v = v3(0, 0, 0);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {   // corner order (fl_v,fl_u),(fl_v,ce_u),(ce_v,fl_u),(ce_v,ce_u)
+        const int yi = c >> 1, xi = c & 1;
+        const int pix = iy[yi] * W + ix[xi];
+        const float4 pv = __ldg(a.vmap + pix);
+        if (pv.w == 0.f) return false;
+        const float4 nv = __ldg(a.nmap + pix);
+        const double wgt_y = wy[yi], wgt_x = wx[xi];
+        // reference: (U * w_y) * w_x, summed over corners in this order
+        o.x += ((double)pv.x * wgt_y) * wgt_x; o.y += ((double)pv.y * wgt_y) * wgt_x; o.z += ((double)pv.z * wgt_y) * wgt_x;
+        n.x += ((double)nv.x * wgt_y) * wgt_x; n.y += ((double)nv.y * wgt_y) * wgt_x; n.z += ((double)nv.z * wgt_y) * wgt_x;
+        if (GRAD) {
+            const double sx = dx[xi] >= 0.0 ? 1.0 : -1.0, sy = dy[yi] >= 0.0 ? 1.0 : -1.0;
+            const double gu = wgt_y * sx, gv = wgt_x * sy;   // d/du, d/dv  (loss.py:147-150)
+            o_u.x += pv.x * gu; o_u.y += pv.y * gu; o_u.z += pv.z * gu;
+            o_v.x += pv.x * gv; o_v.y += pv.y * gv; o_v.z += pv.z * gv;
+            n_u.x += nv.x * gu; n_u.y += nv.y * gu; n_u.z += nv.z * gu;
+            n_v.x += nv.x * gv; n_v.y += nv.y * gv; n_v.z += nv.z * gv;
+        }
+    }
+    V3 diff = v3(T.x - o.x, T.y - o.y, T.z - o.z);
+    ev.r = a.lambda * ((n.x * diff.x + n.y * diff.y) + n.z * diff.z);
+    if (GRAD) {
+        // a^T = n^T (I - dO/dT) + diff^T dN/dT,  d(u,v)/dT uses Z without the 1e-8 (loss.py:161-173)
+        const double cu_ = dot3(diff, n_u) - dot3(n, o_u);
+        const double cv_ = dot3(diff, n_v) - dot3(n, o_v);
+        const double iz = 1.0 / T.z;
+        const double fxz = a.cam.fx * iz, fyz = a.cam.fy * iz;
+        V3 av;
+        av.x = n.x + cu_ * fxz;
+        av.y = n.y + cv_ * fyz;
+        av.z = n.z - (cu_ * fxz * T.x + cv_ * fyz * T.y) * iz;
+#pragma unroll
+        for (int k = 0; k < SB_KNN; ++k) {
+            // node data re-read (L1 hits) instead of being kept live across the bilinear section
+            const double* g = a.ed_points + 3 * ev.idx[k];
+            const double* b = a.beta + 7 * ev.idx[k];
+            const V3 dk = v3(p.x - __ldg(g), p.y - __ldg(g + 1), p.z - __ldg(g + 2));
+            const double qwk = __ldg(b);
+            const V3 qvk = v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+            const V3 cpk = cross3(qvk, dk);
+            const double s = a.lambda * w[k];
+            const double qd = dot3(qvk, dk), aq = dot3(av, qvk), ad = dot3(av, dk);
+            const V3 axd = cross3(av, dk);
+            double* jr = jrow + 7 * k * jstride;
+            jr[0] = s * 2.0 * dot3(av, cpk);
+            jr[1 * jstride] = s * 2.0 * (qd * av.x + aq * dk.x - 2.0 * ad * qvk.x - qwk * axd.x);
+            jr[2 * jstride] = s * 2.0 * (qd * av.y + aq * dk.y - 2.0 * ad * qvk.y - qwk * axd.y);
+            jr[3 * jstride] = s * 2.0 * (qd * av.z + aq * dk.z - 2.0 * ad * qvk.z - qwk * axd.z);
+            jr[4 * jstride] = s * av.x;
+            jr[5 * jstride] = s * av.y;
+            jr[6 * jstride] = s * av.z;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int JT_STRIDE = 36;           // doubles per panel column (32 surfels + 4 pad)
+constexpr int JT_DOUBLES = 32 * JT_STRIDE;
+constexpr int JTJ_WARPS = 4;
+
+__device__ __forceinline__ unsigned long long pack_key(const int* idx) {
+    return ((unsigned long long)(unsigned)idx[0] << 48) | ((unsigned long long)(unsigned)idx[1] << 32) |
+           ((unsigned long long)(unsigned)idx[2] << 16) | (unsigned long long)(unsigned)idx[3];
+}
+
+// Flush one warp accumulator (10 tiles x 2 doubles per lane) into the dense lower-triangular A,
+// g (= -J^T r) and the optional sum r^2.
+__device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, double* A,
+                                          int lda, double* g, double* loss_cur) {
+    int node[4] = {(int)(key >> 48) & 0xffff, (int)(key >> 32) & 0xffff, (int)(key >> 16) & 0xffff,
+                   (int)key & 0xffff};
+    int t = 0;
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti) {
+#pragma unroll
+        for (int tj = ti; tj < 4; ++tj, ++t) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = 8 * ti + (lane >> 2);
+                const int n = 8 * tj + 2 * (lane & 3) + e;
+                const double val = acc[t][e];
+                acc[t][e] = 0.0;
+                if (m > n || n > 28 || val == 0.0) continue;
+                if (n == 28) {
+                    if (m == 28) { if (loss_cur) atomicAdd(loss_cur, val); }
+                    else atomicAdd(g + 7 * node[m / 7] + m % 7, -val);
+                    continue;
+                }
+                const int gm = 7 * node[m / 7] + m % 7, gn = 7 * node[n / 7] + n % 7;
+                const int row = max(gm, gn), col = min(gm, gn);
+                atomicAdd(A + (size_t)row * lda + col, val);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(JTJ_WARPS * 32)
+data_jtj_kernel(DataArgs a, double* __restrict__ A, int lda, double* __restrict__ g, double* loss_cur) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Jt = smem + warp * JT_DOUBLES;
+    for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
+
+    const int n = n_active(a.n_cap, a.n_dev);
+    const int n_chunks = (n + 31) >> 5;
+    const int total_warps = gridDim.x * JTJ_WARPS;
+    const int gw = blockIdx.x * JTJ_WARPS + warp;
+    const int per = (n_chunks + total_warps - 1) / total_warps;
+    const int c0 = gw * per, c1 = min(n_chunks, c0 + per);
+
+    double acc[10][2];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
+    unsigned long long acc_key = 0;
+    bool have = false;
+
+    for (int c = c0; c < c1; ++c) {
+        const int slot = c * 32 + lane;
+        Eval ev;
+        bool matched = false;
+        if (slot < n) {
+            const int sid = a.order ? a.order[slot] : slot;
+            matched = eval_surfel<true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
+        }
+        if (matched) {
+            Jt[28 * JT_STRIDE + lane] = ev.r;
+        } else {
+#pragma unroll
+            for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
+        }
+        __syncwarp();
+        const unsigned long long key = matched ? pack_key(ev.idx) : ~0ull;
+        unsigned remaining = __ballot_sync(0xffffffffu, matched);
+        while (remaining) {
+            const int leader = __ffs(remaining) - 1;
+            const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);
+            const unsigned m = __ballot_sync(0xffffffffu, key == k) & remaining;
+            if (!have || k != acc_key) {
+                if (have) flush_acc(acc, acc_key, lane, A, lda, g, loss_cur);
+                acc_key = k;
+                have = true;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const unsigned m4 = (m >> (4 * ks)) & 0xfu;
+                if (m4 == 0u) continue;   // warp-uniform
+                // rows of other tuples in this k-step are masked out (1.0 / 0.0 factor)
+                const double keep = ((m4 >> (lane & 3)) & 1u) ? 1.0 : 0.0;
+                double x[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    x[t] = keep * Jt[(8 * t + (lane >> 2)) * JT_STRIDE + 4 * ks + (lane & 3)];
+                int t = 0;
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                    for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], x[ti], x[tj]);
+            }
+            remaining &= ~m;
+        }
+        __syncwarp();
+    }
+    if (have) flush_acc(acc, acc_key, lane, A, lda, g, loss_cur);
+}
+
+constexpr int LOSS_BLOCK = 256;
+
+// Loss-only pass (DataLoss.forward(grad=False)): sum r^2, one deterministic partial per block.
+__global__ void __launch_bounds__(LOSS_BLOCK) data_loss_kernel(DataArgs a, double* __restrict__ partials) {
+    __shared__ double red[LOSS_BLOCK / 32];
+    const int n = n_active(a.n_cap, a.n_dev);
+    double s = 0.0;
+    for (int i = blockIdx.x * LOSS_BLOCK + threadIdx.x; i < n; i += gridDim.x * LOSS_BLOCK) {
+        Eval ev;
+        if (eval_surfel<false>(a, i, ev, nullptr, 1)) s += ev.r * ev.r;
+    }
+    s = block_sum<LOSS_BLOCK>(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// Per-surfel rows for parity tests and for the drop-in DataLoss.forward face.
+__global__ void data_rows_kernel(DataArgs a, unsigned char* __restrict__ matched, int* __restrict__ corners,
+                                 double* __restrict__ r, double* __restrict__ jrow_out) {
+    const int n = n_active(a.n_cap, a.n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Eval ev;
+    ev.flv = ev.cev = ev.flu = ev.ceu = 0;
+    ev.r = 0.0;
+    double jrow[28];
+    bool ok = jrow_out ? eval_surfel<true>(a, i, ev, jrow, 1) : eval_surfel<false>(a, i, ev, nullptr, 1);
+    matched[i] = ok ? 1 : 0;
+    if (corners) {
+        corners[4 * i + 0] = ev.flv; corners[4 * i + 1] = ev.cev;
+        corners[4 * i + 2] = ev.flu; corners[4 * i + 3] = ev.ceu;
+    }
+    if (r) r[i] = ok ? ev.r : 0.0;
+    if (jrow_out)
+        for (int c = 0; c < 28; ++c) jrow_out[28 * (size_t)i + c] = ok ? jrow[c] : 0.0;
+}
+
+DataArgs make_args(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
+                   const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
+                   const float* nmap, int H, int W, const double* intr, double lambda) {
+    DataArgs a;
+    a.points = points; a.knn_idx = knn_idx; a.knn_w = knn_w; a.order = order;
+    a.n_cap = n_cap; a.n_dev = n_dev; a.ed_points = ed_points; a.beta = beta; a.J = J;
+    a.vmap = reinterpret_cast<const float4*>(vmap);
+    a.nmap = reinterpret_cast<const float4*>(nmap);
+    a.cam.fx = intr[0]; a.cam.fy = intr[1]; a.cam.cx = intr[2]; a.cam.cy = intr[3];
+    a.cam.H = H; a.cam.W = W;
+    a.lambda = lambda;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_data_loss_blocks(int n_cap) {
+    int b = (n_cap + LOSS_BLOCK - 1) / LOSS_BLOCK;
+    return b < 1 ? 1 : (b > 592 ? 592 : b);   // <= 4 CTAs per SM on 148 SMs
+}
+
+int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
+                     const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
+                     const float* nmap, int H, int W, const double* intr, double lambda, double* A, int lda,
+                     double* g, double* loss_cur, void* stream) {
+    if (!points || !knn_idx || !knn_w || !ed_points || !beta || !vmap || !nmap || !A || !g) return SB_ERR_ARG;
+    if (J <= 0 || J > 65535 || lda < 7 * J) return SB_ERR_ARG;
+    if (n_cap <= 0) return SB_OK;
+    DataArgs a = make_args(points, knn_idx, knn_w, order, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
+                           intr, lambda);
+    const int n_chunks = (n_cap + 31) / 32;
+    int blocks = (n_chunks + JTJ_WARPS * 4 - 1) / (JTJ_WARPS * 4);   // ~4 chunks per warp
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = JTJ_WARPS * JT_DOUBLES * sizeof(double);
+    data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, A, lda, g, loss_cur);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_data_term_loss(const double* points, const int* knn_idx, const double* knn_w, int n_cap,
+                      const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
+                      const float* nmap, int H, int W, const double* intr, double lambda, double* partials,
+                      int n_partials, void* stream) {
+    if (!points || !knn_idx || !knn_w || !ed_points || !beta || !vmap || !nmap || !partials) return SB_ERR_ARG;
+    if (n_partials != sb_data_loss_blocks(n_cap)) return SB_ERR_WORKSPACE;
+    DataArgs a = make_args(points, knn_idx, knn_w, nullptr, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
+                           intr, lambda);
+    data_loss_kernel<<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_data_term_rows(const double* points, const int* knn_idx, const double* knn_w, int n_cap, const int* n_dev,
+                      const double* ed_points, const double* beta, int J, const float* vmap, const float* nmap,
+                      int H, int W, const double* intr, double lambda, unsigned char* matched, int* corners,
+                      double* r, double* jrow, void* stream) {
+    if (!points || !knn_idx || !knn_w || !ed_points || !beta || !vmap || !nmap || !matched) return SB_ERR_ARG;
+    if (n_cap <= 0) return SB_OK;
+    DataArgs a = make_args(points, knn_idx, knn_w, nullptr, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
+                           intr, lambda);
+    data_rows_kernel<<<(n_cap + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, matched, corners, r, jrow);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+}  // extern "C"

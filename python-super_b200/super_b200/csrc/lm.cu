@@ -1,0 +1,246 @@
+// LM solver pieces other than the data term: ARAP + Rot regularisers (residual, analytic Jacobian,
+// normal-equation assembly), additive damping, step application and the device-resident
+// accept/reject controller.  Restates /root/reference/super/loss.py:403-499 and
+// /root/reference/super/LM.py:81-122 without any host synchronisation: u, minimal_loss, the
+// failure flag and the per-iteration trace live in a small device struct.
+#include "common.cuh"
+
+namespace {
+
+// Device-resident controller state (mirrors LM_Solver.LM's locals u, minimal_loss, best_beta).
+struct LMState {
+    double u;             // additive damping (reset to 10 every frame)
+    double v;             // 7.5
+    double minimal_loss;  // 1e10 at frame start
+    int iter;             // iterations completed
+    int failed;           // Cholesky failed -> the reference breaks out of the loop, beta unchanged
+    double loss[64];      // trace: loss at the trial beta of iteration i
+    double loss_terms[64][3];
+    int accept[64];
+    double u_trace[64];
+};
+
+__device__ __forceinline__ void add_lower(double* A, int lda, int r, int c, double v) {
+    if (r >= c) atomicAdd(A + (size_t)r * lda + c, v);
+    else atomicAdd(A + (size_t)c * lda + r, v);
+}
+
+// d[R(q)v]/dq as 3x4 (col 0 = d/dqw, cols 1..3 = d/dqv)   (/root/reference/super/utils.py:59-69)
+__device__ __forceinline__ void quat_jac(const V3& v, double qw, const V3& qv, const V3& cp, double (&Jq)[3][4]) {
+    const double qd = dot3(qv, v);
+    const double q[3] = {qv.x, qv.y, qv.z}, vv[3] = {v.x, v.y, v.z};
+    const double sk[3][3] = {{0, -v.z, v.y}, {v.z, 0, -v.x}, {-v.y, v.x, 0}};
+    Jq[0][0] = 2.0 * cp.x; Jq[1][0] = 2.0 * cp.y; Jq[2][0] = 2.0 * cp.z;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Jq[i][1 + j] = 2.0 * ((i == j ? qd : 0.0) + q[i] * vv[j] - 2.0 * vv[i] * q[j] - qw * sk[i][j]);
+}
+
+// One thread per (node j, neighbour slot k) for ARAP; one thread per node for Rot (threads >= J*K).
+// With A == nullptr only the loss partials are produced.
+__global__ void reg_terms_kernel(const double* __restrict__ ed_points, const int* __restrict__ ed_knn,
+                                 const double* __restrict__ beta, int J, double lam_arap, double lam_rot,
+                                 int use_arap, int use_rot, double* __restrict__ A, int lda,
+                                 double* __restrict__ g, double* __restrict__ loss_arap_rot /* [2] */) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_arap = use_arap ? J * SB_KNN : 0;
+    double la = 0.0, lr = 0.0;
+    if (tid < n_arap) {
+        const int j = tid / SB_KNN;
+        const int n = ed_knn[tid];
+        const V3 gj = v3(ed_points[3 * j], ed_points[3 * j + 1], ed_points[3 * j + 2]);
+        const V3 gn = v3(ed_points[3 * n], ed_points[3 * n + 1], ed_points[3 * n + 2]);
+        const V3 d = v3(gj.x - gn.x, gj.y - gn.y, gj.z - gn.z);
+        const double* bn = beta + 7 * n;
+        const double* bj = beta + 7 * j;
+        const V3 qv = v3(bn[1], bn[2], bn[3]);
+        V3 cp;
+        V3 tv = quat_rot_ref(d, bn[0], qv, cp);
+        // r = lam [ (R(q_n) d + b_n) - (d + b_j) ]        (loss.py:433-437)
+        const double r[3] = {lam_arap * ((tv.x + bn[4]) - (d.x + bj[4])), lam_arap * ((tv.y + bn[5]) - (d.y + bj[5])),
+                             lam_arap * ((tv.z + bn[6]) - (d.z + bj[6]))};
+        la = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        if (A) {
+            double Jq[3][4];
+            quat_jac(d, bn[0], qv, cp, Jq);
+            // residual row c: cols 7n+{0..3} = lam*Jq[c][.], 7n+4+c = lam, 7j+4+c = -lam   (loss.py:418-451)
+            const int bn0 = 7 * n, bj0 = 7 * j;
+            const double l = lam_arap, l2 = lam_arap * lam_arap;
+            for (int a = 0; a < 4; ++a) {
+                for (int b = 0; b <= a; ++b) {
+                    double s = 0.0;
+                    for (int c = 0; c < 3; ++c) s += Jq[c][a] * Jq[c][b];
+                    atomicAdd(A + (size_t)(bn0 + a) * lda + bn0 + b, l2 * s);
+                }
+                double gq = 0.0;
+                for (int c = 0; c < 3; ++c) {
+                    add_lower(A, lda, bn0 + 4 + c, bn0 + a, l2 * Jq[c][a]);     // q_n x b_n
+                    add_lower(A, lda, bj0 + 4 + c, bn0 + a, -l2 * Jq[c][a]);    // q_n x b_j
+                    gq += l * Jq[c][a] * r[c];
+                }
+                atomicAdd(g + bn0 + a, -gq);
+            }
+            for (int c = 0; c < 3; ++c) {
+                atomicAdd(A + (size_t)(bn0 + 4 + c) * lda + bn0 + 4 + c, l2);
+                atomicAdd(A + (size_t)(bj0 + 4 + c) * lda + bj0 + 4 + c, l2);
+                add_lower(A, lda, bj0 + 4 + c, bn0 + 4 + c, -l2);
+                atomicAdd(g + bn0 + 4 + c, -l * r[c]);
+                atomicAdd(g + bj0 + 4 + c, l * r[c]);
+            }
+        }
+    } else if (use_rot && tid < n_arap + J) {
+        // RotLoss in float32 like the reference (loss.py:487-497)
+        const int j = tid - n_arap;
+        const float lam = (float)lam_rot;
+        float q[4];
+        for (int a = 0; a < 4; ++a) q[a] = (float)beta[7 * j + a];
+        const float s = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3];
+        const float r = lam * (1.f - s);
+        lr = (double)(r * r);
+        if (A) {
+            float jv[4];
+            for (int a = 0; a < 4; ++a) jv[a] = -lam * 2.f * q[a];
+            for (int a = 0; a < 4; ++a) {
+                for (int b = 0; b <= a; ++b) atomicAdd(A + (size_t)(7 * j + a) * lda + 7 * j + b, (double)(jv[a] * jv[b]));
+                atomicAdd(g + 7 * j + a, -(double)(jv[a] * r));
+            }
+        }
+    }
+    if (loss_arap_rot) {
+        __shared__ double red[8];
+        double s = block_sum<256>(la, red);
+        if (threadIdx.x == 0 && s != 0.0) atomicAdd(loss_arap_rot + 0, s);
+        s = block_sum<256>(lr, red);
+        if (threadIdx.x == 0 && s != 0.0) atomicAdd(loss_arap_rot + 1, s);
+    }
+}
+
+__global__ void lm_begin_kernel(LMState* st, double* beta, double* best, int J, double u, double v,
+                                double minimal_loss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0;
+    }
+    if (i < 7 * J) {
+        const double val = (i % 7 == 0) ? 1.0 : 0.0;
+        beta[i] = val;
+        best[i] = val;
+    }
+}
+
+__global__ void lm_damp_kernel(const LMState* st, double* A, int lda, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(size_t)i * lda + i] += st->u;
+}
+
+// beta += delta unless the factorisation failed (info != 0  ->  the reference prints and breaks).
+__global__ void lm_step_kernel(LMState* st, const int* info, double* beta, const double* delta, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = st->failed || (info && *info != 0);
+    if (i < n && !bad) beta[i] += delta[i];
+    if (i == 0 && bad) st->failed = 1;
+}
+
+// loss = sum(data partials) + arap + rot; accept iff loss < minimal_loss   (LM.py:107-117)
+__global__ void lm_decide_kernel(LMState* st, const double* partials, int n_partials, double* loss_arap_rot,
+                                 double* beta, double* best, int n) {
+    __shared__ double red[8];
+    __shared__ int s_accept;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += 256) s += partials[i];
+    s = block_sum<256>(s, red);
+    if (threadIdx.x == 0) {
+        const int it = st->iter;
+        if (st->failed) {
+            s_accept = -1;
+        } else {
+            const double la = loss_arap_rot[0], lr = loss_arap_rot[1];
+            const double loss = s + la + lr;
+            const bool acc = loss < st->minimal_loss;
+            if (it < 64) {
+                st->loss[it] = loss;
+                st->loss_terms[it][0] = s; st->loss_terms[it][1] = la; st->loss_terms[it][2] = lr;
+                st->accept[it] = acc ? 1 : 0;
+                st->u_trace[it] = st->u;
+            }
+            if (acc) { st->minimal_loss = loss; st->u /= st->v; }
+            else st->u *= st->v;
+            st->iter = it + 1;
+            s_accept = acc ? 1 : 0;
+        }
+        loss_arap_rot[0] = 0.0;
+        loss_arap_rot[1] = 0.0;
+    }
+    __syncthreads();
+    const int acc = s_accept;
+    if (acc < 0) return;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        if (acc) best[i] = beta[i];
+        else beta[i] = best[i];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_lm_state_bytes() { return (int)sizeof(LMState); }
+
+// Host-readable layout of the trace inside LMState (offsets in bytes): used by the Python face to
+// decode a D2H copy of the state after the frame.
+int sb_lm_state_offsets(int* out /* [8] */) {
+    LMState* p = nullptr;
+    out[0] = (int)(size_t)&p->u; out[1] = (int)(size_t)&p->minimal_loss; out[2] = (int)(size_t)&p->iter;
+    out[3] = (int)(size_t)&p->failed; out[4] = (int)(size_t)&p->loss[0]; out[5] = (int)(size_t)&p->loss_terms[0][0];
+    out[6] = (int)(size_t)&p->accept[0]; out[7] = (int)(size_t)&p->u_trace[0];
+    return SB_OK;
+}
+
+int sb_lm_begin(void* state, double* beta, double* best, int J, double u, double v, double minimal_loss,
+                void* stream) {
+    if (!state || !beta || !best || J <= 0) return SB_ERR_ARG;
+    lm_begin_kernel<<<(7 * J + 255) / 256, 256, 0, (cudaStream_t)stream>>>((LMState*)state, beta, best, J, u, v,
+                                                                         minimal_loss);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_reg_terms(const double* ed_points, const int* ed_knn, const double* beta, int J, double lam_arap,
+                 double lam_rot, int use_arap, int use_rot, double* A, int lda, double* g, double* loss_arap_rot,
+                 void* stream) {
+    if (!ed_points || !ed_knn || !beta || J <= 0) return SB_ERR_ARG;
+    if (A && (!g || lda < 7 * J)) return SB_ERR_ARG;
+    const int threads = (use_arap ? J * SB_KNN : 0) + (use_rot ? J : 0);
+    if (threads == 0) return SB_OK;
+    reg_terms_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        ed_points, ed_knn, beta, J, lam_arap, lam_rot, use_arap, use_rot, A, lda, g, loss_arap_rot);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_lm_damp(const void* state, double* A, int lda, int n, void* stream) {
+    if (!state || !A || n <= 0) return SB_ERR_ARG;
+    lm_damp_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const LMState*)state, A, lda, n);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_lm_step(void* state, const int* info, double* beta, const double* delta, int n, void* stream) {
+    if (!state || !beta || !delta || n <= 0) return SB_ERR_ARG;
+    lm_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((LMState*)state, info, beta, delta, n);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_lm_decide(void* state, const double* partials, int n_partials, double* loss_arap_rot, double* beta,
+                 double* best, int n, void* stream) {
+    if (!state || !partials || !loss_arap_rot || !beta || !best) return SB_ERR_ARG;
+    lm_decide_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((LMState*)state, partials, n_partials, loss_arap_rot,
+                                                         beta, best, n);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+}  // extern "C"

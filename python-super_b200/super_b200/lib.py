@@ -1,0 +1,92 @@
+"""ctypes binding of the C-ABI CUDA library (include/super_b200.h -> libsuper_b200.so).
+
+There is NO fallback: if the library is missing or a call returns non-zero, this raises.  PyTorch
+is used only to own device memory and to supply the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsuper_b200.so")
+
+c_int, c_double, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "super_b200.h")
+_CT = {"p": c_void_p, "i": c_int, "d": c_double}
+
+
+def parse_header(path=HEADER_PATH):
+    """{function name: argument kinds} from the C header -- the header is the single source of truth
+    for the ABI ('p' pointer, 'i' int, 'd' double)."""
+    import re
+    src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\bint\s+(sb_\w+)\s*\(([^)]*)\)\s*;", src):
+        args = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+        kinds = ""
+        for a in args:
+            kinds += "p" if "*" in a else ("d" if a.startswith("double") else "i")
+        sigs[m.group(1)] = kinds
+    return sigs
+
+
+_SIGNATURES = parse_header()
+
+_lib = None
+
+
+class SuperB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsuper_b200.so (built by super_b200.build).  Raises if absent: no CPU / torch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SuperB200Error(
+            f"{LIB_PATH} not found: build it with `python -m super_b200.build` (nvcc, sm_100a). "
+            "super_b200 has no CPU or eager-PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.argtypes = [_CT[c] for c in sig]
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+_ERR = {1: "invalid argument", 2: "CUDA launch error", 3: "workspace size mismatch"}
+
+
+def ptr(t):
+    """Raw device (or host) pointer of a contiguous tensor; None -> NULL."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise SuperB200Error("non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise SuperB200Error(f"{name} failed: {_ERR.get(rc, rc)}")
+
+
+def intr_array(fx, fy, cx, cy):
+    return (c_double * 4)(float(fx), float(fy), float(cx), float(cy))

@@ -1,0 +1,77 @@
+"""Levenberg-Marquardt loop over beta in R^{J x 7} on the device: the B200 restatement of
+LM_Solver.LM (/root/reference/super/LM.py:81-122).
+
+Per iteration: zero A,g -> data-term J^T J kernel (tensor-core Gram panels) -> ARAP/Rot kernel ->
+damping -> dense Cholesky solve -> step -> loss-only pass -> accept/reject.  u, minimal_loss, the
+failure flag and the loss trace stay on the device (ops.LMState): the loop issues no host sync.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+F64 = torch.float64
+
+
+class LMWorkspace:
+    """Buffers reused across frames for a given J."""
+
+    def __init__(self, J, device):
+        n = 7 * J
+        self.J, self.n = J, n
+        self.A = torch.zeros((n, n), dtype=F64, device=device)
+        self.g = torch.zeros((n, 1), dtype=F64, device=device)
+        self.beta = torch.zeros((J, 7), dtype=F64, device=device)
+        self.best = torch.zeros((J, 7), dtype=F64, device=device)
+        self.loss2 = torch.zeros(2, dtype=F64, device=device)
+        self.state = ops.LMState(device)
+        self.partials = None
+
+
+def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
+             on_iter=None):
+    """sf: object with points (N,3) f64, knn_indices (N,4) i32, knn_w (N,4) f64 and ED (points, knn_indices i32).
+    maps: (vmap, nmap) dense float4 images of the new frame.  Returns beta (J,7) f64 (a view of the
+    workspace) -- the same value LM_Solver.LM returns."""
+    ed = sf.ED
+    J = ed.points.shape[0]
+    dev = sf.points.device
+    if ws is None or ws.J != J:
+        ws = LMWorkspace(J, dev)
+    n_cap = sf.points.shape[0]
+    nb = ops.data_loss_blocks(n_cap)
+    if ws.partials is None or ws.partials.numel() != nb:
+        ws.partials = torch.zeros(nb, dtype=F64, device=dev)
+    vmap, nmap = maps
+    use_data, use_arap, use_rot = bool(opt.sf_point_plane), bool(opt.mesh_arap), bool(opt.mesh_rot)
+    lam_d, lam_a, lam_r = opt.sf_point_plane_weight, opt.mesh_arap_weight, opt.mesh_rot_weight
+    if order is None and use_data:
+        order = ops.tuple_order(sf.knn_indices)
+    ops.lm_begin(ws.state, ws.beta, ws.best, u, v, minimal_loss)
+    ws.loss2.zero_()
+    for it in range(opt.num_optimize_iterations):
+        ws.A.zero_()
+        ws.g.zero_()
+        if use_data:
+            ops.data_term_jtj(sf.points, sf.knn_indices, sf.knn_w, order, ed.points, ws.beta, vmap, nmap, cam,
+                              lam_d, ws.A, ws.g, n_dev=n_dev)
+        if use_arap or use_rot:
+            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g)
+        if on_iter is not None:
+            on_iter(it, "normal_equations", ws)
+        ops.lm_damp(ws.state, ws.A)
+        L, info = torch.linalg.cholesky_ex(ws.A, check_errors=False)      # reads the lower triangle
+        delta = torch.cholesky_solve(ws.g, L)
+        ops.lm_step(ws.state, info, ws.beta, delta)
+        if on_iter is not None:
+            on_iter(it, "step", ws, delta)
+        if use_data:
+            ops.data_term_loss(sf.points, sf.knn_indices, sf.knn_w, ed.points, ws.beta, vmap, nmap, cam, lam_d,
+                               ws.partials, n_dev=n_dev)
+        else:
+            ws.partials.zero_()
+        if use_arap or use_rot:
+            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, loss2=ws.loss2)
+        ops.lm_decide(ws.state, ws.partials, ws.loss2, ws.beta, ws.best)
+    return ws.beta, ws

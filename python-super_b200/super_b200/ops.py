@@ -1,0 +1,177 @@
+"""Thin Python wrappers over the C ABI (one function per entry point of include/super_b200.h).
+
+Tensors are torch CUDA tensors used as device-memory handles; all arithmetic happens in the CUDA
+library.  Every wrapper raises if the library is missing (super_b200.lib.load): no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import lib
+from .lib import call, ptr, stream
+
+F64, I32 = torch.float64, torch.int32
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise lib.SuperB200Error("super_b200 ops need CUDA tensors (no CPU path)")
+    return t
+
+
+def as_i32(idx):
+    return idx if idx.dtype == I32 else idx.to(I32)
+
+
+# ---- kNN / weights / warp ----------------------------------------------------------------------
+def knn(query, ref, K, n_dev=None):
+    """find_knn (/root/reference/utils/utils.py:212-220): (sqrt dists (N,K) f64, idx (N,K) i32)."""
+    query, ref = _dev(query).contiguous(), _dev(ref).contiguous()
+    n, dim = query.shape
+    dist = torch.empty((n, K), dtype=F64, device=query.device)
+    idx = torch.empty((n, K), dtype=I32, device=query.device)
+    call("sb_knn", ptr(query), n, ptr(n_dev), ptr(ref), ref.shape[0], dim, K, ptr(dist), ptr(idx), stream())
+    return dist, idx
+
+
+def knn_weights(dist, idx, radii, radius_mode=0, stable=None, n_dev=None):
+    """softmax(exp(-d/r)) (+ clears stable[i] when no node is within its radius)."""
+    n = dist.shape[0]
+    w = torch.empty((n, 4), dtype=F64, device=dist.device)
+    call("sb_knn_weights", ptr(dist), ptr(idx), n, ptr(n_dev), ptr(radii), radius_mode, ptr(w), ptr(stable),
+         stream())
+    return w
+
+
+def reweight(points, idx, ed_points, radii, w_out=None, n_dev=None):
+    n = points.shape[0]
+    if w_out is None:
+        w_out = torch.empty((n, 4), dtype=F64, device=points.device)
+    call("sb_reweight", ptr(points), ptr(idx), n, ptr(n_dev), ptr(ed_points), ptr(radii), ptr(w_out), stream())
+    return w_out
+
+
+def warp_update(points, norms, idx, w, ed_points, ed_norms, beta, n_dev=None):
+    """Surfels.update in place (/root/reference/super/nodes.py:193-223, LM form)."""
+    call("sb_warp_update", ptr(points), ptr(norms), ptr(idx), ptr(w), points.shape[0], ptr(n_dev),
+         ptr(ed_points), ptr(ed_norms), ptr(beta), ed_points.shape[0], stream())
+
+
+# ---- new-frame maps ------------------------------------------------------------------------------
+def dense_maps(nd_points, nd_norms, valid, height, width):
+    """Compact (Nv,3) f64 points/normals + valid (P,) -> dense float4 maps (P,4) f32 [x,y,z,valid].
+    The values are float32-exact in the reference (data_loader.py:453-454 casts f32 results up)."""
+    P = height * width
+    vmap = torch.zeros((P, 4), dtype=torch.float32, device=nd_points.device)
+    nmap = torch.zeros((P, 4), dtype=torch.float32, device=nd_points.device)
+    vmap[valid, :3] = nd_points.to(torch.float32)
+    vmap[valid, 3] = 1.0
+    nmap[valid, :3] = nd_norms.to(torch.float32)
+    return vmap, nmap
+
+
+# ---- LM data term --------------------------------------------------------------------------------
+class Camera:
+    def __init__(self, fx, fy, cx, cy, height, width):
+        self.fx, self.fy, self.cx, self.cy, self.H, self.W = float(fx), float(fy), float(cx), float(cy), height, width
+        self.c = lib.intr_array(fx, fy, cx, cy)
+
+    @staticmethod
+    def from_K(K, height, width):
+        """K: (4,4) or (1,4,4) float32 tensor/array (values promoted to f64 exactly, like the reference)."""
+        K = K.reshape(-1, 4, 4)[0]
+        return Camera(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), height, width)
+
+
+def data_term_rows(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam, want_jrow=True, n_dev=None):
+    n = points.shape[0]
+    dev = points.device
+    matched = torch.zeros(n, dtype=torch.uint8, device=dev)
+    corners = torch.zeros((n, 4), dtype=I32, device=dev)
+    r = torch.zeros(n, dtype=F64, device=dev)
+    jrow = torch.zeros((n, 28), dtype=F64, device=dev) if want_jrow else None
+    call("sb_data_term_rows", ptr(points), ptr(knn_idx), ptr(knn_w), n, ptr(n_dev), ptr(ed_points), ptr(beta),
+         ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam), ptr(matched), ptr(corners),
+         ptr(r), ptr(jrow), stream())
+    return matched.bool(), corners, r, jrow
+
+
+def data_term_jtj(points, knn_idx, knn_w, order, ed_points, beta, vmap, nmap, cam, lam, A, g, loss_cur=None,
+                  n_dev=None):
+    call("sb_data_term_jtj", ptr(points), ptr(knn_idx), ptr(knn_w), ptr(order), points.shape[0], ptr(n_dev),
+         ptr(ed_points), ptr(beta), ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam),
+         ptr(A), A.stride(0), ptr(g), ptr(loss_cur), stream())
+
+
+def data_loss_blocks(n_cap):
+    return lib.load().sb_data_loss_blocks(int(n_cap))
+
+
+def data_term_loss(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam, partials, n_dev=None):
+    call("sb_data_term_loss", ptr(points), ptr(knn_idx), ptr(knn_w), points.shape[0], ptr(n_dev), ptr(ed_points),
+         ptr(beta), ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam), ptr(partials),
+         partials.numel(), stream())
+
+
+def tuple_order(knn_idx):
+    """Surfel ids sorted by their (ordered) 4-tuple of ED nodes: the visiting order of the J^T J
+    kernel, so that a warp's 32 surfels share their node blocks."""
+    k = knn_idx.to(torch.int64)
+    key = (k[:, 0] << 48) | (k[:, 1] << 32) | (k[:, 2] << 16) | k[:, 3]
+    return torch.sort(key, stable=True)[1].to(I32)
+
+
+# ---- LM regularisers / controller ----------------------------------------------------------------
+def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=None, g=None, loss2=None):
+    call("sb_reg_terms", ptr(ed_points), ptr(ed_knn), ptr(beta), ed_points.shape[0], float(lam_arap), float(lam_rot),
+         int(use_arap), int(use_rot), ptr(A), A.stride(0) if A is not None else 0, ptr(g), ptr(loss2), stream())
+
+
+class LMState:
+    """Device-resident controller (u, minimal_loss, trace) -- decoded on demand, never during the loop."""
+
+    def __init__(self, device):
+        l = lib.load()
+        self.nbytes = l.sb_lm_state_bytes()
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        off = (ctypes.c_int * 8)()
+        l.sb_lm_state_offsets(off)
+        self.off = list(off)
+
+    def read(self):
+        """D2H copy + decode (synchronises): dict(u, minimal_loss, iter, failed, loss, loss_terms, accept, u_trace)."""
+        import numpy as np
+        h = self.buf.cpu().numpy()
+        o = self.off
+        it = int(h[o[2]:o[2] + 4].view(np.int32)[0])
+        n = min(it, 64)
+        return {
+            "u": float(h[o[0]:o[0] + 8].view(np.float64)[0]),
+            "minimal_loss": float(h[o[1]:o[1] + 8].view(np.float64)[0]),
+            "iter": it,
+            "failed": int(h[o[3]:o[3] + 4].view(np.int32)[0]),
+            "loss": h[o[4]:o[4] + 8 * 64].view(np.float64)[:n].copy(),
+            "loss_terms": h[o[5]:o[5] + 8 * 192].view(np.float64).reshape(64, 3)[:n].copy(),
+            "accept": h[o[6]:o[6] + 4 * 64].view(np.int32)[:n].copy(),
+            "u_trace": h[o[7]:o[7] + 8 * 64].view(np.float64)[:n].copy(),
+        }
+
+
+def lm_begin(state, beta, best, u=10.0, v=7.5, minimal_loss=1e10):
+    call("sb_lm_begin", ptr(state.buf), ptr(beta), ptr(best), beta.shape[0], float(u), float(v), float(minimal_loss),
+         stream())
+
+
+def lm_damp(state, A):
+    call("sb_lm_damp", ptr(state.buf), ptr(A), A.stride(0), A.shape[0], stream())
+
+
+def lm_step(state, info, beta, delta):
+    call("sb_lm_step", ptr(state.buf), ptr(info), ptr(beta), ptr(delta), beta.numel(), stream())
+
+
+def lm_decide(state, partials, loss2, beta, best):
+    call("sb_lm_decide", ptr(state.buf), ptr(partials), partials.numel(), ptr(loss2), ptr(beta), ptr(best),
+         beta.numel(), stream())
