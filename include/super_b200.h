@@ -23,6 +23,43 @@
 extern "C" {
 #endif
 
+
+/* ---- plain-C views of device state (host structs holding device pointers) ------------------------- */
+
+/* Surfel arrays, reference layouts; capacity-based: rows [0, min(cap,*n_dev)) are live. */
+typedef struct SbSurfels {
+    double* points;         /* (cap,3) f64 */
+    double* norms;          /* (cap,3) f64 */
+    float* colors;          /* (cap,3) f32 */
+    float* confs;           /* (cap,)  f32 */
+    double* radii;          /* (cap,)  f64 */
+    float* time_stamp;      /* (cap,)  f32 */
+    int* knn_idx;           /* (cap,4) i32  (reference: i64) */
+    double* knn_w;          /* (cap,4) f64 */
+    float* projdata;        /* (cap,2) f32  [u,v] */
+    unsigned char* stable;  /* (cap,)  bool */
+    int cap;
+    int* n_dev;             /* device row counter */
+} SbSurfels;
+
+/* One preprocessed input frame as dense per-pixel images (P = H*W). */
+typedef struct SbFrame {
+    const float* vmap;      /* (P,4) f32 x,y,z,valid(1/0)   = new_data.points + valid/index_map */
+    const float* nmap;      /* (P,4) f32 nx,ny,nz,0         = new_data.norms */
+    const double* radii;    /* (P,)  f64                    = new_data.radii scattered */
+    const float* confs;     /* (P,)  f32                    = new_data.confs scattered */
+    const float* color;     /* (3,P) f32 planar             = inputs[("color",0)] */
+    int H, W;
+    double fx, fy, cx, cy;  /* K[0,0], K[1,1], K[0,2], K[1,2] (float32 values promoted) */
+} SbFrame;
+
+typedef struct SbFuseParams {
+    double th_dist;         /* opt.th_dist 0.1 */
+    double th_cos;          /* opt.th_cosine_ang 0.4 */
+    float time_now;         /* sfdata.time */
+    int disable_merging_new, disable_merging_exist, disable_adding_new;
+} SbFuseParams;
+
 int sb_version(void);
 
 /* ---- kNN / weights / warp -------------------------------------------------------------------- */
@@ -49,6 +86,11 @@ int sb_warp_update(double* points, double* norms, const int* idx, const double* 
                    double* ed_points, double* ed_norms, const double* beta, int J, void* stream);
 
 /* ---- LM data term ------------------------------------------------------------------------------ */
+
+/* Sort keys (i64, non-negative) that order surfels by their 4-tuple of ED nodes; rows >= n get the maximum
+ * key.  Sorting them gives the `order` argument of sb_data_term_jtj (the reference has no counterpart: it
+ * builds a COO Jacobian and calls torch.sparse.mm, /root/reference/super/loss.py:285-288,200-205). */
+int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, void* stream);
 
 /* Number of per-block partial sums sb_data_term_loss writes for a given capacity. */
 int sb_data_loss_blocks(int n_cap);
@@ -103,6 +145,37 @@ int sb_lm_step(void* state, const int* info, double* beta, const double* delta, 
 /* loss < minimal_loss ? accept : reject with u /= v | u *= v: /root/reference/super/LM.py:107-117 */
 int sb_lm_decide(void* state, const double* partials, int n_partials, double* loss_arap_rot, double* beta,
                  double* best, int n, void* stream);
+
+
+/* ---- per-frame producer ---------------------------------------------------------------------------- */
+
+/* depth_preprocessing for --load_depth inputs: /root/reference/utils/data_loader.py:333-523 (getN :532-583,
+ * BackprojectDepth /root/reference/depth/monodepth2/layers.py:139-167).  depth (H,W) f32, color (3,H,W) f32,
+ * inval (H,W) u8 optional extra invalid mask, inv_K3x3 = host float[9] (inv_K[:3,:3]), fx = K[0,0].
+ * superv2 != 0 selects that dataset's validity rules.  pcd_scratch (P,4) f32.  Outputs are the SbFrame
+ * images; valid_i32 (P,) optional 0/1 copy of the validity for scans. */
+int sb_preprocess(const float* depth, const float* color, const unsigned char* inval, const float* inv_K3x3,
+                  float fx, float divterm, int superv2, int H, int W, float* pcd_scratch, float* vmap, float* nmap,
+                  double* radii, float* confs, int* valid_i32, void* stream);
+
+/* ---- fusion / compaction ------------------------------------------------------------------------- */
+
+/* Bytes of scratch sb_fuse / sb_compact need for an H x W image and surfel capacity `cap`. */
+long long sb_fuse_workspace_bytes(int H, int W, int cap);
+
+/* Surfels.fuseInputData: /root/reference/super/nodes.py:270-541 (merge_data :301-355).  In place on *sf;
+ * appended rows go to [n, n_out).  track_id (n_track,) i64 device array or NULL.  *overflow is set to 1
+ * if the capacity was too small (rows dropped).  Confidence ties on one pixel -> lower surfel index. */
+int sb_fuse(const SbSurfels* sf, const SbFrame* frame, const double* ed_points, const double* ed_radii, int J,
+            const SbFuseParams* params, long long* track_id, int n_track, int* n_out, int* overflow,
+            void* workspace, long long ws_bytes, void* stream);
+
+/* Surfels.prepareStableIndexNSwapAllModel (state part): /root/reference/super/nodes.py:543-589 plus the
+ * projdata of :540-541.  Stable, recently-updated rows of *src are copied to *dst in order; *dst->n_dev
+ * receives the new count; track ids are remapped. */
+int sb_compact(const SbSurfels* src, const SbSurfels* dst, const SbFrame* frame, double time_now,
+               int th_time_steps, int disable_removing, long long* track_id, int n_track, void* workspace,
+               long long ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

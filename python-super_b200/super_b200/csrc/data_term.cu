@@ -14,6 +14,7 @@
 // one f64 atomic per entry only when the node tuple changes.  No 3 400-op ATen chain, no COO
 // Jacobian, no SpGEMM.
 #include "common.cuh"
+#include "super_b200.h"
 
 namespace {
 
@@ -297,6 +298,18 @@ __global__ void data_rows_kernel(DataArgs a, unsigned char* __restrict__ matched
         for (int c = 0; c < 28; ++c) jrow_out[28 * (size_t)i + c] = ok ? jrow[c] : 0.0;
 }
 
+// 64-bit sort keys of the J^T J visiting order: packed node 4-tuple; rows >= n sort last.
+__global__ void tuple_keys_kernel(const int* __restrict__ knn_idx, int n_cap, const int* n_dev,
+                                  long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cap) return;
+    const int n = n_active(n_cap, n_dev);
+    if (i >= n) { keys[i] = 0x7fffffffffffffffLL; return; }
+    const int4 id = *reinterpret_cast<const int4*>(knn_idx + 4 * (size_t)i);
+    const int idx[4] = {id.x, id.y, id.z, id.w};
+    keys[i] = (long long)(pack_key(idx) >> 1);   // keep it non-negative for a signed sort
+}
+
 DataArgs make_args(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
                    const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
                    const float* nmap, int H, int W, const double* intr, double lambda) {
@@ -318,6 +331,14 @@ extern "C" {
 int sb_data_loss_blocks(int n_cap) {
     int b = (n_cap + LOSS_BLOCK - 1) / LOSS_BLOCK;
     return b < 1 ? 1 : (b > 592 ? 592 : b);   // <= 4 CTAs per SM on 148 SMs
+}
+
+int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, void* stream) {
+    if (!knn_idx || !keys) return SB_ERR_ARG;
+    if (n_cap <= 0) return SB_OK;
+    tuple_keys_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(knn_idx, n_cap, n_dev, keys);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
 }
 
 int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,

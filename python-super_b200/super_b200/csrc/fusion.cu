@@ -1,0 +1,453 @@
+// Projective surfel fusion and stable-surfel compaction:
+//   Surfels.fuseInputData                    /root/reference/super/nodes.py:270-541  (merge_data :301-355)
+//   Surfels.prepareStableIndexNSwapAllModel  /root/reference/super/nodes.py:543-589  (state part)
+//
+// The reference builds up to 16 image-sized "layers" (the i-th most confident surfel of every pixel)
+// with two global sorts and ~3 600 ATen launches, then merges layer by layer.  Every decision it
+// takes is local to ONE pixel: a surfel projects to exactly one pixel, new data lives at one pixel.
+// B200 design: bucket surfels by pixel (count -> exclusive scan -> fill: a CSR over pixels), then
+// one thread per pixel orders its few surfels by (confidence desc, index asc) and replays the
+// reference's layered merge logic sequentially for that pixel.  New surfels are appended in pixel
+// order (scan), exactly the reference's order.  ~10 launches per frame, no host sync.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "super_b200.h"
+
+namespace {
+
+constexpr int MAX_LAYERS = 16;   // nodes.py:379
+
+struct FuseWs {
+    int* cnt;        // (P)   surfels per pixel
+    int* offsets;    // (P+1) exclusive scan of cnt
+    int* seg;        // (cap) surfel ids grouped by pixel
+    int* pix;        // (cap) pixel of each live surfel or -1
+    int* add_flag;   // (P)   1: new pixel passes the node-radius test and is appended
+    int* add_pos;    // (P+1) exclusive scan of add_flag
+    int* add_idx;    // (P,4)
+    double* add_dist;  // (P,4)
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t cub_scan_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, n);
+    return bytes;
+}
+
+size_t carve(FuseWs* w, char* base, int P, int cap) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+    int* cnt = (int*)take(sizeof(int) * (size_t)(P + 1));
+    int* offsets = (int*)take(sizeof(int) * (size_t)(P + 1));
+    int* seg = (int*)take(sizeof(int) * (size_t)cap);
+    int* pix = (int*)take(sizeof(int) * (size_t)cap);
+    int* add_flag = (int*)take(sizeof(int) * (size_t)(P + 1));
+    int* add_pos = (int*)take(sizeof(int) * (size_t)(P + 1));
+    int* add_idx = (int*)take(sizeof(int) * 4 * (size_t)P);
+    double* add_dist = (double*)take(sizeof(double) * 4 * (size_t)P);
+    size_t cb = cub_scan_bytes((P > cap ? P : cap) + 1);
+    void* tmp = take(cb);
+    if (w) {
+        w->cnt = cnt; w->offsets = offsets; w->seg = seg; w->pix = pix; w->add_flag = add_flag;
+        w->add_pos = add_pos; w->add_idx = add_idx; w->add_dist = add_dist; w->cub_tmp = tmp; w->cub_bytes = cb;
+    }
+    return off;
+}
+
+__device__ __forceinline__ Cam cam_of(const SbFrame& f) {
+    Cam c; c.fx = f.fx; c.fy = f.fy; c.cx = f.cx; c.cy = f.cy; c.H = f.H; c.W = f.W;
+    return c;
+}
+
+// ---- 1. project + count ------------------------------------------------------------------------
+__global__ void project_count_kernel(SbSurfels sf, SbFrame fr, int* __restrict__ pix, int* __restrict__ cnt) {
+    const int n = n_active(sf.cap, sf.n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Cam cam = cam_of(fr);
+    double u, v;
+    project_ref(v3(sf.points[3 * (size_t)i], sf.points[3 * (size_t)i + 1], sf.points[3 * (size_t)i + 2]), cam, u, v);
+    int p = -1;
+    if (sf.stable[i] && fabs(u) < 1e9 && fabs(v) < 1e9) {
+        const long long ur = round_ll(u), vr = round_ll(v);
+        if (vr >= 0 && vr < cam.H - 1 && ur >= 0 && ur < cam.W - 1) {   // pcd2depth valid_proj, margin 0
+            p = (int)(vr * cam.W + ur);
+            atomicAdd(cnt + p, 1);
+        }
+    }
+    pix[i] = p;
+}
+
+// ---- 2. fill the per-pixel segments --------------------------------------------------------------
+__global__ void fill_kernel(int n_cap, const int* n_dev, const int* __restrict__ pix, int* __restrict__ cnt,
+                            const int* __restrict__ offsets, int* __restrict__ seg) {
+    const int n = n_active(n_cap, n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = pix[i];
+    if (p < 0) return;
+    const int slot = atomicSub(cnt + p, 1) - 1;   // any order: the pixel thread sorts its segment
+    seg[offsets[p] + slot] = i;
+}
+
+// ---- 3. per-pixel merge logic ----------------------------------------------------------------------
+struct Sample {
+    double p[3], n[3], r;
+    float c[3], w;
+};
+
+__device__ __forceinline__ Sample load_surfel(const SbSurfels& sf, int i) {
+    Sample s;
+    for (int k = 0; k < 3; ++k) {
+        s.p[k] = sf.points[3 * (size_t)i + k];
+        s.n[k] = sf.norms[3 * (size_t)i + k];
+        s.c[k] = sf.colors[3 * (size_t)i + k];
+    }
+    s.r = sf.radii[i];
+    s.w = sf.confs[i];
+    return s;
+}
+
+__device__ __forceinline__ Sample load_new(const SbFrame& fr, int p) {
+    Sample s;
+    const float4 pv = reinterpret_cast<const float4*>(fr.vmap)[p];
+    const float4 nv = reinterpret_cast<const float4*>(fr.nmap)[p];
+    s.p[0] = pv.x; s.p[1] = pv.y; s.p[2] = pv.z;
+    s.n[0] = nv.x; s.n[1] = nv.y; s.n[2] = nv.z;
+    const size_t P = (size_t)fr.H * fr.W;
+    for (int k = 0; k < 3; ++k) s.c[k] = fr.color[k * P + p];
+    s.r = fr.radii[p];
+    s.w = fr.confs[p];
+    return s;
+}
+
+// merge_data (nodes.py:301-355): test, then confidence-weighted blend written into surfel `dst`.
+// float32 quantities (confidence, colour, blend weights) are float here too.
+__device__ __forceinline__ bool try_merge(const SbSurfels& sf, int dst, const Sample& b, double th_dist,
+                                          double th_cos, float time_now, bool add_new) {
+    const Sample a = load_surfel(sf, dst);
+    const double dx = a.p[0] - b.p[0], dy = a.p[1] - b.p[1], dz = a.p[2] - b.p[2];
+    const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    const double cosang = (a.n[0] * b.n[0] + a.n[1] * b.n[1]) + a.n[2] * b.n[2];
+    if (!(dist < th_dist && cosang > th_cos)) return false;
+    const float ws = __fadd_rn(a.w, b.w);
+    const float wa = __fdiv_rn(a.w, ws), wb = __fdiv_rn(b.w, ws);
+    double nn[3], nrm = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        sf.points[3 * (size_t)dst + k] = (double)wa * a.p[k] + (double)wb * b.p[k];
+        nn[k] = (double)wa * a.n[k] + (double)wb * b.n[k];
+        nrm += nn[k] * nn[k];
+    }
+    nrm = fmax(sqrt(nrm), 1e-12);
+    for (int k = 0; k < 3; ++k) sf.norms[3 * (size_t)dst + k] = nn[k] / nrm;
+    sf.radii[dst] = (double)wa * a.r + (double)wb * b.r;
+    sf.confs[dst] = ws;
+    if (add_new) {   // the new sample's colour weight is tripled (nodes.py:337-341)
+        const float wn = __fmul_rn(wb, 3.f);
+        const float wsum = __fadd_rn(wa, wn);
+        const float fa = __fdiv_rn(wa, wsum), fb = __fdiv_rn(wn, wsum);
+        for (int k = 0; k < 3; ++k)
+            sf.colors[3 * (size_t)dst + k] = __fadd_rn(__fmul_rn(fa, a.c[k]), __fmul_rn(fb, b.c[k]));
+    } else {
+        for (int k = 0; k < 3; ++k)
+            sf.colors[3 * (size_t)dst + k] = __fadd_rn(__fmul_rn(wa, a.c[k]), __fmul_rn(wb, b.c[k]));
+    }
+    sf.time_stamp[dst] = time_now;
+    return true;
+}
+
+__global__ void fuse_pixels_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, const int* __restrict__ offsets,
+                                   int* __restrict__ seg, int* __restrict__ add_flag, long long* track_id,
+                                   int n_track) {
+    const int P = fr.H * fr.W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int off = offsets[p];
+    const int m_all = offsets[p + 1] - off;
+    const bool new_valid = reinterpret_cast<const float4*>(fr.vmap)[p].w != 0.f;
+    int want_add = 0;
+    if (m_all == 0) {
+        // no layer covers this pixel: add_valid = valid & ~val_maps[0]  (nodes.py:412); the reference
+        // only reaches that line when at least one layer exists anywhere (checked by the caller: n > 0)
+        if (new_valid && !pr.disable_merging_new) want_add = 1;
+        add_flag[p] = want_add;
+        return;
+    }
+    // order the segment by (confidence desc, surfel index asc): the reference's two sorts with the
+    // tie rule "lower index first" (nodes.py:367-371, DESIGN.md ties)
+    for (int a = 1; a < m_all; ++a) {
+        const int id = seg[off + a];
+        const float c = sf.confs[id];
+        int b = a - 1;
+        while (b >= 0) {
+            const int id2 = seg[off + b];
+            const float c2 = sf.confs[id2];
+            if (c2 > c || (c2 == c && id2 < id)) break;
+            seg[off + b + 1] = id2;
+            --b;
+        }
+        seg[off + b + 1] = id;
+    }
+    const int m = min(m_all, MAX_LAYERS);
+    int ids[MAX_LAYERS];
+    for (int l = 0; l < m; ++l) ids[l] = seg[off + l];
+
+    // ---- merge the new sample into the first layer that accepts it (nodes.py:409-422)
+    if (new_valid && !pr.disable_merging_new) {
+        const Sample nw = load_new(fr, p);
+        bool merged = false;
+        for (int l = 0; l < m && !merged; ++l)
+            merged = try_merge(sf, ids[l], nw, pr.th_dist, pr.th_cos, pr.time_now, true);
+        want_add = merged ? 0 : 1;
+    }
+    add_flag[p] = want_add;
+
+    // ---- merge existing surfels that share the pixel, layer i <- layer j (nodes.py:424-460)
+    if (!pr.disable_merging_exist) {
+        bool present[MAX_LAYERS];
+        for (int l = 0; l < m; ++l) present[l] = true;
+        for (int i = 0; i < m; ++i) {
+            bool cur = present[i];
+            for (int j = i + 1; j < m && cur; ++j) {
+                cur = cur && present[j];       // cumulative mask: val_map &= val_maps[j]
+                if (!cur) break;
+                const Sample sj = load_surfel(sf, ids[j]);
+                if (try_merge(sf, ids[i], sj, pr.th_dist, pr.th_cos, pr.time_now, false)) {
+                    present[j] = false;
+                    sf.stable[ids[j]] = 0;
+                    for (int k = 0; k < n_track; ++k)
+                        if (track_id[k] == ids[j]) track_id[k] = ids[i];
+                }
+            }
+        }
+        for (int l = MAX_LAYERS; l < m_all; ++l) {   // beyond 16 per pixel: deleted (nodes.py:402-403,460)
+            const int id = seg[off + l];
+            sf.stable[id] = 0;
+            for (int k = 0; k < n_track; ++k)
+                if (track_id[k] == id) track_id[k] = -2;
+        }
+    }
+}
+
+// ---- 4. new surfels: kNN against the nodes + radius test -------------------------------------------
+constexpr int ADD_BLOCK = 128;
+constexpr int ADD_TILE = 512;
+
+__global__ void __launch_bounds__(ADD_BLOCK)
+add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* __restrict__ ed_radii, int J,
+               int* __restrict__ add_flag, int* __restrict__ add_idx, double* __restrict__ add_dist) {
+    __shared__ double tile[ADD_TILE * 3];
+    const int P = fr.H * fr.W;
+    const int p = blockIdx.x * ADD_BLOCK + threadIdx.x;
+    const bool active = p < P && add_flag[p] != 0;
+    if (!__syncthreads_or(active)) return;
+    double bd[SB_KNN];
+    int bi[SB_KNN];
+    for (int k = 0; k < SB_KNN; ++k) { bd[k] = INFINITY; bi[k] = -1; }
+    double qx = 0, qy = 0, qz = 0;
+    if (active) {
+        const float4 pv = reinterpret_cast<const float4*>(fr.vmap)[p];
+        qx = pv.x; qy = pv.y; qz = pv.z;
+    }
+    for (int t0 = 0; t0 < J; t0 += ADD_TILE) {
+        const int cnt = min(ADD_TILE, J - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * 3; e += ADD_BLOCK) tile[e] = ed_points[(size_t)t0 * 3 + e];
+        __syncthreads();
+        if (active) {
+            for (int j = 0; j < cnt; ++j) {
+                const double dx = subr(qx, tile[3 * j]), dy = subr(qy, tile[3 * j + 1]), dz = subr(qz, tile[3 * j + 2]);
+                const double d2 = addr(addr(mulr(dx, dx), mulr(dy, dy)), mulr(dz, dz));
+                if (d2 < bd[SB_KNN - 1]) {
+                    bd[SB_KNN - 1] = d2; bi[SB_KNN - 1] = t0 + j;
+#pragma unroll
+                    for (int k = SB_KNN - 1; k > 0; --k)
+                        if (bd[k] < bd[k - 1]) {
+                            const double td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                            const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+                        }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    bool any = false;
+    for (int k = 0; k < SB_KNN; ++k) {
+        bd[k] = __dsqrt_rn(bd[k]);
+        any |= bd[k] <= ed_radii[bi[k]];       // nodes.py:501-502
+        add_idx[4 * (size_t)p + k] = bi[k];
+        add_dist[4 * (size_t)p + k] = bd[k];
+    }
+    if (!any) add_flag[p] = 0;
+}
+
+__global__ void add_write_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, const double* __restrict__ ed_radii,
+                                 const int* __restrict__ add_flag, const int* __restrict__ add_pos,
+                                 const int* __restrict__ add_idx, const double* __restrict__ add_dist,
+                                 int* __restrict__ n_out, int* __restrict__ overflow) {
+    const int P = fr.H * fr.W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_old = n_active(sf.cap, sf.n_dev);
+    if (p == 0) {
+        const int total = n_old + add_pos[P];
+        *n_out = min(total, sf.cap);
+        if (total > sf.cap) *overflow = 1;
+    }
+    if (p >= P || !add_flag[p]) return;
+    const int dst = n_old + add_pos[p];
+    if (dst >= sf.cap) return;
+    const Sample s = load_new(fr, p);
+    double e[SB_KNN], mx = -INFINITY, sum = 0.0;
+    for (int k = 0; k < SB_KNN; ++k) {
+        const int n_ = add_idx[4 * (size_t)p + k];
+        sf.knn_idx[4 * (size_t)dst + k] = n_;
+        e[k] = exp(-add_dist[4 * (size_t)p + k] / ed_radii[n_]);
+        mx = fmax(mx, e[k]);
+    }
+    for (int k = 0; k < SB_KNN; ++k) { e[k] = exp(e[k] - mx); sum += e[k]; }
+    for (int k = 0; k < SB_KNN; ++k) sf.knn_w[4 * (size_t)dst + k] = e[k] / sum;
+    for (int k = 0; k < 3; ++k) {
+        sf.points[3 * (size_t)dst + k] = s.p[k];
+        sf.norms[3 * (size_t)dst + k] = s.n[k];
+        sf.colors[3 * (size_t)dst + k] = s.c[k];
+    }
+    sf.radii[dst] = s.r;
+    sf.confs[dst] = s.w;
+    sf.time_stamp[dst] = pr.time_now;
+    sf.stable[dst] = 1;
+}
+
+// n_out = n when nothing is added
+__global__ void copy_count_kernel(const int* n_dev, int cap, int* n_out) { *n_out = n_active(cap, n_dev); }
+
+// ---- compaction --------------------------------------------------------------------------------------
+__global__ void keep_flag_kernel(SbSurfels sf, float time_now, float th_steps, int disable_removing,
+                                 const long long* track_id, int n_track, int* __restrict__ keep) {
+    const int n = n_active(sf.cap, sf.n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { keep[i] = 0; return; }
+    bool k = true;
+    if (!disable_removing) {
+        k = sf.stable[i] && (time_now - sf.time_stamp[i] < th_steps);     // nodes.py:557
+        for (int t = 0; t < n_track; ++t) k = k || (track_id[t] == i);      // nodes.py:559
+    }
+    keep[i] = k ? 1 : 0;
+}
+
+__global__ void compact_scatter_kernel(SbSurfels src, SbSurfels dst, SbFrame fr, const int* __restrict__ keep,
+                                       const int* __restrict__ pos, int disable_removing) {
+    const int n = n_active(src.cap, src.n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *dst.n_dev = pos[n];
+    if (i >= n || !keep[i]) return;
+    const int d = pos[i];
+    double pt[3];
+    for (int k = 0; k < 3; ++k) {
+        pt[k] = src.points[3 * (size_t)i + k];
+        dst.points[3 * (size_t)d + k] = pt[k];
+        dst.norms[3 * (size_t)d + k] = src.norms[3 * (size_t)i + k];
+        dst.colors[3 * (size_t)d + k] = src.colors[3 * (size_t)i + k];
+    }
+    dst.confs[d] = src.confs[i];
+    dst.radii[d] = src.radii[i];
+    dst.time_stamp[d] = src.time_stamp[i];
+    reinterpret_cast<int4*>(dst.knn_idx)[d] = reinterpret_cast<const int4*>(src.knn_idx)[i];
+    for (int k = 0; k < 4; ++k) dst.knn_w[4 * (size_t)d + k] = src.knn_w[4 * (size_t)i + k];
+    // projdata = unrounded (u,v) as float32 (nodes.py:540-541), computed from the fused position
+    double u, v;
+    project_ref(v3(pt[0], pt[1], pt[2]), cam_of(fr), u, v);
+    dst.projdata[2 * (size_t)d] = (float)u;
+    dst.projdata[2 * (size_t)d + 1] = (float)v;
+    dst.stable[d] = disable_removing ? src.stable[i] : 1;
+}
+
+__global__ void track_remap_kernel(long long* track_id, int n_track, const int* keep, const int* pos, int disable) {
+    const int t = threadIdx.x;
+    if (t >= n_track || disable) return;
+    const long long id = track_id[t];
+    if (id >= 0) track_id[t] = keep[id] ? pos[id] : -1;     // nodes.py:576-580 (id_map is -1 for dropped rows)
+}
+
+}  // namespace
+
+extern "C" {
+
+long long sb_fuse_workspace_bytes(int H, int W, int cap) { return (long long)carve(nullptr, nullptr, H * W, cap); }
+
+int sb_fuse(const SbSurfels* sfp, const SbFrame* frp, const double* ed_points, const double* ed_radii, int J,
+            const SbFuseParams* prp, long long* track_id, int n_track, int* n_out, int* overflow, void* workspace,
+            long long ws_bytes, void* stream) {
+    if (!sfp || !frp || !ed_points || !ed_radii || !prp || !n_out || !overflow || !workspace) return SB_ERR_ARG;
+    const SbSurfels sf = *sfp;
+    const SbFrame fr = *frp;
+    const SbFuseParams pr = *prp;
+    const int P = fr.H * fr.W;
+    FuseWs w;
+    if ((long long)carve(&w, (char*)workspace, P, sf.cap) > ws_bytes) return SB_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gs = (sf.cap + 255) / 256, gp = (P + 255) / 256;
+
+    cudaMemsetAsync(w.cnt, 0, sizeof(int) * (size_t)(P + 1), s);
+    project_count_kernel<<<gs, 256, 0, s>>>(sf, fr, w.pix, w.cnt);
+    SB_CHECK_LAUNCH();
+    size_t cb = w.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.cnt, w.offsets, P + 1, s);
+    fill_kernel<<<gs, 256, 0, s>>>(sf.cap, sf.n_dev, w.pix, w.cnt, w.offsets, w.seg);
+    SB_CHECK_LAUNCH();
+    fuse_pixels_kernel<<<gp, 256, 0, s>>>(sf, fr, pr, w.offsets, w.seg, w.add_flag, track_id, track_id ? n_track : 0);
+    SB_CHECK_LAUNCH();
+    // weights of ALL existing surfels from their fused positions and old indices (nodes.py:480-484)
+    int rc = sb_reweight(sf.points, sf.knn_idx, sf.cap, sf.n_dev, ed_points, ed_radii, sf.knn_w, stream);
+    if (rc) return rc;
+    if (!pr.disable_adding_new && !pr.disable_merging_new) {
+        add_knn_kernel<<<(P + ADD_BLOCK - 1) / ADD_BLOCK, ADD_BLOCK, 0, s>>>(fr, ed_points, ed_radii, J, w.add_flag,
+                                                                             w.add_idx, w.add_dist);
+        SB_CHECK_LAUNCH();
+        cudaMemsetAsync(w.add_flag + P, 0, sizeof(int), s);
+        cb = w.cub_bytes;
+        cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.add_flag, w.add_pos, P + 1, s);
+        add_write_kernel<<<gp, 256, 0, s>>>(sf, fr, pr, ed_radii, w.add_flag, w.add_pos, w.add_idx, w.add_dist, n_out,
+                                            overflow);
+        SB_CHECK_LAUNCH();
+    } else {
+        copy_count_kernel<<<1, 1, 0, s>>>(sf.n_dev, sf.cap, n_out);
+        SB_CHECK_LAUNCH();
+    }
+    return SB_OK;
+}
+
+int sb_compact(const SbSurfels* srcp, const SbSurfels* dstp, const SbFrame* frp, double time_now, int th_time_steps,
+               int disable_removing, long long* track_id, int n_track, void* workspace, long long ws_bytes,
+               void* stream) {
+    if (!srcp || !dstp || !frp || !workspace) return SB_ERR_ARG;
+    const SbSurfels src = *srcp, dst = *dstp;
+    if (dst.cap < src.cap) return SB_ERR_ARG;
+    FuseWs w;
+    const int P = frp->H * frp->W;
+    if ((long long)carve(&w, (char*)workspace, P, src.cap) > ws_bytes) return SB_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((size_t)src.cap + 1 > (size_t)4 * P) return SB_ERR_WORKSPACE;
+    int* keep = w.add_idx;                  // (4P ints) >= cap+1, free after sb_fuse
+    int* pos = (int*)w.add_dist;            // (8P ints) >= cap+1
+    const int g = (src.cap + 1 + 255) / 256;
+    keep_flag_kernel<<<g, 256, 0, s>>>(src, (float)time_now, (float)th_time_steps, disable_removing, track_id,
+                                       track_id ? n_track : 0, keep);
+    SB_CHECK_LAUNCH();
+    size_t cb = w.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, keep, pos, src.cap + 1, s);
+    compact_scatter_kernel<<<g, 256, 0, s>>>(src, dst, *frp, keep, pos, disable_removing);
+    SB_CHECK_LAUNCH();
+    if (track_id && n_track > 0) {
+        track_remap_kernel<<<1, 64, 0, s>>>(track_id, n_track, keep, pos, disable_removing);
+        SB_CHECK_LAUNCH();
+    }
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -8,6 +8,7 @@
 // ascending, ties -> lower index.  Brute force: the reference set (J <= a few thousand nodes) is
 // staged through shared memory in tiles, one query per thread keeps its K best in registers.
 #include "common.cuh"
+#include "super_b200.h"
 
 namespace {
 

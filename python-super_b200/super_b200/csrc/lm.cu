@@ -4,6 +4,7 @@
 // /root/reference/super/LM.py:81-122 without any host synchronisation: u, minimal_loss, the
 // failure flag and the per-iteration trace live in a small device struct.
 #include "common.cuh"
+#include "super_b200.h"
 
 namespace {
 

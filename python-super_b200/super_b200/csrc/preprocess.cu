@@ -1,0 +1,149 @@
+// Per-frame producer: depth image -> candidate surfels, as dense per-pixel maps.
+// Restates depth_preprocessing for --load_depth inputs
+//   /root/reference/utils/data_loader.py:333-523  (getN :532-583,
+//   BackprojectDepth /root/reference/depth/monodepth2/layers.py:139-167)
+// in two stencil passes instead of ~150 ATen launches, and keeps everything on the device (the
+// reference leaves index_map on the CPU, data_loader.py:464).
+//
+// float32 arithmetic follows the reference's op order where it decides VALUES that the tracker
+// treats as exact (back-projected points are f32 and compared bit-exactly in tests); normals go
+// through expf/sqrtf and are tolerance-checked (1e-6).
+#include "common.cuh"
+#include "super_b200.h"
+
+namespace {
+
+struct PreArgs {
+    const float* depth;          // (H,W) f32
+    const float* color;          // (3,H,W) f32 planar
+    const unsigned char* inval;  // (H,W) optional extra invalid mask (valid-mask / del_seg_classes / morphology)
+    float ik[9];                 // inv_K[:3,:3] row-major, float32
+    float fx;                    // K[0,0] float32
+    float divterm;
+    float depth_max;             // superv1: 1.5 ; superv2: +inf
+    int zero_invalid;            // superv2: depth == 0 invalid ; superv1: depth <= 0 invalid
+    int mask_rows;               // superv2: first int(0.1*W) ROWS invalid (reference quirk, Appendix B #10)
+    int H, W;
+};
+
+// pass 1: back-projection + depth validity -> pcd (float4: x,y,z,depth; NaN where invalid)
+__global__ void backproject_kernel(PreArgs a, float4* __restrict__ pcd) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.W) return;
+    const int p = y * a.W + x;
+    const float d = a.depth[p];
+    bool bad = a.zero_invalid ? (d == 0.f) : (d <= 0.f);
+    bad |= d > a.depth_max;
+    bad |= y < a.mask_rows;
+    if (a.inval) bad |= a.inval[p] != 0;
+    const float fxp = (float)x, fyp = (float)y;
+    float4 o;
+    if (bad) {
+        o.x = o.y = o.z = o.w = __int_as_float(0x7fc00000);
+    } else {
+        // matmul(inv_K[:3,:3], [x,y,1]) then depth * (.)   (layers.py:162-163)
+        const float cx_ = __fadd_rn(__fadd_rn(__fmul_rn(a.ik[0], fxp), __fmul_rn(a.ik[1], fyp)), a.ik[2]);
+        const float cy_ = __fadd_rn(__fadd_rn(__fmul_rn(a.ik[3], fxp), __fmul_rn(a.ik[4], fyp)), a.ik[5]);
+        const float cz_ = __fadd_rn(__fadd_rn(__fmul_rn(a.ik[6], fxp), __fmul_rn(a.ik[7], fyp)), a.ik[8]);
+        o.x = __fmul_rn(d, cx_); o.y = __fmul_rn(d, cy_); o.z = __fmul_rn(d, cz_); o.w = d;
+    }
+    pcd[p] = o;
+}
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 add3(F3 a, F3 b) { return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+__device__ __forceinline__ F3 crossf(F3 a, F3 b) {   // torch.cross CPU pattern: fma(a1,b2,-(a2*b1))
+    return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+              __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+
+// pass 2: 8-neighbour colour-weighted normals, validity, radii, confidences
+__global__ void normals_kernel(PreArgs a, const float4* __restrict__ pcd, float4* __restrict__ vmap,
+                               float4* __restrict__ nmap, double* __restrict__ radii, float* __restrict__ confs,
+                               int* __restrict__ valid_i32) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.W) return;
+    const int W = a.W, H = a.H, P = W * H, p = y * W + x;
+    const float nanf_ = __int_as_float(0x7fc00000);
+    const float4 pc = pcd[p];
+    const float c0 = a.color[p], c1 = a.color[P + p], c2 = a.color[2 * P + p];
+    // ring order L, LU, U, RU, R, RD, D, DL   (data_loader.py:553-570)
+    const int dxs[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+    const int dys[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    F3 h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int xx = x + dxs[k], yy = y + dys[k];
+        if (xx < 0 || xx >= W || yy < 0 || yy >= H) { h[k] = f3(nanf_, nanf_, nanf_); continue; }
+        const int q = yy * W + xx;
+        const float4 pa = pcd[q];
+        const float m = __fdiv_rn(__fadd_rn(__fadd_rn(fabsf(__fsub_rn(a.color[q], c0)), fabsf(__fsub_rn(a.color[P + q], c1))),
+                                            fabsf(__fsub_rn(a.color[2 * P + q], c2))), 3.f);
+        const float wgt = expf(-m);
+        h[k] = f3(__fmul_rn(__fsub_rn(pa.x, pc.x), wgt), __fmul_rn(__fsub_rn(pa.y, pc.y), wgt),
+                  __fmul_rn(__fsub_rn(pa.z, pc.z), wgt));
+    }
+    F3 N = f3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        F3 rest = h[i + 1];
+#pragma unroll
+        for (int j = i + 2; j < 8; ++j) rest = add3(rest, h[j]);
+        const F3 c = crossf(h[i], rest);
+        N = (i == 0) ? c : add3(N, c);
+    }
+    const float nn = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(N.x, N.x), __fmul_rn(N.y, N.y)), __fmul_rn(N.z, N.z))), 1e-12f);
+    N = f3(__fdiv_rn(N.x, nn), __fdiv_rn(N.y, nn), __fdiv_rn(N.z, nn));
+    const bool valid = !(isnan(N.x) || isnan(N.y) || isnan(N.z) || isnan(pc.x) || isnan(pc.y) || isnan(pc.z));
+    float4 v, n;
+    if (valid) {
+        v.x = pc.x; v.y = pc.y; v.z = pc.z; v.w = 1.f;
+        n.x = N.x; n.y = N.y; n.z = N.z; n.w = 0.f;
+        // radii = (-depth) / (sqrt(2) * fx * clamp(|n_z|, 0.26, 1))   (data_loader.py:444,468-469)
+        const float c = __fmul_rn((float)1.4142135623730951, a.fx);
+        radii[p] = (double)(-pc.w) / ((double)c * fmin(fmax(fabs((double)N.z), 0.26), 1.0));
+    } else {
+        v.x = v.y = v.z = v.w = 0.f;
+        n.x = n.y = n.z = n.w = 0.f;
+        radii[p] = 0.0;
+    }
+    vmap[p] = v;
+    nmap[p] = n;
+    // confs = exp(-((2x/W-1)^2 + (2y/H-1)^2) * divterm)   (data_loader.py:472-475), float32
+    const float su = __fsub_rn(__fmul_rn(2.f, __fdiv_rn((float)x, (float)W)), 1.f);
+    const float sv = __fsub_rn(__fmul_rn(2.f, __fdiv_rn((float)y, (float)H)), 1.f);
+    const float dc2 = __fadd_rn(__fmul_rn(su, su), __fmul_rn(sv, sv));
+    confs[p] = expf(__fmul_rn(-dc2, a.divterm));
+    if (valid_i32) valid_i32[p] = valid ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_preprocess(const float* depth, const float* color, const unsigned char* inval, const float* inv_K3x3,
+                  float fx, float divterm, int superv2, int H, int W, float* pcd_scratch, float* vmap, float* nmap,
+                  double* radii, float* confs, int* valid_i32, void* stream) {
+    if (!depth || !color || !inv_K3x3 || !pcd_scratch || !vmap || !nmap || !radii || !confs) return SB_ERR_ARG;
+    if (H <= 2 || W <= 2) return SB_ERR_ARG;
+    PreArgs a;
+    a.depth = depth; a.color = color; a.inval = inval;
+    for (int i = 0; i < 9; ++i) a.ik[i] = inv_K3x3[i];
+    a.fx = fx; a.divterm = divterm;
+    a.depth_max = superv2 ? INFINITY : 1.5f;
+    a.zero_invalid = superv2 ? 1 : 0;
+    a.mask_rows = superv2 ? (int)(0.1 * W) : 0;
+    a.H = H; a.W = W;
+    dim3 block(128), grid((W + 127) / 128, H);
+    cudaStream_t s = (cudaStream_t)stream;
+    backproject_kernel<<<grid, block, 0, s>>>(a, reinterpret_cast<float4*>(pcd_scratch));
+    SB_CHECK_LAUNCH();
+    normals_kernel<<<grid, block, 0, s>>>(a, reinterpret_cast<const float4*>(pcd_scratch),
+                                         reinterpret_cast<float4*>(vmap), reinterpret_cast<float4*>(nmap), radii, confs,
+                                         valid_i32);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+"""Device-resident tracker state and the per-frame pipeline (host side, above the C ABI).
+
+This is the B200-native equivalent of SuPer.forward / SuPer.fusion
+(/root/reference/super/super.py:23-83): preprocess -> [init | LM -> update -> fuse -> compact],
+with every stage a handful of CUDA kernels from libsuper_b200.so and NO host synchronisation in
+the tracked-frame path (row counts live on the device; the host only keeps an upper bound that it
+refreshes asynchronously through pinned memory).
+
+Layouts are the reference's in capacity-sized buffers; the drop-in classes in
+super_b200/super/ expose exact-size views of them.
+"""
+from __future__ import annotations
+
+import ctypes
+from types import SimpleNamespace as NS
+
+import torch
+
+from . import lib, ops, lm
+from .lib import call, ptr, stream
+
+F64, F32, I32, I64, U8 = torch.float64, torch.float32, torch.int32, torch.int64, torch.uint8
+
+
+# ---- ctypes mirrors of the structs in include/super_b200.h -------------------------------------------
+class SbSurfels(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("points", "norms", "colors", "confs", "radii", "time_stamp",
+                                               "knn_idx", "knn_w", "projdata", "stable")] + \
+               [("cap", ctypes.c_int), ("n_dev", ctypes.c_void_p)]
+
+
+class SbFrame(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("vmap", "nmap", "radii", "confs", "color")] + \
+               [("H", ctypes.c_int), ("W", ctypes.c_int)] + [(n, ctypes.c_double) for n in ("fx", "fy", "cx", "cy")]
+
+
+class SbFuseParams(ctypes.Structure):
+    _fields_ = [("th_dist", ctypes.c_double), ("th_cos", ctypes.c_double), ("time_now", ctypes.c_float),
+                ("disable_merging_new", ctypes.c_int), ("disable_merging_exist", ctypes.c_int),
+                ("disable_adding_new", ctypes.c_int)]
+
+
+SURFEL_FIELDS = (("points", 3, F64), ("norms", 3, F64), ("colors", 3, F32), ("confs", 0, F32), ("radii", 0, F64),
+                 ("time_stamp", 0, F32), ("knn_idx", 4, I32), ("knn_w", 4, F64), ("projdata", 2, F32),
+                 ("stable", 0, U8))
+
+
+class SurfelBuffers:
+    """One capacity-sized set of surfel arrays + its device row counter."""
+
+    def __init__(self, cap, device):
+        self.cap = int(cap)
+        for name, width, dt in SURFEL_FIELDS:
+            shape = (self.cap, width) if width else (self.cap,)
+            setattr(self, name, torch.zeros(shape, dtype=dt, device=device))
+        self.n_dev = torch.zeros(1, dtype=I32, device=device)
+        self.c = SbSurfels(*[ptr(getattr(self, n)) for n, _, _ in SURFEL_FIELDS], self.cap, ptr(self.n_dev))
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+
+class Frame:
+    """One preprocessed input frame as dense per-pixel images (the SbFrame of the C ABI)."""
+
+    def __init__(self, H, W, device):
+        P = H * W
+        self.H, self.W, self.P = H, W, P
+        self.vmap = torch.zeros((P, 4), dtype=F32, device=device)
+        self.nmap = torch.zeros((P, 4), dtype=F32, device=device)
+        self.radii = torch.zeros(P, dtype=F64, device=device)
+        self.confs = torch.zeros(P, dtype=F32, device=device)
+        self.valid_i32 = torch.zeros(P, dtype=I32, device=device)
+        self.pcd = torch.zeros((P, 4), dtype=F32, device=device)
+        self.color = None
+        self.cam = None
+        self.time = 0.0
+        self.c = None
+
+    def bind(self, color, cam, time):
+        self.color, self.cam, self.time = color, cam, float(time)
+        self.c = SbFrame(ptr(self.vmap), ptr(self.nmap), ptr(self.radii), ptr(self.confs), ptr(color), self.H,
+                         self.W, cam.fx, cam.fy, cam.cx, cam.cy)
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+    @property
+    def valid(self):
+        return self.vmap[:, 3] != 0
+
+
+def preprocess(opt, depth, color, K, inv_K, time, frame=None, inval=None, divterm=1.0 / (2.0 * 0.6 * 0.6)):
+    """depth_preprocessing (/root/reference/utils/data_loader.py:333-523) on the device.
+    depth (H,W) f32, color (3,H,W) f32 CUDA tensors; K, inv_K (4,4) f32 host or device tensors."""
+    H, W = opt.height, opt.width
+    dev = depth.device
+    if frame is None:
+        frame = Frame(H, W, dev)
+    Kh = K.detach().cpu().reshape(-1, 4, 4)[0] if torch.is_tensor(K) else torch.as_tensor(K).reshape(-1, 4, 4)[0]
+    iKh = inv_K.detach().cpu().reshape(-1, 4, 4)[0] if torch.is_tensor(inv_K) else torch.as_tensor(inv_K).reshape(-1, 4, 4)[0]
+    ik = (ctypes.c_float * 9)(*[float(iKh[i, j]) for i in range(3) for j in range(3)])
+    cam = ops.Camera.from_K(Kh, H, W)
+    depth = depth.reshape(H, W).contiguous()
+    color = color.reshape(3, H, W).contiguous()
+    call("sb_preprocess", ptr(depth), ptr(color), ptr(inval), ik, float(Kh[0, 0]), float(divterm),
+         1 if opt.data == "superv2" else 0, H, W, ptr(frame.pcd), ptr(frame.vmap), ptr(frame.nmap), ptr(frame.radii),
+         ptr(frame.confs), ptr(frame.valid_i32), stream())
+    frame.bind(color, cam, time)
+    return frame
+
+
+def extra_invalid_mask(opt, depth, seg=None, mask=None):
+    """The morphology part of the reference's invalid mask (data_loader.py:374-397): only needed when a
+    valid mask is loaded or classes are deleted; otherwise the open/dilate of an all-false mask is a no-op."""
+    if mask is None and not getattr(opt, "del_seg_classes", []):
+        return None
+    import torch.nn.functional as Fn
+    H, W = opt.height, opt.width
+    inval = torch.zeros((1, 1, H, W), dtype=torch.bool, device=depth.device) if mask is None else ~mask.reshape(1, 1, H, W)
+    for c in getattr(opt, "del_seg_classes", []):
+        inval |= seg.reshape(1, 1, H, W) == c
+    if opt.data == "superv1" and opt.dilate_invalid_kernel > 0:
+        def dil(x, k):
+            return Fn.conv2d(x, torch.ones((1, 1, k, k), device=x.device), padding="same") > 0
+        inval = ~dil((~inval).float(), opt.dilate_invalid_kernel)
+        inval = dil(inval.float(), 2 * opt.dilate_invalid_kernel)
+    return inval.reshape(H, W).to(U8).contiguous()
+
+
+# ---- ED graph (once per sequence) -------------------------------------------------------------------
+def build_graph(opt, frame):
+    """init_graph + DirectDeformGraph grid_mesh (/root/reference/super/graph_encoder.py:11-67,128-193)
+    from the dense maps.  Runs once per sequence: plain torch indexing on the device."""
+    H, W, s = frame.H, frame.W, opt.mesh_step_size
+    dev = frame.vmap.device
+    valid = frame.valid.view(H, W)
+    us = torch.arange(0, W - 1, s, device=dev)
+    vs = torch.arange(0, H - 1, s, device=dev)
+    vv, uu = torch.meshgrid(vs, us, indexing="ij")
+    av = valid[vv, uu]
+    u, v = uu[av], vv[av]
+    J = int(u.numel())
+    nid = torch.full((H + s, W + s), -1, dtype=I64, device=dev)
+    nid[v, u] = torch.arange(J, device=dev)
+
+    a, r, d, rd = nid[v, u], nid[v, u + s], nid[v + s, u], nid[v + s, u + s]
+    e = torch.stack([torch.stack([a, r], 1), torch.stack([a, rd], 1), torch.stack([a, d], 1),
+                     torch.stack([r, d], 1)], 1).reshape(-1, 2)
+    e = e[(e >= 0).all(1)]
+    f = torch.stack([torch.stack([a, r, rd], 1), torch.stack([a, rd, d], 1)], 1).reshape(-1, 3)
+    f = f[(f >= 0).all(1)]
+    pix = v * W + u
+    g = NS()
+    g.points = frame.vmap[pix, :3].to(F64).contiguous()
+    g.norms = frame.nmap[pix, :3].to(F64).contiguous()
+    g.edge_index, g.triangles = e.t().contiguous(), f.t().contiguous()
+    lens = torch.linalg.norm(g.points[e[:, 0]] - g.points[e[:, 1]], dim=1)
+    ssum = torch.zeros(J, dtype=F64, device=dev).index_add_(0, e.reshape(-1), lens.repeat_interleave(2))
+    cnt = torch.zeros(J, dtype=F64, device=dev).index_add_(0, e.reshape(-1), torch.ones(2 * len(e), dtype=F64, device=dev))
+    radii = ssum / cnt                                   # mean incident edge length; 0/0 -> NaN like .mean() of empty
+    bad = torch.isnan(radii)
+    radii = torch.where(bad, radii[~bad].mean(), radii)
+    g.radii = radii.contiguous()
+    g.edges_lens = lens
+    ta = torch.linalg.cross(g.points[f[:, 1]] - g.points[f[:, 0]], g.points[f[:, 2]] - g.points[f[:, 0]], dim=1)
+    g.triangles_areas = 0.5 * torch.sqrt((ta ** 2).sum(1) + 1e-13)
+    g.num, g.param_num = J, 7 * J
+    # update_ed (/root/reference/super/nodes.py:154-168): K+1 nearest, drop self, weights use the query radius
+    dist, idx = ops.knn(g.points, g.points, opt.num_ED_neighbors + 1)
+    g.knn_indices = idx[:, 1:].contiguous()
+    g.knn_w = ops.knn_weights(dist[:, 1:].contiguous(), g.knn_indices, g.radii, radius_mode=1)
+    return g
+
+
+# ---- tracker -----------------------------------------------------------------------------------------
+class Tracker:
+    """Sequence state + per-frame step.  opt: the reference's option namespace (options.py flags)."""
+
+    def __init__(self, opt, device="cuda", capacity_factor=2.5):
+        lib.load()
+        self.opt = opt
+        self.dev = torch.device(device)
+        self.H, self.W = opt.height, opt.width
+        self.P = self.H * self.W
+        self.cap = int(capacity_factor * self.P)
+        self.cur = None              # SurfelBuffers holding the state
+        self.alt = None              # ping-pong partner for compaction
+        self.ED = None
+        self.ws = None               # LM workspace
+        self.fuse_ws = None
+        self.n_bound = 0             # host upper bound on the row count
+        self._n_pinned = torch.zeros(1, dtype=I32).pin_memory() if torch.cuda.is_available() else None
+        self._n_event = None
+        self._frames_since_known = 0
+        self.n_tmp = torch.zeros(1, dtype=I32, device=self.dev)
+        self.overflow = torch.zeros(1, dtype=I32, device=self.dev)
+        self.track_id = None
+        self.frames = [Frame(self.H, self.W, self.dev), Frame(self.H, self.W, self.dev)]
+        self._fi = 0
+        self.time = None
+        self.last_beta = None
+
+    # -- row-count bookkeeping (no blocking sync on the tracked-frame path) ----------------------------
+    def _publish_count(self):
+        self._n_pinned.copy_(self.cur.n_dev, non_blocking=True)
+        self._n_event = torch.cuda.Event()
+        self._n_event.record()
+        self._frames_since_known = 0
+
+    def _refresh_bound(self):
+        if self._n_event is not None and self._n_event.query():
+            self.n_bound = min(self.cap, int(self._n_pinned[0]) + self._frames_since_known * self.P)
+            self._n_event = None
+
+    def num_surfels(self):
+        """Exact row count (synchronises)."""
+        return int(self.cur.n_dev.item())
+
+    # -- frame stages -------------------------------------------------------------------------------------
+    def next_frame(self):
+        self._fi ^= 1
+        return self.frames[self._fi]
+
+    def init(self, frame):
+        """Surfels.__init__ + update_sfed_knn + first compaction (nodes.py:93-191, super.py:60-63)."""
+        opt, dev = self.opt, self.dev
+        self.ED = build_graph(opt, frame)
+        self.cur, self.alt = SurfelBuffers(self.cap, dev), SurfelBuffers(self.cap, dev)
+        self.fuse_ws = torch.zeros(int(lib.load().sb_fuse_workspace_bytes(self.H, self.W, self.cap)), dtype=U8, device=dev)
+        valid = frame.valid
+        n = int(valid.sum())                               # init only: a sync is fine here
+        if n > self.cap:
+            raise lib.SuperB200Error("surfel capacity too small")
+        b = self.cur
+        b.points[:n] = frame.vmap[valid, :3].to(F64)
+        b.norms[:n] = frame.nmap[valid, :3].to(F64)
+        b.colors[:n] = frame.color.reshape(3, -1).t()[valid]
+        b.confs[:n] = frame.confs[valid]
+        b.radii[:n] = frame.radii[valid]
+        b.time_stamp[:n] = frame.time
+        b.stable[:n] = 1
+        b.n_dev.fill_(n)
+        dist, idx = ops.knn(b.points[:n], self.ED.points, opt.num_neighbors)
+        b.knn_idx[:n] = idx
+        b.knn_w[:n] = ops.knn_weights(dist, idx, self.ED.radii, 0, b.stable)
+        # projdata of the init frame = pixel coordinates (x,y) of the valid pixels (nodes.py:143-145)
+        pix = valid.nonzero()[:, 0]
+        b.projdata[:n, 0] = (pix % self.W).to(F32)
+        b.projdata[:n, 1] = (pix // self.W).to(F32)
+        self.n_bound = n
+        self.time = frame.time
+        self._compact(frame, keep_projdata=True)
+        self._publish_count()
+
+    def _compact(self, frame, keep_projdata=False):
+        opt = self.opt
+        proj = self.cur.projdata.clone() if keep_projdata else None
+        call("sb_compact", self.cur.ref(), self.alt.ref(), frame.ref(), float(frame.time), int(opt.th_time_steps),
+             int(bool(opt.disable_removing_unstable_surfels)), ptr(self.track_id),
+             0 if self.track_id is None else self.track_id.numel(), ptr(self.fuse_ws), self.fuse_ws.numel(), stream())
+        if keep_projdata:   # init frame: projdata is the integer pixel grid, not a re-projection
+            n = int(self.cur.n_dev.item())
+            keep = (self.cur.stable[:n] != 0)
+            m = int(keep.sum())
+            self.alt.projdata[:m] = proj[:n][keep]
+        self.cur, self.alt = self.alt, self.cur
+
+    def track(self, frame):
+        """SuPer.fusion (/root/reference/super/super.py:66-83), LM path."""
+        opt = self.opt
+        self._refresh_bound()
+        self._frames_since_known += 1
+        sfv = self.view(self.n_bound)
+        beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, n_dev=self.cur.n_dev)
+        self.last_beta = beta
+        ops.warp_update(sfv.points, sfv.norms, sfv.knn_indices, sfv.knn_w, self.ED.points, self.ED.norms, beta,
+                        n_dev=self.cur.n_dev)
+        pr = SbFuseParams(opt.th_dist, opt.th_cosine_ang, float(frame.time), int(bool(opt.disable_merging_new_surfels)),
+                          int(bool(opt.disable_merging_exist_surfels)), int(bool(opt.disable_adding_new_surfels)))
+        call("sb_fuse", self.cur.ref(), frame.ref(), ptr(self.ED.points), ptr(self.ED.radii), self.ED.num,
+             ctypes.byref(pr), ptr(self.track_id), 0 if self.track_id is None else self.track_id.numel(),
+             ptr(self.n_tmp), ptr(self.overflow), ptr(self.fuse_ws), self.fuse_ws.numel(), stream())
+        self.cur.n_dev.copy_(self.n_tmp)
+        self.n_bound = min(self.cap, self.n_bound + self.P)
+        self.time = frame.time
+        self._compact(frame)
+        self._publish_count()
+        return beta
+
+    def view(self, n):
+        """Views of the first n rows of the current buffers, in the layouts the LM solver takes."""
+        b = self.cur
+        return NS(points=b.points[:n], norms=b.norms[:n], knn_indices=b.knn_idx[:n], knn_w=b.knn_w[:n], ED=self.ED)
+
+    def step(self, depth, color, K, inv_K, time, inval=None):
+        """One SuPer.forward: preprocess + (init | track).  Returns beta or None."""
+        frame = preprocess(self.opt, depth, color, K, inv_K, time, frame=self.next_frame(), inval=inval)
+        if self.cur is None:
+            self.init(frame)
+            return None
+        return self.track(frame)
+
+    def snapshot(self):
+        """Exact-size copies of the state in the reference's layouts (synchronises)."""
+        n = self.num_surfels()
+        b = self.cur
+        out = {name: getattr(b, name)[:n].clone() for name, _, _ in SURFEL_FIELDS}
+        out["knn_indices"] = out.pop("knn_idx").to(I64)
+        out["isStable"] = out.pop("stable").bool()
+        return out

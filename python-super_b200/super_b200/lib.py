@@ -16,7 +16,10 @@ LIB_PATH = os.path.join(_HERE, "libsuper_b200.so")
 c_int, c_double, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
 
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "super_b200.h")
-_CT = {"p": c_void_p, "i": c_int, "d": c_double}
+_CT = {"p": c_void_p, "i": c_int, "d": c_double, "f": ctypes.c_float, "l": ctypes.c_longlong}
+
+
+_RESTYPE = {}
 
 
 def parse_header(path=HEADER_PATH):
@@ -25,12 +28,22 @@ def parse_header(path=HEADER_PATH):
     import re
     src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
     sigs = {}
-    for m in re.finditer(r"\bint\s+(sb_\w+)\s*\(([^)]*)\)\s*;", src):
-        args = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+    for m in re.finditer(r"\b(int|long long)\s+(sb_\w+)\s*\(([^)]*)\)\s*;", src):
+        args = [a.strip() for a in m.group(3).split(",") if a.strip() and a.strip() != "void"]
         kinds = ""
         for a in args:
-            kinds += "p" if "*" in a else ("d" if a.startswith("double") else "i")
-        sigs[m.group(1)] = kinds
+            if "*" in a:
+                kinds += "p"
+            elif a.startswith("double"):
+                kinds += "d"
+            elif a.startswith("float"):
+                kinds += "f"
+            elif a.startswith("long long"):
+                kinds += "l"
+            else:
+                kinds += "i"
+        sigs[m.group(2)] = kinds
+        _RESTYPE[m.group(2)] = ctypes.c_longlong if m.group(1) == "long long" else c_int
     return sigs
 
 
@@ -56,7 +69,7 @@ def load():
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.argtypes = [_CT[c] for c in sig]
-        fn.restype = c_int
+        fn.restype = _RESTYPE.get(name, c_int)
     _lib = lib
     return lib
 

@@ -47,7 +47,7 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
     use_data, use_arap, use_rot = bool(opt.sf_point_plane), bool(opt.mesh_arap), bool(opt.mesh_rot)
     lam_d, lam_a, lam_r = opt.sf_point_plane_weight, opt.mesh_arap_weight, opt.mesh_rot_weight
     if order is None and use_data:
-        order = ops.tuple_order(sf.knn_indices)
+        order = ops.tuple_order(sf.knn_indices, n_dev)
     ops.lm_begin(ws.state, ws.beta, ws.best, u, v, minimal_loss)
     ws.loss2.zero_()
     for it in range(opt.num_optimize_iterations):

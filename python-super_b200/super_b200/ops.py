@@ -115,12 +115,13 @@ def data_term_loss(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam
          partials.numel(), stream())
 
 
-def tuple_order(knn_idx):
+def tuple_order(knn_idx, n_dev=None):
     """Surfel ids sorted by their (ordered) 4-tuple of ED nodes: the visiting order of the J^T J
-    kernel, so that a warp's 32 surfels share their node blocks."""
-    k = knn_idx.to(torch.int64)
-    key = (k[:, 0] << 48) | (k[:, 1] << 32) | (k[:, 2] << 16) | k[:, 3]
-    return torch.sort(key, stable=True)[1].to(I32)
+    kernel, so that a warp's 32 surfels share their node blocks.  Rows beyond *n_dev sort last."""
+    n = knn_idx.shape[0]
+    keys = torch.empty(n, dtype=torch.int64, device=knn_idx.device)
+    call("sb_tuple_keys", ptr(knn_idx), n, ptr(n_dev), ptr(keys), stream())
+    return torch.sort(keys, stable=True)[1].to(I32)
 
 
 # ---- LM regularisers / controller ----------------------------------------------------------------

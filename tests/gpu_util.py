@@ -31,3 +31,39 @@ def device_maps(nd, H, W, dev="cuda"):
 
 def camera(nd, H, W):
     return ops.Camera.from_K(nd.K, H, W)
+
+
+def frame_from_newdata(nd, frame_np, H, W, dev="cuda"):
+    """engine.Frame filled with the ORACLE's (i.e. the reference's) new_data values, so that fusion
+    tests are teacher-forced on exact inputs."""
+    from super_b200 import engine
+    fr = engine.Frame(H, W, dev)
+    valid = nd.valid.to(dev)
+    fr.vmap[valid, :3] = nd.points.to(dev).float()
+    fr.vmap[valid, 3] = 1.0
+    fr.nmap[valid, :3] = nd.norms.to(dev).float()
+    fr.radii[valid] = nd.radii.to(dev)
+    fr.confs[valid] = nd.confs.to(dev)
+    color = torch.from_numpy(frame_np["color"]).to(dev).contiguous()
+    fr.bind(color, camera(nd, H, W), float(frame_np["time"]))
+    return fr
+
+
+def tracker_from_state(opt, sf, dev="cuda"):
+    """engine.Tracker whose device buffers hold an oracle/golden state."""
+    from super_b200 import engine, lib
+    trk = engine.Tracker(opt, device=dev)
+    n = len(sf.points)
+    trk.cur, trk.alt = engine.SurfelBuffers(trk.cap, trk.dev), engine.SurfelBuffers(trk.cap, trk.dev)
+    trk.fuse_ws = torch.zeros(int(lib.load().sb_fuse_workspace_bytes(trk.H, trk.W, trk.cap)), dtype=torch.uint8, device=dev)
+    b = trk.cur
+    b.points[:n] = sf.points.to(dev); b.norms[:n] = sf.norms.to(dev); b.colors[:n] = sf.colors.to(dev)
+    b.confs[:n] = sf.confs.to(dev); b.radii[:n] = sf.radii.to(dev); b.time_stamp[:n] = sf.time_stamp.to(dev)
+    b.knn_idx[:n] = sf.knn_indices.to(torch.int32).to(dev); b.knn_w[:n] = sf.knn_w.to(dev)
+    b.projdata[:n] = sf.projdata.to(dev); b.stable[:n] = sf.isStable.to(torch.uint8).to(dev)
+    b.n_dev.fill_(n)
+    trk.n_bound = n
+    trk.ED = to_device_state(sf).ED
+    trk.ED.num = sf.ED.num
+    trk._publish_count()
+    return trk
