@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- tracked frames/sec of full ED tracking (producer + LM x10 + warp + fusion + compaction)
+at 640x480 / mesh_step_size 32 (BASELINE.json config 2) on N B200s, one independent sequence per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework (C-ABI CUDA path)
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPU (oracle port)
+    torchrun ... bench.py --gpus N ...                        # N independent replicas, NCCL only for the metric gather
+
+One JSON line on stdout (rank 0).  A "step" is one tracked frame.  `value` = frames/s with the frame's
+inputs already resident in HBM; `e2e` = the same metric through the drop-in SuPer.forward call with
+pinned HOST buffers (H2D of depth+colour and a D2H read of beta inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "python-super_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+H, W, STEP, LM_ITERS = 480, 640, 32, 10
+METRIC = "tracked frames/sec (ED warp+ICP+LM) at 640x480"
+WORKLOAD = ("SuPer LM tracking, synthetic 640x480 deforming-surface depth, mesh_step_size 32, "
+            "--sf_point_plane --mesh_rot --mesh_arap --use_derived_gradient, 10 LM iterations/frame")
+
+
+def make_opt():
+    from types import SimpleNamespace as NS
+    return NS(method="super", phase="test", use_derived_gradient=True, num_optimize_iterations=LM_ITERS,
+              num_ED_neighbors=4, num_neighbors=4, th_dist=0.1, th_cosine_ang=0.4, th_time_steps=30,
+              disable_removing_unstable_surfels=False, disable_merging_new_surfels=False,
+              disable_merging_exist_surfels=False, disable_adding_new_surfels=False, mesh_step_size=STEP,
+              data="superv1", height=H, width=W, dilate_invalid_kernel=5, sf_point_plane=True,
+              sf_point_plane_weight=1.0, mesh_arap=True, mesh_arap_weight=10.0, mesh_rot=True, mesh_rot_weight=1.0,
+              mesh_face=False, mesh_face_weight=1.0, optimizer="SGD", learning_rate=5e-5)
+
+
+def seq_time(i):
+    """Frame index -> synthetic time: triangle wave so that depth stays inside (0, 1.5] for any K."""
+    period = 300
+    j = i % period
+    return 1 + (j if j < period // 2 else period - j)
+
+
+def frames_host(n, seed=0):
+    from super_b200 import synth
+    tex = synth.texture(H, W, seed)
+    return [synth.frame_inputs(seq_time(i), H, W, tex=tex) for i in range(n)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_cuda(args, rank, world, local_rank):
+    from super_b200 import engine, lib
+    from super_b200.super.super import SuPer
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib.load()
+    K, Wm = args.steps, args.warmup
+    nfr = 1 + Wm + K
+    host = frames_host(nfr, seed=rank)                      # one independent sequence per rank
+    opt = make_opt()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- arm 1: inputs resident in HBM ----------------------------------------------------------------
+    dd = [torch.from_numpy(f["depth"]).to(dev) for f in host]
+    dc = torch.from_numpy(host[0]["color"]).to(dev)
+    Kt, iKt = torch.from_numpy(host[0]["K"]), torch.from_numpy(host[0]["inv_K"])
+    trk = engine.Tracker(opt, device=dev)
+    trk.step(dd[0], dc, Kt, iKt, host[0]["time"])
+    for i in range(1, 1 + Wm):
+        trk.step(dd[i], dc, Kt, iKt, host[i]["time"])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.LAUNCHES = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kev = []          # (start, end) around the dominant data-term kernel, first LM iteration of each frame
+    lib.KERNEL_EVENTS = kev
+    t_wall = time.perf_counter()
+    for k in range(K):
+        i = 1 + Wm + k
+        flush.fill_(k & 0xff)                                # L2 flush, outside the timed events
+        ev[k][0].record()
+        trk.step(dd[i], dc, Kt, iKt, host[i]["time"])
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    lib.KERNEL_EVENTS = None
+    launches = lib.LAUNCHES
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    jt_ms = [a.elapsed_time(b) for a, b in kev]
+    n_surf = trk.num_surfels()
+    st = trk.ws.state.read()
+    overflow = int(trk.overflow.item())
+
+    # ---- arm 2: end to end through the drop-in SuPer.forward with pinned host buffers ------------------
+    pin = []
+    for f in host:
+        pin.append({("depth", 0): torch.from_numpy(f["depth"])[None].pin_memory(),
+                    ("color", 0): torch.from_numpy(f["color"])[None].pin_memory(),
+                    "K": torch.from_numpy(f["K"])[None], "inv_K": torch.from_numpy(f["inv_K"])[None],
+                    "time": torch.tensor([f["time"]], dtype=torch.float64), "filename": [f["filename"]],
+                    "ID": torch.tensor([f["ID"]]), "divterm": torch.tensor([f["divterm"]], dtype=torch.float64)})
+    h2d = int(pin[0][("depth", 0)].numel() * 4 + pin[0][("color", 0)].numel() * 4)
+    model = SuPer(opt)
+    models = type("Models", (), {})()
+    models.super = model
+    beta_host = torch.zeros((1, 7), dtype=torch.float64).pin_memory()
+    model(models, dict(pin[0]))
+    for i in range(1, 1 + Wm):
+        model(models, dict(pin[i]))
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2h = 0
+    for k in range(K):
+        beta = model(models, dict(pin[1 + Wm + k]))
+        if beta_host.shape != beta.shape:
+            beta_host = torch.zeros(beta.shape, dtype=torch.float64).pin_memory()
+        beta_host.copy_(beta, non_blocking=False)            # D2H read of the step's result (synchronises)
+        d2h = beta.numel() * 8
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_wall = time.perf_counter() - t0
+
+    # ---- reduce over ranks: max time, sum frames ----------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        gathered = [None] * world
+        torch.distributed.all_gather_object(gathered, {"rank": rank, "fps": K / (sum(step_ms) / 1e3), "surfels": n_surf})
+    else:
+        gathered = None
+    if rank != 0:
+        return
+
+    value = world * K / (total_ms / 1e3)
+    N, P = n_surf, H * W
+    b_pass = 44 * N + 28 * P                                 # algorithmic bytes of one surfel pass
+    jt_avg_ms = float(np.mean(jt_ms)) if jt_ms else None
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = (b_pass / 1e9) / (jt_avg_ms / 1e3) if jt_avg_ms else None
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms / K, "ms_per_lm_iteration": (total_ms / K) / LM_ITERS,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "configs_index": 1, "frames_timed": K, "surfels": N, "ed_nodes": int(trk.ED.num),
+                   "parallelism": f"{world} independent sequence replica(s), no data-path collective",
+                   "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events)",
+                   "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
+        "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K,
+                "api": "super_b200.super.super.SuPer.forward(models, inputs) with pinned host depth+colour"},
+        "gpu_launches": launches,
+        "gpu_launches_per_lm_iteration": launches / (K * LM_ITERS),
+        "clocks": clocks,
+        "roofline": {"kernel": "data_jtj_kernel (fused warp+project+bilinear+Jacobian+J^T J, one LM iteration)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "algorithmic_bytes": b_pass, "launch_ms": jt_avg_ms,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+        "lm_trace_last_frame": {"loss": [float(x) for x in st["loss"]], "accept": [int(x) for x in st["accept"]]},
+        "wall_s_timed_region": wall, "capacity_overflow": overflow,
+    }
+    if gathered:
+        out["per_rank"] = gathered
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(iters=args.cpu_iters)
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_setup():
+    from oracle import super_oracle as so
+    opt = so.default_opt(height=H, width=W, mesh_step_size=STEP)
+    host = frames_host(2)
+    trk = so.Tracker(opt, assemble="sparse_mm")
+    trk.step(host[0])
+    return so, opt, trk, host
+
+
+def cpu_one_iteration(so, opt, sf, nd, beta, u):
+    """One LM iteration as the reference executes it (LM.py:96-107): normal equations (COO Jacobian +
+    torch.sparse.mm), damping, Cholesky solve, loss-only pass."""
+    A, g, _ = so.lm_normal_equations(opt, sf, nd, beta, "sparse_mm")
+    n = A.shape[0]
+    A[torch.arange(n), torch.arange(n)] += u
+    L = torch.linalg.cholesky(A)
+    delta = torch.cholesky_solve(g, L).view(-1, 7)
+    loss, _ = so.lm_cost(opt, sf, nd, beta + delta)
+    return beta + delta, float(loss)
+
+
+def cpu_baseline(iters=3):
+    """Oracle port (reference algorithm, torch CPU, all host threads) on a bounded sample: `iters` LM
+    iterations of the first tracked frame + one update/fuse/compact, extrapolated to 10 iterations/frame."""
+    torch.set_num_threads(os.cpu_count())
+    so, opt, trk, host = cpu_setup()
+    t0 = time.perf_counter()
+    nd = so.preprocess(opt, host[1])
+    t_pre = time.perf_counter() - t0
+    J = trk.sf.ED.num
+    beta = torch.tensor([[1., 0, 0, 0, 0, 0, 0]], dtype=torch.float64).repeat(J, 1)
+    u, its = 10.0, []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        beta, _ = cpu_one_iteration(so, opt, trk.sf, nd, beta, u)
+        its.append(time.perf_counter() - t0)
+        u /= 7.5
+    t0 = time.perf_counter()
+    so.update(opt, trk.sf, beta)
+    so.fuse(opt, trk.sf, nd)
+    so.compact(opt, trk.sf, float(host[1]["time"]))
+    t_rest = time.perf_counter() - t0
+    t_it = float(np.mean(its))
+    frame_s = t_pre + LM_ITERS * t_it + t_rest
+    return {"value": 1.0 / frame_s, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{iters} LM iterations ({t_it:.2f} s each) + producer {t_pre:.2f} s + update/fuse/compact "
+                      f"{t_rest:.2f} s of tracked frame 1, extrapolated to {LM_ITERS} iterations/frame",
+            "ms_per_lm_iteration": 1e3 * t_it}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the Python
+    reference cannot travel to the GPU box).  Each step = one LM iteration of a tracked frame."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    so, opt, trk, host = cpu_setup()
+    t0 = time.perf_counter()
+    nd = so.preprocess(opt, host[1])
+    t_pre = time.perf_counter() - t0
+    J = trk.sf.ED.num
+    ident = torch.tensor([[1., 0, 0, 0, 0, 0, 0]], dtype=torch.float64).repeat(J, 1)
+    beta, u = ident.clone(), 10.0
+    budget_s = 240.0
+    t_start = time.perf_counter()
+    for _ in range(args.warmup):
+        if time.perf_counter() - t_start > 0.3 * budget_s:
+            break
+        beta, _ = cpu_one_iteration(so, opt, trk.sf, nd, beta, u)
+    times, steps_done = [], 0
+    for k in range(args.steps):
+        if k % LM_ITERS == 0:
+            beta, u = ident.clone(), 10.0
+        t0 = time.perf_counter()
+        beta, _ = cpu_one_iteration(so, opt, trk.sf, nd, beta, u)
+        times.append(time.perf_counter() - t0)
+        u /= 7.5
+        steps_done += 1
+        if time.perf_counter() - t_start > budget_s:       # keep the whole run within a few minutes
+            break
+    t0 = time.perf_counter()
+    so.update(opt, trk.sf, beta)
+    so.fuse(opt, trk.sf, nd)
+    so.compact(opt, trk.sf, float(host[1]["time"]))
+    t_rest = time.perf_counter() - t0
+    t_it = float(np.mean(times))
+    frame_s = t_pre + LM_ITERS * t_it + t_rest
+    value = 1.0 / frame_s
+    sample = (f"each step = one LM iteration (normal equations via COO Jacobian + torch.sparse.mm, Cholesky, loss pass) "
+              f"of a 640x480 tracked frame on the host CPU; {steps_done} steps timed ({t_it:.2f} s each); frame time = "
+              f"producer {t_pre:.2f} s + {LM_ITERS} x iteration + update/fuse/compact {t_rest:.2f} s")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+           "steps": steps_done, "warmup": args.warmup, "ms_per_step": 1e3 * frame_s,
+           "ms_per_lm_iteration": 1e3 * t_it, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "configs_index": 1},
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_cuda(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

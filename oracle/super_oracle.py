@@ -171,7 +171,15 @@ def preprocess(opt, frame):
     xs, ys = np.meshgrid(range(W), range(H), indexing="xy")
     pix = torch.from_numpy(np.stack([xs.reshape(-1), ys.reshape(-1), np.ones(H * W)], 0)
                            .astype(np.float32))[None]
-    cam = torch.matmul(inv_K[:, :3, :3], pix)
+    # The reference does torch.matmul(inv_K[:, :3, :3], pix) in float32.  Its CPU BLAS evaluates each
+    # entry as the FMA chain  t = a*x; t = fma(b, y, t); t = fma(c, 1, t)  (measured here, bit for bit:
+    # oracle/validate_port.py); the restatement spells that chain out so that it does not depend on the
+    # BLAS build of the machine it runs on.  fma is emulated in float64 (f32 products are exact there).
+    ik = inv_K[0, :3, :3].double()
+    px, py, p1 = pix[0, 0:1].double(), pix[0, 1:2].double(), pix[0, 2:3].double()
+    t = (ik[:, 0:1] * px).float()
+    t = (ik[:, 1:2] * py + t.double()).float()
+    cam = (ik[:, 2:3] * p1 + t.double()).float()[None]
     cam = depth.view(1, 1, -1) * cam
     pcd = cam.reshape(1, 3, H, W).permute(0, 2, 3, 1).clone()
 

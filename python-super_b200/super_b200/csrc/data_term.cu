@@ -351,10 +351,19 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
     DataArgs a = make_args(points, knn_idx, knn_w, order, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
                            intr, lambda);
     const int n_chunks = (n_cap + 31) / 32;
-    int blocks = (n_chunks + JTJ_WARPS * 4 - 1) / (JTJ_WARPS * 4);   // ~4 chunks per warp
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    if (blocks < 1) blocks = 1;
     const size_t smem = JTJ_WARPS * JT_DOUBLES * sizeof(double);
+    // exactly one wave: resident CTAs per SM x SM count (a partial second wave was a 40% tail, ncu r1)
+    static int resident = 0;
+    if (resident == 0) {
+        int per_sm = 0, dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_jtj_kernel, JTJ_WARPS * 32, smem);
+        resident = (per_sm > 0 ? per_sm : 1) * sms;
+    }
+    int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
     data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, A, lda, g, loss_cur);
     SB_CHECK_LAUNCH();
     return SB_OK;

@@ -41,10 +41,11 @@ __global__ void backproject_kernel(PreArgs a, float4* __restrict__ pcd) {
     if (bad) {
         o.x = o.y = o.z = o.w = __int_as_float(0x7fc00000);
     } else {
-        // matmul(inv_K[:3,:3], [x,y,1]) then depth * (.)   (layers.py:162-163)
-        const float cx_ = __fadd_rn(__fadd_rn(__fmul_rn(a.ik[0], fxp), __fmul_rn(a.ik[1], fyp)), a.ik[2]);
-        const float cy_ = __fadd_rn(__fadd_rn(__fmul_rn(a.ik[3], fxp), __fmul_rn(a.ik[4], fyp)), a.ik[5]);
-        const float cz_ = __fadd_rn(__fadd_rn(__fmul_rn(a.ik[6], fxp), __fmul_rn(a.ik[7], fyp)), a.ik[8]);
+        // matmul(inv_K[:3,:3], [x,y,1]) then depth * (.)   (layers.py:162-163).  The reference's CPU BLAS
+        // evaluates each entry as t = a*x; t = fma(b,y,t); t = fma(c,1,t) (measured bit for bit, see oracle).
+        const float cx_ = __fadd_rn(__fmaf_rn(a.ik[1], fyp, __fmul_rn(a.ik[0], fxp)), a.ik[2]);
+        const float cy_ = __fadd_rn(__fmaf_rn(a.ik[4], fyp, __fmul_rn(a.ik[3], fxp)), a.ik[5]);
+        const float cz_ = __fadd_rn(__fmaf_rn(a.ik[7], fyp, __fmul_rn(a.ik[6], fxp)), a.ik[8]);
         o.x = __fmul_rn(d, cx_); o.y = __fmul_rn(d, cy_); o.z = __fmul_rn(d, cz_); o.w = d;
     }
     pcd[p] = o;

@@ -94,11 +94,29 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels of OURS launched per C-ABI call (library kernels such as the CUB scans are not counted)
+KERNELS_PER_CALL = {"sb_knn": 1, "sb_knn_weights": 1, "sb_reweight": 1, "sb_warp_update": 2, "sb_tuple_keys": 1,
+                    "sb_data_term_jtj": 1, "sb_data_term_loss": 1, "sb_data_term_rows": 1, "sb_lm_begin": 1,
+                    "sb_reg_terms": 1, "sb_lm_damp": 1, "sb_lm_step": 1, "sb_lm_decide": 1, "sb_preprocess": 2,
+                    "sb_fuse": 6, "sb_compact": 2}
+LAUNCHES = 0            # running count (bench.py resets it around the timed region)
+KERNEL_EVENTS = None    # bench.py: list receiving (start, end) CUDA events around each sb_data_term_jtj launch
+
+
 def call(name, *args):
+    global LAUNCHES
     lib = load()
+    ev = None
+    if KERNEL_EVENTS is not None and name == "sb_data_term_jtj":
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     rc = getattr(lib, name)(*args)
+    if ev is not None:
+        ev[1].record()
+        KERNEL_EVENTS.append(ev)
     if rc != 0:
         raise SuperB200Error(f"{name} failed: {_ERR.get(rc, rc)}")
+    LAUNCHES += KERNELS_PER_CALL.get(name, 0)
 
 
 def intr_array(fx, fy, cx, cy):

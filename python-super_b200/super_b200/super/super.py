@@ -1,0 +1,63 @@
+"""SuPer: per-frame orchestration, call-compatible with /root/reference/super/super.py:11-83.
+
+    models.super(models, inputs)      # once per frame, inputs = one DataLoader item (batch 1)
+
+Host->device staging of the frame (super.py:31-34), producer, then init or fusion
+(LM -> update -> fuse -> compact), all through super_b200.engine.Tracker, i.e. libsuper_b200.so.
+Only the derived-gradient (LM) path is built in this round; the autograd GraphFit path raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import engine
+from .nodes import Surfels
+
+
+class SuPer(torch.nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.sf = None
+        self._trk = None
+        if not opt.use_derived_gradient:
+            raise NotImplementedError(
+                "super_b200 round 1 implements the derived-gradient LM path (--use_derived_gradient); "
+                "the autograd GraphFit path (super/deform_mesh.py) is the next SURVEY 8 row")
+        from .LM import LM_Solver
+        self.lm = LM_Solver(opt)
+
+    def forward(self, models, inputs):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self._trk is None:
+            self._trk = engine.Tracker(self.opt, device=dev)
+        staged = {}
+        for key, ipt in inputs.items():                          # super.py:31-34
+            if torch.is_tensor(ipt):
+                if key == "divterm":
+                    staged[key] = float(ipt.reshape(-1)[0])
+                elif key in ("K", "inv_K", "time", "ID"):
+                    staged[key] = ipt                            # small host-side parameters
+                else:
+                    staged[key] = ipt.to(dev, non_blocking=True)
+            else:
+                staged[key] = ipt
+        inputs.update(staged)
+        depth, color = inputs[("depth", 0)], inputs[("color", 0)]
+        time = float(torch.as_tensor(inputs["time"]).reshape(-1)[0])
+        seg = inputs.get(("seg", 0))
+        inval = engine.extra_invalid_mask(self.opt, depth, seg=seg, mask=inputs.get("valid_mask"))
+        frame = engine.preprocess(self.opt, depth, color, inputs["K"], inputs["inv_K"], time,
+                                  frame=self._trk.next_frame(), inval=inval,
+                                  divterm=inputs.get("divterm", 1.0 / (2.0 * 0.6 * 0.6)))
+        self.last_frame = frame
+        if self._trk.cur is None:
+            self._trk.init(frame)
+            self.sf = Surfels(self.opt, self._trk)
+            deform_param = None
+        else:
+            deform_param = self.fusion(models, inputs, frame)
+        return deform_param
+
+    def fusion(self, models, inputs, sfdata):
+        return self._trk.track(sfdata)
