@@ -90,7 +90,8 @@ int sb_warp_update(double* points, double* norms, const int* idx, const double* 
 /* Sort keys (i64, non-negative) that order surfels by their 4-tuple of ED nodes; rows >= n get the maximum
  * key.  Sorting them gives the `order` argument of sb_data_term_jtj (the reference has no counterpart: it
  * builds a COO Jacobian and calls torch.sparse.mm, /root/reference/super/loss.py:285-288,200-205). */
-int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, void* stream);
+int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, const int* node_pos,
+                  int* block_bw, void* stream);
 
 /* Number of per-block partial sums sb_data_term_loss writes for a given capacity. */
 int sb_data_loss_blocks(int n_cap);
@@ -98,11 +99,13 @@ int sb_data_loss_blocks(int n_cap);
 /* DataLoss.forward(grad=True) + LossTool.prepare_jtj_jtl: /root/reference/super/loss.py:200-205,222-288.
  * Accumulates J^T J into the LOWER triangle of dense row-major A (lda >= 7J) and -J^T r into g (7J);
  * both must be zeroed (or hold the other terms) by the caller.  `order` (n,) optional kNN-tuple-sorted
- * surfel ids.  intr = host double[4] {fx,fy,cx,cy}.  loss_cur (optional) accumulates sum r^2 at beta. */
+ * surfel ids.  intr = host double[4] {fx,fy,cx,cy}.  loss_cur (optional) accumulates sum r^2 at beta.
+ * Matrix target: bw < 0 -> dense A[row*lda + col]; bw >= 0 -> lower band A[row*lda + col - row + bw] in the
+ * node order node_pos (node id -> position, may be NULL); entries outside the band set *band_overflow. */
 int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
                      const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
                      const float* nmap, int H, int W, const double* intr, double lambda, double* A, int lda,
-                     double* g, double* loss_cur, void* stream);
+                     int bw, const int* node_pos, int* band_overflow, double* g, double* loss_cur, void* stream);
 
 /* DataLoss.forward(grad=False): /root/reference/super/loss.py:222-248,289-290.  partials[b] = sum of r^2
  * over the surfels of block b (n_partials == sb_data_loss_blocks(n_cap)); deterministic. */
@@ -133,14 +136,24 @@ int sb_lm_begin(void* state, double* beta, double* best, int J, double u, double
 /* ARAPLoss + RotLoss (Rot in float32 like the reference): /root/reference/super/loss.py:403-499.
  * With A != NULL adds J^T J (lower) and -J^T r; always adds sum r^2 to loss_arap_rot[0..1] if non-NULL. */
 int sb_reg_terms(const double* ed_points, const int* ed_knn, const double* beta, int J, double lam_arap,
-                 double lam_rot, int use_arap, int use_rot, double* A, int lda, double* g, double* loss_arap_rot,
-                 void* stream);
+                 double lam_rot, int use_arap, int use_rot, double* A, int lda, int bw, const int* node_pos,
+                 int* band_overflow, double* g, double* loss_arap_rot, void* stream);
 
 /* jtj[diag] += u: /root/reference/super/LM.py:97 */
 int sb_lm_damp(const void* state, double* A, int lda, int n, void* stream);
 
 /* beta += delta unless *info != 0 (failed factorisation -> loop stops): /root/reference/super/LM.py:99-105 */
-int sb_lm_step(void* state, const int* info, double* beta, const double* delta, int n, void* stream);
+int sb_lm_step(void* state, const int* info, double* beta, const double* delta, int n, const int* node_pos,
+               void* stream);
+
+/* Banded Cholesky solve of (A + u I) x = g replacing torch.linalg.cholesky + cholesky_solve:
+ * /root/reference/super/LM.py:38-51,97-100.  AB (n, ldab) lower band row-major (overwritten by L), g (n) rhs in /
+ * solution out, u device scalar (NULL = 0), dinv (n) scratch, *info set to 1 on a non-positive pivot.
+ * One launch on one thread-block cluster of `cluster_size` CTAs (1,2,4,8 or 16). */
+int sb_band_max_bw(void);
+int sb_band_debug(int flags); /* timing experiments only: 1 skip trailing update, 2 skip back-substitution, 4 skip panel math */
+int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                  int cluster_size, void* stream);
 
 /* loss < minimal_loss ? accept : reject with u /= v | u *= v: /root/reference/super/LM.py:107-117 */
 int sb_lm_decide(void* state, const double* partials, int n_partials, double* loss_arap_rot, double* beta,

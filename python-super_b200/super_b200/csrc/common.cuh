@@ -81,6 +81,26 @@ __device__ __forceinline__ int n_active(int n_cap, const int* n_dev) {
     return n_dev ? min(n_cap, *n_dev) : n_cap;
 }
 
+// Lower-triangular normal-equation matrix, dense (bw < 0: A[row*lda + col]) or band
+// (A[row*lda + col - row + bw], entries with row - col > bw raise *overflow), with an optional node
+// permutation (node id -> position in the solver's ordering).
+struct MatView {
+    double* A;
+    int lda, bw;
+    const int* node_pos;
+    int* overflow;
+    __device__ __forceinline__ int pos(int node) const { return node_pos ? node_pos[node] : node; }
+    __device__ __forceinline__ void add(int row, int col, double v) const {   // requires row >= col
+        if (bw < 0) {
+            atomicAdd(A + (size_t)row * lda + col, v);
+        } else if (row - col <= bw) {
+            atomicAdd(A + (size_t)row * lda + (col - row + bw), v);
+        } else {
+            *overflow = 1;
+        }
+    }
+};
+
 // ---- block-wide deterministic sum (fixed tree), result valid in thread 0 -----------------------
 template <int BLOCK>
 __device__ __forceinline__ double block_sum(double v, double* smem /* BLOCK/32 doubles */) {

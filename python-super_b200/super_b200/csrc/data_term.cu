@@ -162,12 +162,14 @@ __device__ __forceinline__ unsigned long long pack_key(const int* idx) {
            ((unsigned long long)(unsigned)idx[2] << 16) | (unsigned long long)(unsigned)idx[3];
 }
 
-// Flush one warp accumulator (10 tiles x 2 doubles per lane) into the dense lower-triangular A,
-// g (= -J^T r) and the optional sum r^2.
-__device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, double* A,
-                                          int lda, double* g, double* loss_cur) {
+// Flush one warp accumulator (10 tiles x 2 doubles per lane) into the lower-triangular A (dense or band,
+// common.cuh MatView), g (= -J^T r) and the optional sum r^2.
+__device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, const MatView& M,
+                                          double* g, double* loss_cur) {
     int node[4] = {(int)(key >> 48) & 0xffff, (int)(key >> 32) & 0xffff, (int)(key >> 16) & 0xffff,
                    (int)key & 0xffff};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) node[k] = M.pos(node[k]);
     int t = 0;
 #pragma unroll
     for (int ti = 0; ti < 4; ++ti) {
@@ -186,15 +188,14 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
                     continue;
                 }
                 const int gm = 7 * node[m / 7] + m % 7, gn = 7 * node[n / 7] + n % 7;
-                const int row = max(gm, gn), col = min(gm, gn);
-                atomicAdd(A + (size_t)row * lda + col, val);
+                M.add(max(gm, gn), min(gm, gn), val);
             }
         }
     }
 }
 
 __global__ void __launch_bounds__(JTJ_WARPS * 32)
-data_jtj_kernel(DataArgs a, double* __restrict__ A, int lda, double* __restrict__ g, double* loss_cur) {
+data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Jt = smem + warp * JT_DOUBLES;
@@ -235,7 +236,7 @@ data_jtj_kernel(DataArgs a, double* __restrict__ A, int lda, double* __restrict_
             const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);
             const unsigned m = __ballot_sync(0xffffffffu, key == k) & remaining;
             if (!have || k != acc_key) {
-                if (have) flush_acc(acc, acc_key, lane, A, lda, g, loss_cur);
+                if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur);
                 acc_key = k;
                 have = true;
             }
@@ -259,7 +260,7 @@ data_jtj_kernel(DataArgs a, double* __restrict__ A, int lda, double* __restrict_
         }
         __syncwarp();
     }
-    if (have) flush_acc(acc, acc_key, lane, A, lda, g, loss_cur);
+    if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur);
 }
 
 constexpr int LOSS_BLOCK = 256;
@@ -300,14 +301,32 @@ __global__ void data_rows_kernel(DataArgs a, unsigned char* __restrict__ matched
 
 // 64-bit sort keys of the J^T J visiting order: packed node 4-tuple; rows >= n sort last.
 __global__ void tuple_keys_kernel(const int* __restrict__ knn_idx, int n_cap, const int* n_dev,
-                                  long long* __restrict__ keys) {
+                                  long long* __restrict__ keys, const int* __restrict__ node_pos,
+                                  int* __restrict__ block_bw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cap) return;
-    const int n = n_active(n_cap, n_dev);
-    if (i >= n) { keys[i] = 0x7fffffffffffffffLL; return; }
-    const int4 id = *reinterpret_cast<const int4*>(knn_idx + 4 * (size_t)i);
-    const int idx[4] = {id.x, id.y, id.z, id.w};
-    keys[i] = (long long)(pack_key(idx) >> 1);   // keep it non-negative for a signed sort
+    int span = 0;
+    if (i < n_cap) {
+        const int n = n_active(n_cap, n_dev);
+        if (i >= n) {
+            keys[i] = 0x7fffffffffffffffLL;
+        } else {
+            const int4 id = *reinterpret_cast<const int4*>(knn_idx + 4 * (size_t)i);
+            const int idx[4] = {id.x, id.y, id.z, id.w};
+            keys[i] = (long long)(pack_key(idx) >> 1);   // keep it non-negative for a signed sort
+            if (block_bw) {
+                int lo = 1 << 30, hi = -1;
+                for (int k = 0; k < 4; ++k) {
+                    const int p = node_pos ? node_pos[idx[k]] : idx[k];
+                    lo = min(lo, p); hi = max(hi, p);
+                }
+                span = hi - lo;
+            }
+        }
+    }
+    if (block_bw) {   // block half-bandwidth the surfel tuples need in the solver's node order
+        span = __reduce_max_sync(0xffffffffu, span);
+        if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(block_bw, span);
+    }
 }
 
 DataArgs make_args(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
@@ -333,10 +352,12 @@ int sb_data_loss_blocks(int n_cap) {
     return b < 1 ? 1 : (b > 592 ? 592 : b);   // <= 4 CTAs per SM on 148 SMs
 }
 
-int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, void* stream) {
+int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, const int* node_pos,
+                  int* block_bw, void* stream) {
     if (!knn_idx || !keys) return SB_ERR_ARG;
     if (n_cap <= 0) return SB_OK;
-    tuple_keys_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(knn_idx, n_cap, n_dev, keys);
+    tuple_keys_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(knn_idx, n_cap, n_dev, keys, node_pos,
+                                                                           block_bw);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -344,9 +365,12 @@ int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* ke
 int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
                      const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
                      const float* nmap, int H, int W, const double* intr, double lambda, double* A, int lda,
-                     double* g, double* loss_cur, void* stream) {
+                     int bw, const int* node_pos, int* band_overflow, double* g, double* loss_cur, void* stream) {
     if (!points || !knn_idx || !knn_w || !ed_points || !beta || !vmap || !nmap || !A || !g) return SB_ERR_ARG;
-    if (J <= 0 || J > 65535 || lda < 7 * J) return SB_ERR_ARG;
+    if (J <= 0 || J > 65535) return SB_ERR_ARG;
+    if (bw < 0 ? lda < 7 * J : (lda < bw + 1 || !band_overflow)) return SB_ERR_ARG;
+    MatView M;
+    M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow;
     if (n_cap <= 0) return SB_OK;
     DataArgs a = make_args(points, knn_idx, knn_w, order, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
                            intr, lambda);
@@ -364,7 +388,7 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, A, lda, g, loss_cur);
+    data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, g, loss_cur);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

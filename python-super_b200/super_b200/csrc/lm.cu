@@ -21,9 +21,9 @@ struct LMState {
     double u_trace[64];
 };
 
-__device__ __forceinline__ void add_lower(double* A, int lda, int r, int c, double v) {
-    if (r >= c) atomicAdd(A + (size_t)r * lda + c, v);
-    else atomicAdd(A + (size_t)c * lda + r, v);
+__device__ __forceinline__ void add_lower(const MatView& M, int r, int c, double v) {
+    if (r >= c) M.add(r, c, v);
+    else M.add(c, r, v);
 }
 
 // d[R(q)v]/dq as 3x4 (col 0 = d/dqw, cols 1..3 = d/dqv)   (/root/reference/super/utils.py:59-69)
@@ -43,8 +43,9 @@ __device__ __forceinline__ void quat_jac(const V3& v, double qw, const V3& qv, c
 // With A == nullptr only the loss partials are produced.
 __global__ void reg_terms_kernel(const double* __restrict__ ed_points, const int* __restrict__ ed_knn,
                                  const double* __restrict__ beta, int J, double lam_arap, double lam_rot,
-                                 int use_arap, int use_rot, double* __restrict__ A, int lda,
+                                 int use_arap, int use_rot, MatView M,
                                  double* __restrict__ g, double* __restrict__ loss_arap_rot /* [2] */) {
+    double* const A = M.A;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_arap = use_arap ? J * SB_KNN : 0;
     double la = 0.0, lr = 0.0;
@@ -67,26 +68,26 @@ __global__ void reg_terms_kernel(const double* __restrict__ ed_points, const int
             double Jq[3][4];
             quat_jac(d, bn[0], qv, cp, Jq);
             // residual row c: cols 7n+{0..3} = lam*Jq[c][.], 7n+4+c = lam, 7j+4+c = -lam   (loss.py:418-451)
-            const int bn0 = 7 * n, bj0 = 7 * j;
+            const int bn0 = 7 * M.pos(n), bj0 = 7 * M.pos(j);
             const double l = lam_arap, l2 = lam_arap * lam_arap;
             for (int a = 0; a < 4; ++a) {
                 for (int b = 0; b <= a; ++b) {
                     double s = 0.0;
                     for (int c = 0; c < 3; ++c) s += Jq[c][a] * Jq[c][b];
-                    atomicAdd(A + (size_t)(bn0 + a) * lda + bn0 + b, l2 * s);
+                    M.add(bn0 + a, bn0 + b, l2 * s);
                 }
                 double gq = 0.0;
                 for (int c = 0; c < 3; ++c) {
-                    add_lower(A, lda, bn0 + 4 + c, bn0 + a, l2 * Jq[c][a]);     // q_n x b_n
-                    add_lower(A, lda, bj0 + 4 + c, bn0 + a, -l2 * Jq[c][a]);    // q_n x b_j
+                    add_lower(M, bn0 + 4 + c, bn0 + a, l2 * Jq[c][a]);     // q_n x b_n
+                    add_lower(M, bj0 + 4 + c, bn0 + a, -l2 * Jq[c][a]);    // q_n x b_j
                     gq += l * Jq[c][a] * r[c];
                 }
                 atomicAdd(g + bn0 + a, -gq);
             }
             for (int c = 0; c < 3; ++c) {
-                atomicAdd(A + (size_t)(bn0 + 4 + c) * lda + bn0 + 4 + c, l2);
-                atomicAdd(A + (size_t)(bj0 + 4 + c) * lda + bj0 + 4 + c, l2);
-                add_lower(A, lda, bj0 + 4 + c, bn0 + 4 + c, -l2);
+                M.add(bn0 + 4 + c, bn0 + 4 + c, l2);
+                M.add(bj0 + 4 + c, bj0 + 4 + c, l2);
+                add_lower(M, bj0 + 4 + c, bn0 + 4 + c, -l2);
                 atomicAdd(g + bn0 + 4 + c, -l * r[c]);
                 atomicAdd(g + bj0 + 4 + c, l * r[c]);
             }
@@ -103,9 +104,10 @@ __global__ void reg_terms_kernel(const double* __restrict__ ed_points, const int
         if (A) {
             float jv[4];
             for (int a = 0; a < 4; ++a) jv[a] = -lam * 2.f * q[a];
+            const int pj = 7 * M.pos(j);
             for (int a = 0; a < 4; ++a) {
-                for (int b = 0; b <= a; ++b) atomicAdd(A + (size_t)(7 * j + a) * lda + 7 * j + b, (double)(jv[a] * jv[b]));
-                atomicAdd(g + 7 * j + a, -(double)(jv[a] * r));
+                for (int b = 0; b <= a; ++b) M.add(pj + a, pj + b, (double)(jv[a] * jv[b]));
+                atomicAdd(g + pj + a, -(double)(jv[a] * r));
             }
         }
     }
@@ -137,10 +139,12 @@ __global__ void lm_damp_kernel(const LMState* st, double* A, int lda, int n) {
 }
 
 // beta += delta unless the factorisation failed (info != 0  ->  the reference prints and breaks).
-__global__ void lm_step_kernel(LMState* st, const int* info, double* beta, const double* delta, int n) {
+// delta is in the solver's node order when node_pos is given.
+__global__ void lm_step_kernel(LMState* st, const int* info, double* beta, const double* delta, int n,
+                               const int* node_pos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool bad = st->failed || (info && *info != 0);
-    if (i < n && !bad) beta[i] += delta[i];
+    if (i < n && !bad) beta[i] += delta[node_pos ? 7 * node_pos[i / 7] + i % 7 : i];
     if (i == 0 && bad) st->failed = 1;
 }
 
@@ -209,14 +213,16 @@ int sb_lm_begin(void* state, double* beta, double* best, int J, double u, double
 }
 
 int sb_reg_terms(const double* ed_points, const int* ed_knn, const double* beta, int J, double lam_arap,
-                 double lam_rot, int use_arap, int use_rot, double* A, int lda, double* g, double* loss_arap_rot,
-                 void* stream) {
+                 double lam_rot, int use_arap, int use_rot, double* A, int lda, int bw, const int* node_pos,
+                 int* band_overflow, double* g, double* loss_arap_rot, void* stream) {
     if (!ed_points || !ed_knn || !beta || J <= 0) return SB_ERR_ARG;
-    if (A && (!g || lda < 7 * J)) return SB_ERR_ARG;
+    if (A && (!g || (bw < 0 ? lda < 7 * J : (lda < bw + 1 || !band_overflow)))) return SB_ERR_ARG;
+    MatView M;
+    M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow;
     const int threads = (use_arap ? J * SB_KNN : 0) + (use_rot ? J : 0);
     if (threads == 0) return SB_OK;
     reg_terms_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        ed_points, ed_knn, beta, J, lam_arap, lam_rot, use_arap, use_rot, A, lda, g, loss_arap_rot);
+        ed_points, ed_knn, beta, J, lam_arap, lam_rot, use_arap, use_rot, M, g, loss_arap_rot);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -228,9 +234,11 @@ int sb_lm_damp(const void* state, double* A, int lda, int n, void* stream) {
     return SB_OK;
 }
 
-int sb_lm_step(void* state, const int* info, double* beta, const double* delta, int n, void* stream) {
+int sb_lm_step(void* state, const int* info, double* beta, const double* delta, int n, const int* node_pos,
+               void* stream) {
     if (!state || !beta || !delta || n <= 0) return SB_ERR_ARG;
-    lm_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((LMState*)state, info, beta, delta, n);
+    lm_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((LMState*)state, info, beta, delta, n,
+                                                                    node_pos);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

@@ -30,10 +30,12 @@ class LMWorkspace:
 
 
 def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
-             on_iter=None):
+             on_iter=None, band=None, cluster_size=16):
     """sf: object with points (N,3) f64, knn_indices (N,4) i32, knn_w (N,4) f64 and ED (points, knn_indices i32).
     maps: (vmap, nmap) dense float4 images of the new frame.  Returns beta (J,7) f64 (a view of the
-    workspace) -- the same value LM_Solver.LM returns."""
+    workspace) -- the same value LM_Solver.LM returns.
+    band: ops.Band -> normal equations assembled straight into band storage and solved by sb_band_solve;
+    None -> dense A + the library Cholesky (torch.linalg / cuSOLVER), kept as the cross-check path."""
     ed = sf.ED
     J = ed.points.shape[0]
     dev = sf.points.device
@@ -50,20 +52,31 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
         order = ops.tuple_order(sf.knn_indices, n_dev)
     ops.lm_begin(ws.state, ws.beta, ws.best, u, v, minimal_loss)
     ws.loss2.zero_()
+    if band is not None:
+        band.info.zero_()
     for it in range(opt.num_optimize_iterations):
-        ws.A.zero_()
-        ws.g.zero_()
+        if band is not None:
+            band.store.zero_()                                             # AB and g in one memset
+        else:
+            ws.A.zero_()
+            ws.g.zero_()
         if use_data:
             ops.data_term_jtj(sf.points, sf.knn_indices, sf.knn_w, order, ed.points, ws.beta, vmap, nmap, cam,
-                              lam_d, ws.A, ws.g, n_dev=n_dev)
+                              lam_d, ws.A, ws.g, n_dev=n_dev, band=band)
         if use_arap or use_rot:
-            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g)
+            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g, band=band)
         if on_iter is not None:
             on_iter(it, "normal_equations", ws)
-        ops.lm_damp(ws.state, ws.A)
-        L, info = torch.linalg.cholesky_ex(ws.A, check_errors=False)      # reads the lower triangle
-        delta = torch.cholesky_solve(ws.g, L)
-        ops.lm_step(ws.state, info, ws.beta, delta)
+        if band is not None:
+            # own banded Cholesky on one thread-block cluster; damping u is read from the device state
+            ops.band_solve(band, ws.state.buf.data_ptr(), cluster_size)
+            delta = band.g
+            ops.lm_step(ws.state, band.info, ws.beta, delta, band.node_pos)
+        else:
+            ops.lm_damp(ws.state, ws.A)
+            L, info = torch.linalg.cholesky_ex(ws.A, check_errors=False)      # reads the lower triangle
+            delta = torch.cholesky_solve(ws.g, L)
+            ops.lm_step(ws.state, info, ws.beta, delta)
         if on_iter is not None:
             on_iter(it, "step", ws, delta)
         if use_data:

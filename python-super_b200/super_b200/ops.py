@@ -98,11 +98,49 @@ def data_term_rows(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam
     return matched.bool(), corners, r, jrow
 
 
+class Band:
+    """Band-storage target of the normal equations: AB (n, ldab) lower band row-major in the node order
+    `node_pos` (node id -> position), scalar half-bandwidth bw; `overflow` is raised by the assembly
+    kernels if an entry falls outside the band."""
+
+    def __init__(self, n, bw, node_pos, device):
+        self.n, self.bw = int(n), int(bw)
+        self.ldab = self.bw + 1
+        # AB and g share one allocation so that one memset clears both
+        self.store = torch.zeros(self.n * self.ldab + self.n, dtype=F64, device=device)
+        self.AB = self.store[: self.n * self.ldab].view(self.n, self.ldab)
+        self.g = self.store[self.n * self.ldab:]
+        self.node_pos = node_pos
+        self.overflow = torch.zeros(1, dtype=I32, device=device)
+        self.dinv = torch.zeros(self.n, dtype=F64, device=device)
+        self.info = torch.zeros(1, dtype=I32, device=device)
+
+    def to_dense(self):
+        """Symmetric dense matrix in the ORIGINAL node order (tests)."""
+        n, bw = self.n, self.bw
+        AB = self.AB.cpu()
+        A = torch.zeros((n, n), dtype=F64)
+        for d in range(bw + 1):                       # diagonal offset i - j = bw - d
+            off = bw - d
+            if off < n:
+                A.diagonal(-off).copy_(AB[off:, d])
+        A = A + torch.tril(A, -1).t()
+        if self.node_pos is not None:
+            pos = self.node_pos.cpu().long()
+            sidx = (7 * pos[:, None] + torch.arange(7)[None, :]).reshape(-1)   # original scalar -> permuted
+            A = A[sidx][:, sidx]
+        return A
+
+
 def data_term_jtj(points, knn_idx, knn_w, order, ed_points, beta, vmap, nmap, cam, lam, A, g, loss_cur=None,
-                  n_dev=None):
+                  n_dev=None, band=None):
+    if band is not None:
+        A, lda, bw, pos, ovf, g = band.AB, band.ldab, band.bw, band.node_pos, band.overflow, band.g
+    else:
+        lda, bw, pos, ovf = A.stride(0), -1, None, None
     call("sb_data_term_jtj", ptr(points), ptr(knn_idx), ptr(knn_w), ptr(order), points.shape[0], ptr(n_dev),
          ptr(ed_points), ptr(beta), ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam),
-         ptr(A), A.stride(0), ptr(g), ptr(loss_cur), stream())
+         ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss_cur), stream())
 
 
 def data_loss_blocks(n_cap):
@@ -115,19 +153,30 @@ def data_term_loss(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam
          partials.numel(), stream())
 
 
-def tuple_order(knn_idx, n_dev=None):
+def tuple_order(knn_idx, n_dev=None, node_pos=None, block_bw=None):
     """Surfel ids sorted by their (ordered) 4-tuple of ED nodes: the visiting order of the J^T J
-    kernel, so that a warp's 32 surfels share their node blocks.  Rows beyond *n_dev sort last."""
+    kernel, so that a warp's 32 surfels share their node blocks.  Rows beyond *n_dev sort last.
+    block_bw (1,) i32: atomically max-ed with the node-block half-bandwidth the tuples need."""
     n = knn_idx.shape[0]
     keys = torch.empty(n, dtype=torch.int64, device=knn_idx.device)
-    call("sb_tuple_keys", ptr(knn_idx), n, ptr(n_dev), ptr(keys), stream())
+    call("sb_tuple_keys", ptr(knn_idx), n, ptr(n_dev), ptr(keys), ptr(node_pos), ptr(block_bw), stream())
     return torch.sort(keys, stable=True)[1].to(I32)
 
 
 # ---- LM regularisers / controller ----------------------------------------------------------------
-def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=None, g=None, loss2=None):
+def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=None, g=None, loss2=None, band=None):
+    if band is not None:
+        A, lda, bw, pos, ovf, g = band.AB, band.ldab, band.bw, band.node_pos, band.overflow, band.g
+    else:
+        lda, bw, pos, ovf = (A.stride(0) if A is not None else 0), -1, None, None
     call("sb_reg_terms", ptr(ed_points), ptr(ed_knn), ptr(beta), ed_points.shape[0], float(lam_arap), float(lam_rot),
-         int(use_arap), int(use_rot), ptr(A), A.stride(0) if A is not None else 0, ptr(g), ptr(loss2), stream())
+         int(use_arap), int(use_rot), ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss2), stream())
+
+
+def band_solve(band, u_ptr=None, cluster_size=16):
+    """(A + u I) x = g in place: band.AB <- L, band.g <- x (solver node order).  u_ptr: device address of u."""
+    call("sb_band_solve", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
+         ptr(band.info), int(cluster_size), stream())
 
 
 class LMState:
@@ -169,8 +218,8 @@ def lm_damp(state, A):
     call("sb_lm_damp", ptr(state.buf), ptr(A), A.stride(0), A.shape[0], stream())
 
 
-def lm_step(state, info, beta, delta):
-    call("sb_lm_step", ptr(state.buf), ptr(info), ptr(beta), ptr(delta), beta.numel(), stream())
+def lm_step(state, info, beta, delta, node_pos=None):
+    call("sb_lm_step", ptr(state.buf), ptr(info), ptr(beta), ptr(delta), beta.numel(), ptr(node_pos), stream())
 
 
 def lm_decide(state, partials, loss2, beta, best):

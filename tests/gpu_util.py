@@ -65,5 +65,6 @@ def tracker_from_state(opt, sf, dev="cuda"):
     trk.n_bound = n
     trk.ED = to_device_state(sf).ED
     trk.ED.num = sf.ED.num
+    trk.ED.node_pos = None
     trk._publish_count()
     return trk

@@ -1,0 +1,113 @@
+"""GPU: the banded cluster Cholesky (sb_band_solve) and the band-assembled LM loop."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import super_oracle as so
+from golden_util import Golden
+from gpu_util import to_device_state, device_maps, camera
+
+pytestmark = pytest.mark.gpu
+G = Golden()
+
+
+def _random_band_system(n, bw, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.zeros((n, n), dtype=torch.float64)
+    for d in range(1, bw + 1):
+        A.diagonal(-d).copy_(torch.randn(n - d, generator=g, dtype=torch.float64))
+    A = A + A.t()
+    A.diagonal().copy_(A.abs().sum(1) + 1.0 + torch.rand(n, generator=g, dtype=torch.float64))   # SPD (diag dominant)
+    b = torch.randn(n, generator=g, dtype=torch.float64)
+    return A, b
+
+
+@pytest.mark.parametrize("n,bw,cluster", [(40, 5, 1), (97, 13, 2), (256, 40, 4), (1000, 150, 8), (1862, 300, 16),
+                                          (1862, 300, 8), (333, 332, 8), (64, 0, 4), (31, 6, 16)])
+def test_band_solve_matches_dense(n, bw, cluster):
+    from super_b200 import ops
+    A, b = _random_band_system(n, bw, seed=n + bw)
+    band = ops.Band(n, bw, None, "cuda")
+    AB = torch.zeros((n, bw + 1), dtype=torch.float64)
+    for d in range(bw + 1):
+        off = bw - d
+        if off < n:
+            AB[off:, d] = A.diagonal(-off)
+    band.AB.copy_(AB.cuda())
+    band.g.copy_(b.cuda())
+    u = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+    ops.band_solve(band, u.data_ptr(), cluster)
+    x = band.g.cpu()
+    x_ref = torch.linalg.solve(A + 0.5 * torch.eye(n, dtype=torch.float64), b)
+    assert int(band.info.item()) == 0
+    assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
+    # the factor itself
+    L_ref = torch.linalg.cholesky(A + 0.5 * torch.eye(n, dtype=torch.float64))
+    Lb = band.AB.cpu()
+    for d in (bw, max(bw - 1, 0), 0):
+        off = bw - d
+        if off < n:
+            assert (Lb[off:, d] - L_ref.diagonal(-off)).abs().max() < 1e-10
+
+
+def test_band_solve_flags_indefinite_matrix():
+    from super_b200 import ops
+    n, bw = 64, 4
+    band = ops.Band(n, bw, None, "cuda")
+    band.AB[:, bw] = -1.0
+    ops.band_solve(band, None, 4)
+    assert int(band.info.item()) == 1
+
+
+@pytest.mark.parametrize("t", G.frames[1:3])
+def test_band_assembly_equals_dense_assembly(t):
+    from super_b200 import ops, engine
+    sf, nd = G.state(t - 1), G.new_data(t)
+    J = sf.ED.num
+    d = to_device_state(sf)
+    vmap, nmap = device_maps(nd, G.H, G.W)
+    cam = camera(nd, G.H, G.W)
+    beta = torch.from_numpy(G[f"f{t}.lm.beta_try"][1].copy()).cuda()
+    A_ref, g_ref, _ = so.lm_normal_equations(G.opt, sf, nd, beta.cpu(), "blocks")
+    pos = torch.randperm(J, generator=torch.Generator().manual_seed(1)).to(torch.int32).cuda()
+    for node_pos, bwb in ((None, J - 1), (pos, J - 1)):
+        band = ops.Band(7 * J, 7 * bwb + 6, node_pos, "cuda")
+        order = ops.tuple_order(d.knn_indices)
+        ops.data_term_jtj(d.points, d.knn_indices, d.knn_w, order, d.ED.points, beta, vmap, nmap, cam, 1.0, None, None,
+                          band=band)
+        ops.reg_terms(d.ED.points, d.ED.knn_indices, beta, 10.0, 1.0, True, True, band=band)
+        assert int(band.overflow.item()) == 0
+        A = band.to_dense()
+        assert (A - A_ref).abs().max() < 1e-11 * A_ref.abs().max()
+        g = band.g.cpu()
+        if node_pos is not None:
+            p = node_pos.cpu().long()
+            sidx = (7 * p[:, None] + torch.arange(7)[None, :]).reshape(-1)
+            g = g[sidx]
+        assert (g - g_ref[:, 0]).abs().max() < 1e-12 * max(1.0, float(A_ref.abs().max()))
+    # too narrow a band must raise the overflow flag, not silently drop entries
+    band = ops.Band(7 * J, 6, None, "cuda")
+    ops.reg_terms(d.ED.points, d.ED.knn_indices, beta, 10.0, 1.0, True, True, band=band)
+    assert int(band.overflow.item()) == 1
+
+
+@pytest.mark.parametrize("t", G.frames[1:])
+def test_lm_with_band_solver_matches_reference(t):
+    from super_b200 import lm, ops
+    sf, nd = G.state(t - 1), G.new_data(t)
+    J = sf.ED.num
+    d = to_device_state(sf)
+    maps = device_maps(nd, G.H, G.W)
+    cam = camera(nd, G.H, G.W)
+    pos = torch.arange(J, dtype=torch.int32, device="cuda").flip(0).contiguous()      # any permutation works
+    bwb = torch.zeros(1, dtype=torch.int32, device="cuda")
+    order = ops.tuple_order(d.knn_indices, None, pos, bwb)
+    need = max(int(bwb.item()), int((pos.long()[:, None] - pos.long()[d.ED.knn_indices.long()]).abs().max()))
+    band = ops.Band(7 * J, 7 * need + 6, pos, "cuda")
+    beta, ws = lm.lm_solve(d, maps, cam, G.opt, order=order, band=band, cluster_size=8)
+    st = ws.state.read()
+    assert st["failed"] == 0 and int(band.overflow.item()) == 0
+    ref_loss = G[f"f{t}.lm.loss"]
+    rel = np.abs(st["loss"] - ref_loss) / ref_loss
+    assert rel.max() < 1e-8, f"per-iteration loss rel err {rel}"
+    assert np.abs(beta.cpu().numpy() - G[f"f{t}.beta"]).max() < 1e-9
