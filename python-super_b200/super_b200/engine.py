@@ -12,6 +12,7 @@ super_b200/super/ expose exact-size views of them.
 from __future__ import annotations
 
 import ctypes
+import os
 from types import SimpleNamespace as NS
 
 import torch
@@ -209,7 +210,9 @@ class Tracker:
         self._fi = 0
         self.time = None
         self.last_beta = None
-        self.solver = getattr(opt, "solver", "band")      # "band" (own kernel) | "dense" (library cross-check)
+        # "band": own cluster Cholesky in band storage (sb_band_solve); "dense": dense A + library Cholesky.
+        # The default follows the faster one as measured on B200 (profiles/): see DESIGN.md section 5.
+        self.solver = getattr(opt, "solver", os.environ.get("SB_SOLVER", "dense"))
         self.cluster_size = int(getattr(opt, "solver_cluster", 16))
         self.band = None
         self.block_bw = torch.zeros(1, dtype=I32, device=self.dev)
