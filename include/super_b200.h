@@ -150,6 +150,15 @@ int sb_lm_step(void* state, const int* info, double* beta, const double* delta, 
  * /root/reference/super/LM.py:38-51,97-100.  AB (n, ldab) lower band row-major (overwritten by L), g (n) rhs in /
  * solution out, u device scalar (NULL = 0), dinv (n) scratch, *info set to 1 on a non-positive pivot.
  * One launch on one thread-block cluster of `cluster_size` CTAs (1,2,4,8 or 16). */
+/* v2: same contract, pipelined (one CTA runs the pivot chain, one the forward substitution, the others the
+ * panel rows and trailing updates, synchronised by release/acquire flags).  The factor L is written OUT OF PLACE
+ * into the workspace (AB keeps the updated, unfactored tiles); workspace >= sb_band2_workspace_bytes2(n, ldab);
+ * cluster_size 3..16. */
+long long sb_band2_workspace_bytes2(int n, int ldab);
+int sb_band_solve2(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                   void* workspace, long long ws_bytes, int cluster_size, void* stream);
+int sb_band2_debug(int flags);
+int sb_band2_fits(int n, int bw);
 int sb_band_max_bw(void);
 int sb_band_debug(int flags); /* timing experiments only: 1 skip trailing update, 2 skip back-substitution, 4 skip panel math */
 int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,

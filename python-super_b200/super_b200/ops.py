@@ -173,10 +173,21 @@ def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=N
          int(use_arap), int(use_rot), ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss2), stream())
 
 
-def band_solve(band, u_ptr=None, cluster_size=16):
-    """(A + u I) x = g in place: band.AB <- L, band.g <- x (solver node order).  u_ptr: device address of u."""
-    call("sb_band_solve", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
-         ptr(band.info), int(cluster_size), stream())
+def band_solve(band, u_ptr=None, cluster_size=16, variant=None):
+    """(A + u I) x = g in place: band.AB <- L, band.g <- x (solver node order).  u_ptr: device address of u.
+    variant 2 (default): pipelined kernel sb_band_solve2; variant 1: barrier-per-panel kernel sb_band_solve."""
+    import os
+    if variant is None:
+        variant = int(os.environ.get("SB_BAND_VARIANT", "2"))
+    if variant == 2 and cluster_size >= 3 and lib.load().sb_band2_fits(band.n, band.bw):
+        if getattr(band, "ws2", None) is None:
+            band.ws2 = torch.zeros(int(lib.load().sb_band2_workspace_bytes2(band.n, band.ldab)), dtype=torch.uint8,
+                                   device=band.AB.device)
+        call("sb_band_solve2", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
+             ptr(band.info), ptr(band.ws2), band.ws2.numel(), int(cluster_size), stream())
+    else:
+        call("sb_band_solve", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
+             ptr(band.info), int(cluster_size), stream())
 
 
 class LMState:

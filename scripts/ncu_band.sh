@@ -15,5 +15,5 @@ for _ in range(3):
     band.AB.copy_(ABd); band.g.copy_(rd); ops.band_solve(band, None, 16)
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:band_chol_kernel -s 2 -c 1 -f -o gpurun_out/prof_band python /tmp/one_band.py > gpurun_out/ncu_band.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:band_chol2_kernel -s 2 -c 1 -f -o gpurun_out/prof_band python /tmp/one_band.py > gpurun_out/ncu_band.log 2>&1
 tail -3 gpurun_out/ncu_band.log
