@@ -159,6 +159,16 @@ int sb_band_solve2(double* AB, int ldab, int n, int bw, double* g, const double*
                    void* workspace, long long ws_bytes, int cluster_size, void* stream);
 int sb_band2_debug(int flags);
 int sb_band2_fits(int n, int bw);
+/* v3: same contract as v2 (pivot-chain CTA + substitution CTA + update CTAs, release/acquire counters), with every
+ * 32x32 triangular solve replaced by an FP64 tensor-core product with the explicit inverse of the diagonal factor
+ * and a push-style back substitution.  AB keeps the updated, unfactored tiles; L and the inverses live in the
+ * workspace (>= sb_band3_workspace_bytes(n, bw)); n_ctas >= 3 CTAs of one cooperative grid (clamped to the SM count). */
+long long sb_band3_workspace_bytes(int n, int bw);
+int sb_band3_fits(int n, int bw);
+int sb_band3_debug(int flags); /* timing experiments only: 1 no trailing update, 2 no back substitution, 4 cycle counters */
+long long sb_band3_prof_offset(int n, int bw);
+int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                   void* workspace, long long ws_bytes, int n_ctas, void* stream);
 int sb_band_max_bw(void);
 int sb_band_debug(int flags); /* timing experiments only: 1 skip trailing update, 2 skip back-substitution, 4 skip panel math */
 int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,

@@ -1,0 +1,928 @@
+// Banded Cholesky solve v3 of (A + u I) x = g -- the LM step solve, replacing
+// torch.linalg.cholesky + cholesky_solve   /root/reference/super/LM.py:38-51,97-100.
+//
+// What v2 (band_chol2.cu) measured on B200 (profiles/r1b_band_probe.md): the pivot-chain CTA alone needs
+// 11 k cycles per 32-column panel (one-warp triangular solve 2.8 k, scalar syrk 1.7 k, one-warp Cholesky
+// 6.2 k), the update CTAs need 19 k (two redundant one-warp triangular solves per tile) and the
+// back substitution 192 us.  v3 keeps the role split (the factorisation is a chain of n pivots, everything
+// else has slack) and removes those costs:
+//
+//   * every 32x32 triangular solve is a tensor-core product with the explicit inverse of the diagonal
+//     factor: while warp 0 of the pivot CTA factors block k column by column, warp 1 builds L(k,k)^-1 row by
+//     row behind it (the columns travel through a NaN-initialised shared buffer: a value is its own
+//     "ready" flag).  P publishes only L(k,k)^-1; nobody needs L(k,k).
+//   * P: L(k,k-1) = A(k,k-1) Linv^T and D -= L L^T are FP64 DMMA products on four warps; three I/O warps
+//     publish flags, store L(k,k-1) and stage the next panel's tiles behind the Cholesky.
+//   * U: one tile per CTA and panel, three DMMA products (two "triangular solves", one update).
+//   * R: forward substitution y_p = Linv s_p behind P, then -- on the same CTA, no grid barrier -- a
+//     push-style back substitution x_k = Linv^T s_k, s_j -= L(k,j)^T x_k with register-prefetched tiles.
+//
+// Synchronisation: release/acquire counters in global memory (diag_done | rows_done | upd_done per panel),
+// zeroed by a memset node in front of the launch.  The grid is launched cooperatively only for the
+// co-residency guarantee (spinning CTAs); there is no grid-wide barrier.  Every spin is bounded and traps.
+#include "common.cuh"
+#include "super_b200.h"
+
+namespace {
+
+constexpr int NB = 32;
+constexpr int S36 = 36;             // stride of DMMA operand tiles (conflict-free fragment loads)
+constexpr int S33 = 33;             // stride of row-per-lane tiles
+constexpr int T36 = NB * S36, T33 = NB * S33, T32 = NB * NB;
+constexpr int THREADS = 256;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_WB3 = 28;
+
+struct Args3 {
+    double* AB; int ldab, n, bw;
+    double* g; const double* u; double* dinv; int* info;
+    double* LB;      // L tiles below the diagonal, tile (I, d = I-J in 1..WB) at ((I*WB + d-1) * 1024), row-major 32x32
+    double* LI;      // L(k,k)^-1, tile k at k*1024, row-major
+    int* flags;      // diag_done[NP] | rows_done[NP] | upd_done[NP]
+    int NP, WB;
+    long long* prof;   // 32 counters (debug & 4)
+    int debug;         // 1: U skips its tile work, 2: no back substitution, 4: cycle counters
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// one thread spins until *flag >= target; bounded (a lost signal must not hang the GPU)
+__device__ __forceinline__ void spin_until(const int* flag, int target) {
+    long long it = 0;
+    while (ld_acquire(flag) < target) {
+        __nanosleep(32);
+        if (++it > (1LL << 24)) __trap();
+    }
+}
+// whole CTA waits (thread 0 polls)
+__device__ __forceinline__ void cta_wait(const int* flag, int target) {
+    if (threadIdx.x == 0) spin_until(flag, target);
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool in_band(const Args3& a, int i, int j) { return i < a.n && j <= i && i - j <= a.bw; }
+__device__ __forceinline__ double* ab_at(const Args3& a, int i, int j) {
+    return a.AB + (size_t)i * a.ldab + (j - i + a.bw);
+}
+__device__ __forceinline__ double* lb_tile(const Args3& a, int I, int d) {
+    return a.LB + ((size_t)I * a.WB + (d - 1)) * T32;
+}
+
+// tile (I,J) of the band matrix -> shared (row-major, given stride), executed by threads t of nt; outside = 0
+__device__ __forceinline__ void load_ab_tile(const Args3& a, int I, int J, double* __restrict__ T, int stride, int t,
+                                             int nt) {
+    for (int base = 0; base < T32; base += 4 * nt) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = base + q * nt + t, i = NB * I + (e >> 5), j = NB * J + (e & 31);
+            v[q] = (e < T32 && in_band(a, i, j)) ? __ldcg(ab_at(a, i, j)) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = base + q * nt + t;
+            if (e < T32) T[(e >> 5) * stride + (e & 31)] = v[q];
+        }
+    }
+}
+// two band tiles at once with EVERY load in flight before the first shared store (one L2 round trip instead of one
+// per batch of four: the batched loader cost 5 k cycles per panel on the 96 I/O threads of the pivot CTA)
+template <int NT>
+__device__ __forceinline__ void load_ab_tiles2(const Args3& a, int I0, int J0, double* __restrict__ T0, int s0,
+                                               int I1, int J1, double* __restrict__ T1, int s1, int t) {
+    static_assert(NT % 32 == 0, "whole warps");
+    constexpr int RSTEP = NT / 32, PER = (NB + RSTEP - 1) / RSTEP;
+    // thread -> fixed column c, rows r0, r0+RSTEP, ...: one pointer per tile, advanced by RSTEP*(ldab-1) per load
+    const int c = t & 31, r0 = t >> 5;
+    const long long step = (long long)RSTEP * (a.ldab - 1);
+    const bool has1 = I1 >= 0;
+    const double* p0 = a.AB + (size_t)(NB * I0 + r0) * a.ldab + (NB * J0 + c - NB * I0 - r0 + a.bw);
+    const double* p1 = has1 ? a.AB + (size_t)(NB * I1 + r0) * a.ldab + (NB * J1 + c - NB * I1 - r0 + a.bw) : p0;
+    const int d0 = NB * (I0 - J0) + r0 - c, d1 = NB * (I1 - J1) + r0 - c;     // i - j at q = 0, +RSTEP per q
+    const int i0 = NB * I0 + r0, i1 = NB * I1 + r0;
+    double v0[PER], v1[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int dr = q * RSTEP;
+        const bool ok0 = (r0 + dr < NB) && (i0 + dr < a.n) && (d0 + dr >= 0) && (d0 + dr <= a.bw);
+        const bool ok1 = has1 && (r0 + dr < NB) && (i1 + dr < a.n) && (d1 + dr >= 0) && (d1 + dr <= a.bw);
+        v0[q] = ok0 ? __ldcg(p0 + q * step) : 0.0;
+        v1[q] = ok1 ? __ldcg(p1 + q * step) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int r = r0 + q * RSTEP;
+        if (r < NB) {
+            T0[r * s0 + c] = v0[q];
+            if (has1) T1[r * s1 + c] = v1[q];
+        }
+    }
+}
+// contiguous row-major 32x32 global tile -> shared with stride
+__device__ __forceinline__ void load_g_tile(const double* __restrict__ G, double* __restrict__ T, int stride, int t,
+                                            int nt) {
+    for (int base = 0; base < T32; base += 4 * nt) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = base + q * nt + t;
+            v[q] = (e < T32) ? __ldcg(G + e) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = base + q * nt + t;
+            if (e < T32) T[(e >> 5) * stride + (e & 31)] = v[q];
+        }
+    }
+}
+__device__ __forceinline__ void store_g_tile(double* __restrict__ G, const double* __restrict__ T, int stride, int t,
+                                             int nt) {
+    for (int e = t; e < T32; e += nt) __stcg(G + e, T[(e >> 5) * stride + (e & 31)]);
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a_, double b_) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a_), "d"(b_));
+}
+
+// Dst[8*bi .. +8, 8*bj .. +8] = Src[8*bi.., :] * Linv[8*bj.., :]^T for the block columns bj in `mask`;
+// Linv is lower triangular, so only k < 8*bj+8 contributes (2*bj+2 k-steps of 4).  All tiles stride S36.
+__device__ __forceinline__ void trsm_strip(const double* __restrict__ Src, const double* __restrict__ Linv,
+                                           double* __restrict__ Dst, int bi, unsigned mask, int lane) {
+    const int fr = lane >> 2, fc = lane & 3;
+    double af[8], c[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) af[ks] = Src[(8 * bi + fr) * S36 + 4 * ks + fc];
+#pragma unroll
+    for (int bj = 0; bj < 4; ++bj) c[bj][0] = c[bj][1] = 0.0;
+    // k-steps outermost: the (up to) four accumulator chains are independent and overlap in the DMMA pipe
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj)
+            if (((mask >> bj) & 1u) && ks < 2 * bj + 2)
+                dmma884(c[bj][0], c[bj][1], af[ks], Linv[(8 * bj + fr) * S36 + 4 * ks + fc]);
+#pragma unroll
+    for (int bj = 0; bj < 4; ++bj)
+        if ((mask >> bj) & 1u)
+            *reinterpret_cast<double2*>(Dst + (8 * bi + fr) * S36 + 8 * bj + 2 * fc) = make_double2(c[bj][0], c[bj][1]);
+}
+// acc = sum_k Pa[8*bi.., k] * Pb[8*bj.., k]   (full 32-deep product of two stride-S36 tiles)
+__device__ __forceinline__ void mma_block(const double* __restrict__ Pa, const double* __restrict__ Pb, int bi, int bj,
+                                          int lane, double& c0, double& c1) {
+    const int fr = lane >> 2, fc = lane & 3;
+    c0 = 0.0; c1 = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        dmma884(c0, c1, Pa[(8 * bi + fr) * S36 + 4 * ks + fc], Pb[(8 * bj + fr) * S36 + 4 * ks + fc]);
+}
+
+// reciprocal square root for the pivot chain: float seed + one Newton step in double (rel. error ~1e-14)
+__device__ __forceinline__ double rsqrt_chain(double x) {
+    const double r = (double)rsqrtf((float)x);
+    const double e = fma(-x * r, r, 1.0);
+    return fma(0.5 * r, e, r);
+}
+
+// the six lower 8x8 blocks right of the first block column: (1,1) (2,1) (3,1) (2,2) (3,2) (3,3)
+__host__ __device__ constexpr int pair_i(int q) { return q == 0 ? 1 : q == 1 ? 2 : q == 2 ? 3 : q == 3 ? 2 : 3; }
+__host__ __device__ constexpr int pair_j(int q) { return q < 3 ? 1 : q < 5 ? 2 : 3; }
+
+// reciprocal square root for the pivot chain: MUFU.RSQ64H seed (rel. error 9e-7 measured) + one Halley step
+//   e = 1 - x r0^2,  r = r0 + r0 e (1/2 + 3/8 e)      (cubic: rel. error ~1e-16; 4 dependent FP64 ops + MUFU = 53
+// cycles measured, against 63 for float seed + Newton at 3e-14)
+__device__ __forceinline__ double rsqrt_pivot(double x) {
+    double r0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = fma(-x * r0, r0, 1.0);
+    const double t = fma(0.375, e, 0.5);
+    return fma(r0 * e, t, r0);
+}
+
+// ---- 32x32 Cholesky in one warp, blocked by 8 columns.  D (shared, stride S33) holds the block.
+// The pivot chain must not contain a shuffle or a shared-memory round trip (26 and 34 cycles measured, against 8.4
+// for a dependent DFMA): every lane keeps a REPLICA of the current 8x8 diagonal block (36 registers) and factors it
+// redundantly, so rsqrt -> scale -> own-pivot FMA stays inside one thread (about 70 cycles per column).  Lane r also
+// carries the 8 entries of its own row r and solves them against the replica as the columns appear.  Column C of L
+// goes to Lcol[C*S36 + row] and 1/L(C,C) to dinvs[C] immediately (the inverse builder reads them behind us); the
+// trailing columns are updated in shared memory by DMMA products (next block column first).
+// Small code on purpose: fully unrolled 32-column versions of this and of the inverse are ~100 KB of SASS.
+__device__ __forceinline__ bool warp_potrf_blocked(double* __restrict__ D, double* __restrict__ Lcol,
+                                                   double* __restrict__ dinvs, double* __restrict__ Ls, int lane,
+                                                   long long* ts = nullptr, long long tbase = 0) {
+    const int fr = lane >> 2, fc = lane & 3, jc = lane & 7;
+    bool bad = false;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 8 * b;
+        double d[8][8], p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) d[i][j] = D[(c0 + i) * S33 + c0 + j];      // broadcast loads
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = D[lane * S33 + c0 + j];
+        double x[8];                                                                 // column jc of T_b = L_bb^-1
+        long long q0 = 0, q1;
+        if (ts) { if (p[7] + d[7][7] != 1.2345e300) q0 = clock64(); ts[4] += q0 - tbase; tbase = q0; }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double piv = d[c][c];
+            // row c of the inverse only needs row c of L (final since step c-1): everything but the last
+            // multiply is off the pivot chain and fills its idle issue slots
+            double s0 = (jc == c) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < c; ++t) {
+                if (t & 1) s1 = fma(-d[c][t], x[t], s1); else s0 = fma(-d[c][t], x[t], s0);
+            }
+            const double inv = rsqrt_pivot(piv);
+            x[c] = (s0 + s1) * inv;
+            bad = bad || !(piv > 0.0);
+#pragma unroll
+            for (int i = c + 1; i < 8; ++i) d[i][c] *= inv;                          // l_ic of the replica
+#pragma unroll
+            for (int j = c + 1; j < 8; ++j)
+#pragma unroll
+                for (int i = j; i < 8; ++i) d[i][j] = fma(-d[i][c], d[j][c], d[i][j]);
+            p[c] *= inv;                                                             // l_rc of my own row
+#pragma unroll
+            for (int j = c + 1; j < 8; ++j) p[j] = fma(-p[c], d[j][c], p[j]);
+            Lcol[(c0 + c) * S36 + lane] = p[c];
+            if (lane == c) dinvs[c0 + c] = inv;
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Ls[(c0 + i) * S36 + c0 + lane] = bad ? 0.0 : x[i];   // (7,7) last: the block's ready flag
+        }
+        __syncwarp();
+        if (ts) { if (x[7] + p[7] != 1.2345e300) q1 = clock64(); ts[5] += q1 - tbase; tbase = q1; }
+        if (b < 3) {
+            // D[i][j] -= sum_{t in block b} L[i][t] L[j][t] for every lower 8x8 block right of b, all at once: the
+            // (up to six) accumulator chains are independent, so the whole update costs one LDS -> 2 DMMA -> RMW
+            // round instead of one per block column
+            double af[3][2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) af[r][ks] = (r + 1 > b) ? Lcol[(c0 + 4 * ks + fc) * S36 + 8 * (r + 1) + fr] : 0.0;
+            double acc[6][2];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int q = 0; q < 6; ++q)
+                    if (pair_j(q) > b) dmma884(acc[q][0], acc[q][1], af[pair_i(q) - 1][ks], af[pair_j(q) - 1][ks]);
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                if (pair_j(q) > b) {
+                    double* dd = D + (8 * pair_i(q) + fr) * S33 + 8 * pair_j(q) + 2 * fc;
+                    dd[0] -= acc[q][0];
+                    dd[1] -= acc[q][1];
+                }
+            __syncwarp();
+        }
+        if (ts) { q1 = clock64(); ts[6] += q1 - tbase; tbase = q1; }
+    }
+    return bad;
+}
+
+// ---- L^-1 behind the Cholesky, blocked by 8, on two warps.  With 8x8 blocks L_ik, T_b = L_bb^-1:
+//        M_bb = T_b,     M_bj = -T_b * S_bj,   S_bj = sum_{k=j}^{b-1} L_bk M_kj     (j < b)
+// Warp "T" (warp_tinv_trailing) inverts the diagonal blocks row by row right behind the pivot chain; warp "M"
+// (warp_linv_blocked) forms S_bj while the chain is still on block b (it only needs block columns < b), then
+// M_bj and publishes block row b.  After the last pivot only T_3 's last row, three 8x8 products and one store
+// remain.  Hand-over is by value: L[i][t] = Lcol[t*S36+i], 1/L[i][i] = dinvs[i] and the diagonal blocks of the
+// inverse tile are NaN until written (a value is its own ready flag; a NaN in any result re-reads).
+__device__ __forceinline__ void warp_tinv_trailing(const volatile double* Lcol, const volatile double* dinvs,
+                                                   double* Ls, int lane, bool& failed, long long* ts = nullptr,
+                                                   long long tbase = 0) {
+    const int jc = lane & 7;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 8 * b;
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = 0.0;
+            if (!failed) {
+                int tries = 0;
+                while (true) {
+                    double d = dinvs[c0 + i];
+                    int spins = 0;
+                    while (d != d && ++spins < (1 << 18)) d = dinvs[c0 + i];
+                    double s0 = (jc == i) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < i; ++t) {
+                        const double l = Lcol[(c0 + t) * S36 + c0 + i];
+                        if (t & 1) s1 = fma(-l, x[t], s1); else s0 = fma(-l, x[t], s0);
+                    }
+                    v = (s0 + s1) * d;
+                    if (!__any_sync(FULL, v != v)) break;
+                    if (++tries > 4) { failed = true; v = 0.0; break; }   // NaN input / indefinite block: give up
+                }
+            }
+            x[i] = v;
+            if (lane < 8) Ls[(c0 + i) * S36 + c0 + lane] = v;          // row 7 last: (7,7) is the block's ready flag
+        }
+        if (ts) ts[b] += clock64() - tbase;
+    }
+}
+
+// Ls: shared inverse tile (stride S36; diagonal blocks NaN-armed, rest zero), Lg: global tile, Sc: 3 x 96 scratch.
+__device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const volatile double* dinvs, double* Ls,
+                                                  double* __restrict__ Lg, double* __restrict__ Sc, int lane,
+                                                  bool& failed, long long* wacc = nullptr, long long* ts = nullptr,
+                                                  long long tbase = 0) {
+    const int fr = lane >> 2, fc = lane & 3;
+    constexpr int SS = 12;
+    long long w0 = wacc ? clock64() : 0, w1;
+#define WPROF(slot) do { if (wacc) { w1 = clock64(); wacc[slot] += w1 - w0; w0 = w1; } } while (0)
+    auto wait_value = [&](const volatile double* p) {
+        if (failed) return;
+        int spins = 0;
+        double dq = *p;
+        while (dq != dq && ++spins < (1 << 18)) dq = *p;
+        if (dq != dq) failed = true;
+        asm volatile("" ::: "memory");       // the plain loads below stay behind the flag
+    };
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 8 * b;
+        if (b >= 1) {
+            wait_value(dinvs + c0 - 1);      // block columns < b are complete
+            WPROF(0);
+            for (int tries = 0; tries < 4; ++tries) {
+                double sacc[3][2];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) sacc[j][0] = sacc[j][1] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k >= b) break;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const int kk = 8 * k + 4 * ks + fc;
+                        const double lf = ((const volatile double*)Lcol)[kk * S36 + c0 + fr];
+#pragma unroll
+                        for (int j = 0; j <= k; ++j)
+                            dmma884(sacc[j][0], sacc[j][1], lf, ((const volatile double*)Ls)[kk * S36 + 8 * j + fr]);
+                    }
+                }
+                bool nan_seen = false;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < b) {
+                        Sc[j * 8 * SS + fr * SS + 2 * fc] = sacc[j][0];
+                        Sc[j * 8 * SS + fr * SS + 2 * fc + 1] = sacc[j][1];
+                        nan_seen = nan_seen || (sacc[j][0] != sacc[j][0]) || (sacc[j][1] != sacc[j][1]);
+                    }
+                if (failed || !__any_sync(FULL, nan_seen)) break;
+                if (tries == 3) failed = true;
+            }
+            __syncwarp();
+            WPROF(1);
+        }
+        wait_value(Ls + (c0 + 7) * S36 + c0 + 7);      // T_b is complete (warp "T")
+        WPROF(2);
+        if (b >= 1) {
+            // M_bj = -T_b S_bj, the three products interleaved
+            for (int tries = 0; tries < 4; ++tries) {
+                double m[3][2];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) m[j][0] = m[j][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const double tf = ((const volatile double*)Ls)[(c0 + fr) * S36 + c0 + 4 * ks + fc];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (j < b) dmma884(m[j][0], m[j][1], tf, Sc[j * 8 * SS + (4 * ks + fc) * SS + fr]);
+                }
+                bool nan_seen = false;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < b) {
+                        Ls[(c0 + fr) * S36 + 8 * j + 2 * fc] = -m[j][0];
+                        Ls[(c0 + fr) * S36 + 8 * j + 2 * fc + 1] = -m[j][1];
+                        nan_seen = nan_seen || (m[j][0] != m[j][0]) || (m[j][1] != m[j][1]);
+                    }
+                if (failed || !__any_sync(FULL, nan_seen)) break;
+                if (tries == 3) failed = true;
+            }
+            __syncwarp();
+            WPROF(3);
+        }
+        // block row b of the inverse is final: publish it
+        {
+            double r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = ((const volatile double*)Ls)[(c0 + i) * S36 + lane];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) __stcg(Lg + (c0 + i) * NB + lane, (r[i] == r[i]) ? r[i] : 0.0);
+        }
+        WPROF(4);
+        if (ts) ts[b] += clock64() - tbase;
+    }
+#undef WPROF
+}
+
+// =====================================================================================================
+// P: the pivot chain.  Warp roles: 0 Cholesky (+DMMA), 1 inverse builder, {0,2,3,5} DMMA products,
+// {4,6,7} I/O (flags, L(k,k-1) store, staging of the next panel's tiles).
+// =====================================================================================================
+__device__ void role_P(const Args3& a, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, NP = a.NP, WB = a.WB;
+    int* diag_done = a.flags;
+    int* rows_done = a.flags + NP;
+    int* upd_done = a.flags + 2 * NP;
+    const int NU = (int)gridDim.x - 2;
+    const double u = a.u ? *a.u : 0.0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    double* Dbuf = smem;                   // 2 x T33
+    double* Xbuf = Dbuf + 2 * T33;         // 2 x T36
+    double* Lxbuf = Xbuf + 2 * T36;        // 2 x T36
+    double* Linv = Lxbuf + 2 * T36;        // 2 x T36
+    double* Lcol = Linv + 2 * T36;         // 2 x T36 (column-major L: Lcol[c*S36 + r])
+    double* dinvs = Lcol + 2 * T36;        // 2 x NB
+    double* Sc = dinvs + 2 * NB;           // 3 x 96 scratch of the inverse builder
+
+    const int cw = (warp == 0) ? 0 : (warp == 2) ? 1 : (warp == 3) ? 2 : (warp == 5) ? 3 : -1;   // compute rank
+    const int iw = (warp == 4) ? 0 : (warp == 6) ? 1 : (warp == 7) ? 2 : -1;                     // I/O rank
+    const int it = iw * 32 + lane;                                                               // I/O thread id (0..95)
+
+    load_ab_tile(a, 0, 0, Dbuf, S33, tid, THREADS);
+    for (int e = tid; e < T36; e += THREADS) Lcol[e] = qnan;
+    if (tid < NB) dinvs[tid] = qnan;
+    for (int e = tid; e < T36; e += THREADS) Xbuf[e] = 0.0;
+
+    bool linv_failed = false, tinv_failed = false;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long ioacc[6] = {0, 0, 0, 0, 0, 0};
+    long long w1acc = 0;
+    long long wacc[5] = {0, 0, 0, 0, 0};
+    long long tsacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t0 = clock64(), t1;
+    const bool prof = (a.debug & 4) != 0;
+    // BAR.SYNC is issued "defer blocking": a clock read right behind it executes before the barrier completes.
+    // The volatile shared load below cannot, and the clock read is made control-dependent on its value.
+#define PROF(slot) do { if (prof) { if (*(volatile double*)dinvs != 1.2345e300) t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; } } while (0)
+    if (prof && tid == 0) { a.prof[8] = clock64(); for (int q = 16; q < 24; ++q) a.prof[q] = 0; }
+    for (int k = 0; k < NP; ++k) {
+        double* D = Dbuf + (k & 1) * T33;
+        double* X = Xbuf + (k & 1) * T36;
+        double* Lx = Lxbuf + (k & 1) * T36;
+        const double* Lp = Linv + ((k + 1) & 1) * T36;     // L(k-1,k-1)^-1
+        double* Lc = Lcol + (k & 1) * T36;
+        double* dv = dinvs + (k & 1) * NB;
+        PROF(0);
+        __syncthreads();                                   // staged tiles + previous inverse are in shared memory
+        PROF(1);
+        const long long tA = t0;
+        if (cw >= 0) {
+            // ---- L(k,k-1) = A(k,k-1) L(k-1,k-1)^-T, then D = A(k,k) - L(k,k-1) L(k,k-1)^T (+ u on the diagonal) ----
+            if (cw == 3) {   // warp "T": NaN-arm the diagonal blocks of this panel's inverse tile
+                double* Ls = Linv + (k & 1) * T36;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int e = q * 32 + lane, bb = e >> 6, r = (e >> 3) & 7, c = e & 7;
+                    Ls[(8 * bb + r) * S36 + 8 * bb + c] = qnan;
+                }
+            }
+            if (k >= 1) trsm_strip(X, Lp, Lx, cw, 0xfu, lane);
+            bar_sync(2, 128);
+            bar_arrive(1, 224);                            // I/O warps may store L(k,k-1)
+            PROF(2);
+            {
+                // lower 8x8 blocks dealt 3,3,2,2; the accumulator chains of a warp's blocks are interleaved
+                const int nblk = (cw < 2) ? 3 : 2;
+                const int bis[4][3] = {{0, 2, 3}, {1, 2, 3}, {1, 3, 0}, {2, 3, 0}};
+                const int bjs[4][3] = {{0, 1, 2}, {0, 2, 3}, {1, 0, 0}, {0, 1, 0}};
+                const int fr = lane >> 2, fc = lane & 3;
+                int bi[3], bj[3];
+                double acc[3][2];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    bi[b] = bj[b] = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c == cw) { bi[b] = bis[c][b]; bj[b] = bjs[c][b]; }
+                    acc[b][0] = acc[b][1] = 0.0;
+                }
+                if (k >= 1) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b)
+                            if (b < nblk)
+                                dmma884(acc[b][0], acc[b][1], Lx[(8 * bi[b] + fr) * S36 + 4 * ks + fc],
+                                        Lx[(8 * bj[b] + fr) * S36 + 4 * ks + fc]);
+                }
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (b >= nblk) break;
+                    const int i = 8 * bi[b] + fr, j = 8 * bj[b] + 2 * fc, gi = NB * k + i;
+                    double v0 = D[i * S33 + j] - acc[b][0], v1 = D[i * S33 + j + 1] - acc[b][1];
+                    if (i == j) v0 = (gi < n) ? v0 + u : 1.0;
+                    if (i == j + 1) v1 = (gi < n) ? v1 + u : 1.0;
+                    D[i * S33 + j] = v0;
+                    D[i * S33 + j + 1] = v1;
+                }
+            }
+            bar_sync(2, 128);
+            PROF(3);
+            if (warp == 0) {
+                if (warp_potrf_blocked(D, Lc, dv, Linv + (k & 1) * T36, lane, prof ? tsacc : nullptr, tA)) *a.info = 1;
+                PROF(4);
+            }
+        } else if (warp == 1) {
+            // ---- L(k,k)^-1 behind the Cholesky; publish to shared (next panel's product) and global (U, R) ----
+            {   // zero the inverse tile while the products of this panel run, then build it behind the Cholesky
+                long long w0 = prof ? clock64() : 0;
+                double* Ls = Linv + (k & 1) * T36;
+                for (int e = lane; e < T36; e += 32) {
+                    const int r = e / S36, c = e - r * S36;
+                    if ((r >> 3) != (c >> 3) || c >= NB) Ls[e] = 0.0;          // the diagonal blocks are NaN-armed by warp "T"
+                }
+                __syncwarp();
+                warp_linv_blocked(Lc, dv, Ls, a.LI + (size_t)k * T32, Sc, lane, linv_failed, prof ? wacc : nullptr,
+                                  prof ? tsacc : nullptr, tA);
+                if (prof) w1acc += clock64() - w0;
+            }
+            if (NB * k + lane < n) a.dinv[NB * k + lane] = dv[lane];
+            if (linv_failed && lane == 0) *a.info = 1;
+        } else {
+            // ---- I/O warps ----
+            long long q0 = 0, q1;
+#define IOPROF(slot) do { if (prof && lane == 0) { q1 = clock64(); ioacc[slot] += q1 - q0; q0 = q1; } } while (0)
+            if (prof && lane == 0) q0 = clock64();
+            if (k >= 1 && it == 0 && !(a.debug & 8)) red_release(diag_done + (k - 1), 1);   // covers warp 1's stores (bar.sync above)
+            IOPROF(0);
+            {   // NaN-arm the other column buffer for panel k+1 (its last reader finished before the barrier)
+                double* Ln = Lcol + ((k + 1) & 1) * T36;
+                if (!(a.debug & 32)) for (int e = it; e < T36; e += 96) Ln[e] = qnan;
+                if (it < NB) dinvs[((k + 1) & 1) * NB + it] = qnan;
+            }
+            bar_sync(1, 224);                                              // L(k,k-1) is complete
+            if (prof && lane == 0 && *(volatile double*)Lx == 1.2345e300) q0 = 0;
+            IOPROF(1);
+            if (k >= 1 && WB >= 1) {
+                store_g_tile(lb_tile(a, k, 1), Lx, S36, it, 96);
+                if (iw == 2) {
+                    bar_sync(3, 96);
+                    IOPROF(2);
+                    if (lane == 0 && !(a.debug & 8)) red_release(rows_done + (k - 1), 1);
+                    IOPROF(3);
+                } else {
+                    bar_arrive(3, 96);
+                    IOPROF(2);
+                }
+            }
+            if (k + 1 < NP) {
+                if (k >= 1 && NU > 0) {
+                    if (lane == 0) spin_until(upd_done + (k - 1), NU);
+                    __syncwarp();
+                    IOPROF(4);
+                }
+                load_ab_tiles2<96>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
+                                   Xbuf + ((k + 1) & 1) * T36, S36, it);
+                IOPROF(5);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) red_release(diag_done + (NP - 1), 1);
+    if (prof && tid == 0) {
+        a.prof[9] = clock64();
+        for (int q = 0; q < 5; ++q) a.prof[q] = tacc[q];
+    }
+    if (prof && iw >= 0 && lane == 0) for (int q = 0; q < 6; ++q) a.prof[12 + 6 * iw + q] = ioacc[q];
+    if (prof && warp == 1 && lane == 0) { a.prof[30] = w1acc; for (int q = 0; q < 5; ++q) a.prof[3 + 0 * q + 0] += 0; }
+    if (prof && warp == 1 && lane == 0) for (int q = 0; q < 5; ++q) a.prof[31 + q] = wacc[q];
+    if (prof && lane == 0 && (warp == 0 || warp == 5 || warp == 1))
+        for (int q = 0; q < 4; ++q) a.prof[36 + 4 * (warp == 0 ? 0 : warp == 5 ? 1 : 2) + q] = tsacc[q];
+    if (prof && tid == 0) for (int q = 4; q < 7; ++q) a.prof[44 + q] = tsacc[q];
+#undef PROF
+#undef IOPROF
+}
+
+// =====================================================================================================
+// R: forward substitution behind P, then the back substitution (same CTA, no grid barrier in between).
+// =====================================================================================================
+__device__ void role_R(const Args3& a, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, NP = a.NP, WB = a.WB;
+    int* diag_done = a.flags;
+    int* rows_done = a.flags + NP;
+    double* s = smem;                          // NP*NB running right-hand side -> y -> x
+    double* LinvS = s + (size_t)NP * NB;       // T33
+    double* ys = LinvS + T33;                  // NB
+    double* Lrows = ys + NB;                   // 8 x T33
+
+    if (a.debug & 8) return;
+    for (int i = tid; i < NP * NB; i += THREADS) s[i] = (i < n) ? __ldcg(a.g + i) : 0.0;
+    for (int p = 0; p < NP; ++p) {
+        cta_wait(diag_done + p, 1);
+        load_g_tile(a.LI + (size_t)p * T32, LinvS, S33, tid, THREADS);
+        __syncthreads();
+        if (warp == 0) {                       // y_p = L(p,p)^-1 s_p
+            double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; c += 2) {
+                y0 = fma(LinvS[lane * S33 + c], s[NB * p + c], y0);
+                y1 = fma(LinvS[lane * S33 + c + 1], s[NB * p + c + 1], y1);
+            }
+            __syncwarp();
+            ys[lane] = y0 + y1;
+            s[NB * p + lane] = y0 + y1;
+        }
+        const int nrows = min(NP - 1, p + WB) - p;
+        if (nrows > 0) {
+            if (a.debug & 1) __syncthreads(); else cta_wait(rows_done + p, nrows);    // also orders ys
+            for (int q0 = 0; q0 < nrows; q0 += 8) {
+                const int nq = min(8, nrows - q0);
+                for (int q = 0; q < nq; ++q)
+                    load_g_tile(lb_tile(a, p + 1 + q0 + q, q0 + q + 1), Lrows + (size_t)q * T33, S33, tid, THREADS);
+                __syncthreads();
+                const int q = tid >> 5;
+                if (q < nq) {                  // s_i -= L(i, panel p) . y_p
+                    const double* Lr = Lrows + (size_t)q * T33 + lane * S33;
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) {
+                        s0 = fma(Lr[c], ys[c], s0);
+                        s1 = fma(Lr[c + 1], ys[c + 1], s1);
+                    }
+                    s[NB * (p + 1 + q0 + q) + lane] -= s0 + s1;
+                }
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+    }
+
+    if ((a.debug & 4) && tid == 0) a.prof[10] = clock64();
+    if (a.debug & 2) {
+        for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
+        return;
+    }
+    // ---- back substitution L^T x = y, push style.  Register-prefetched operands: job A = tile d = warp+1 (all
+    // warps), job B = L(k,k)^-1 on warp 0 / tile d = warp+8 on warps 1..7; wider bands go on demand. ----
+    double pa[NB], pb[NB];
+    const int dA = warp + 1, dB = warp + 8;
+    auto prefetch = [&](int k) {
+        const int nd = min(WB, k);
+        if (dA <= nd) {
+            const double* G = lb_tile(a, k, dA);
+#pragma unroll
+            for (int r = 0; r < NB; ++r) pa[r] = __ldcg(G + r * NB + lane);
+        }
+        if (warp == 0 || dB <= nd) {
+            const double* G = (warp == 0) ? a.LI + (size_t)k * T32 : lb_tile(a, k, dB);
+#pragma unroll
+            for (int r = 0; r < NB; ++r) pb[r] = __ldcg(G + r * NB + lane);
+        }
+    };
+    __syncthreads();
+    prefetch(NP - 1);
+    for (int k = NP - 1; k >= 0; --k) {
+        const double* sk = s + NB * k;
+        if (warp == 0) {                       // x_k = L(k,k)^-T s_k
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 4) {
+                x0 = fma(pb[r], sk[r], x0);
+                x1 = fma(pb[r + 1], sk[r + 1], x1);
+                x2 = fma(pb[r + 2], sk[r + 2], x2);
+                x3 = fma(pb[r + 3], sk[r + 3], x3);
+            }
+            __syncwarp();
+            s[NB * k + lane] = (x0 + x1) + (x2 + x3);
+        }
+        __syncthreads();
+        const int nd = min(WB, k);
+        if (dA <= nd) {                        // s_{k-d} -= L(k,k-d)^T x_k
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 2) {
+                c0 = fma(pa[r], sk[r], c0);
+                c1 = fma(pa[r + 1], sk[r + 1], c1);
+            }
+            s[NB * (k - dA) + lane] -= c0 + c1;
+        }
+        if (warp != 0 && dB <= nd) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 2) {
+                c0 = fma(pb[r], sk[r], c0);
+                c1 = fma(pb[r + 1], sk[r + 1], c1);
+            }
+            s[NB * (k - dB) + lane] -= c0 + c1;
+        }
+        for (int d = 16 + warp; d <= nd; d += 8) {     // wide bands: remaining tiles on demand
+            const double* G = lb_tile(a, k, d);
+            double c0 = 0.0;
+            for (int r = 0; r < NB; ++r) c0 = fma(__ldcg(G + r * NB + lane), sk[r], c0);
+            s[NB * (k - d) + lane] -= c0;
+        }
+        if (k >= 1) prefetch(k - 1);
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
+    if ((a.debug & 4) && tid == 0) a.prof[11] = clock64();
+}
+
+// =====================================================================================================
+// U: trailing update.  Tile t of panel p's trailing triangle goes to CTA (t + p) % NU; a tile costs three
+// DMMA products: L(I,p) = A(I,p) Linv^T, L(J,p) = A(J,p) Linv^T, A(I,J) -= L(I,p) L(J,p)^T.  The diagonal tile
+// (I,I) also stores L(I,p) for the substitutions.
+// =====================================================================================================
+__device__ void role_U(const Args3& a, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = a.NP, WB = a.WB, bw = a.bw;
+    int* diag_done = a.flags;
+    int* rows_done = a.flags + NP;
+    int* upd_done = a.flags + 2 * NP;
+    const int NU = (int)gridDim.x - 2, ui = (int)blockIdx.x - 2;
+    double* LinvS = smem;            // T36
+    double* As = LinvS + T36;
+    double* Bs = As + T36;
+    double* LIs = Bs + T36;
+    double* LJs = LIs + T36;
+    const int fr = lane >> 2, fc = lane & 3;
+
+    for (int p = 0; p < NP; ++p) {
+        const int last = min(NP - 1, p + WB);
+        const int nrows = last - p;
+        const int ntiles = nrows * (nrows + 1) / 2;
+        int t = ((ui - p) % NU + NU) % NU;
+        bool first = true;
+        int rows_written = 0;
+        for (; t < ntiles && !(a.debug & 1); t += NU) {
+            if (t == 0) continue;                                         // tile (p+1,p+1) belongs to P
+            int ri = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+            while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
+            while (ri * (ri + 1) / 2 > t) --ri;
+            const int I = p + 1 + ri, J = p + 1 + (t - ri * (ri + 1) / 2);
+            if (NB * (I - J) - (NB - 1) > bw) continue;                   // entirely outside the band
+            const bool diag = (I == J);
+            if (first && p >= 1) cta_wait(upd_done + (p - 1), NU);       // every tile carries panels <= p-1
+            else __syncthreads();                                        // shared buffers of the previous tile are free
+            load_ab_tiles2<THREADS>(a, I, p, As, S36, diag ? -1 : J, p, Bs, S36, tid);
+            // old values of my two 8x8 output blocks (fragment layout), issued with the operand loads
+            const int bi = warp >> 1;
+            double oldv[2][2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int bj = 2 * (warp & 1) + q;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * bj + 2 * fc + e;
+                    oldv[q][e] = in_band(a, i, j) ? __ldcg(ab_at(a, i, j)) : 0.0;
+                }
+            }
+            if (first) {
+                cta_wait(diag_done + p, 1);
+                load_g_tile(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS);
+                first = false;
+            }
+            __syncthreads();
+            if (diag) {
+                trsm_strip(As, LinvS, LIs, warp >> 1, (warp & 1) ? 0x6u : 0x9u, lane);
+            } else if (warp < 4) {
+                trsm_strip(As, LinvS, LIs, warp, 0xfu, lane);
+            } else {
+                trsm_strip(Bs, LinvS, LJs, warp - 4, 0xfu, lane);
+            }
+            __syncthreads();
+            const double* Lb = diag ? LIs : LJs;
+            {
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                const int bj0 = 2 * (warp & 1);
+                const bool skip1 = diag && (bj0 + 1 > bi), skip0 = diag && (bj0 > bi);   // above the diagonal: not stored
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double af = LIs[(8 * bi + fr) * S36 + 4 * ks + fc];
+                    if (!skip0) dmma884(acc[0][0], acc[0][1], af, Lb[(8 * bj0 + fr) * S36 + 4 * ks + fc]);
+                    if (!skip1) dmma884(acc[1][0], acc[1][1], af, Lb[(8 * (bj0 + 1) + fr) * S36 + 4 * ks + fc]);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 0 ? skip0 : skip1) continue;
+                    const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * (bj0 + q) + 2 * fc;
+                    if (in_band(a, i, j)) __stcg(ab_at(a, i, j), oldv[q][0] - acc[q][0]);
+                    if (in_band(a, i, j + 1)) __stcg(ab_at(a, i, j + 1), oldv[q][1] - acc[q][1]);
+                }
+            }
+            if (diag) {
+                store_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
+                ++rows_written;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // one release fence for both counters
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(upd_done + p), "r"(1) : "memory");
+            if (rows_written)
+                asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(rows_done + p), "r"(rows_written) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) band_chol3_kernel(Args3 a) {
+    extern __shared__ double smem[];
+    if (blockIdx.x == 0) role_P(a, smem);
+    else if (blockIdx.x == 1) role_R(a, smem);
+    else role_U(a, smem);
+}
+
+size_t smem_bytes3(int n) {
+    const size_t NP = (size_t)(n + NB - 1) / NB;
+    const size_t p_role = 2 * (size_t)T33 + 8 * (size_t)T36 + 2 * NB + 3 * 96;
+    const size_t r_role = NP * NB + (size_t)T33 + NB + 8 * (size_t)T33;
+    const size_t u_role = 5 * (size_t)T36;
+    size_t m = p_role > r_role ? p_role : r_role;
+    if (u_role > m) m = u_role;
+    return m * sizeof(double);
+}
+
+long long ws_bytes3(int n, int bw) {
+    const long long NP = (n + NB - 1) / NB, WB = (bw + NB - 1) / NB;
+    return (NP * (WB > 0 ? WB : 1) + NP) * (long long)T32 * (long long)sizeof(double) + ((3 * NP * (long long)sizeof(int) + 255) & ~255LL) + 256 + 1024;
+}
+
+int g_debug3 = 0;
+
+}  // namespace
+
+extern "C" {
+
+int sb_band3_debug(int flags) { g_debug3 = flags; return SB_OK; }
+
+/* byte offset of the 32 cycle counters inside the workspace (debug flag 4) */
+long long sb_band3_prof_offset(int n, int bw) { return ws_bytes3(n, bw) - 1024; }
+
+int sb_band3_fits(int n, int bw) {
+    return (n > 0 && bw >= 0 && (bw + NB - 1) / NB <= MAX_WB3 && smem_bytes3(n) <= 227 * 1024) ? 1 : 0;
+}
+
+long long sb_band3_workspace_bytes(int n, int bw) { return ws_bytes3(n, bw); }
+
+int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                   void* workspace, long long ws_bytes, int n_ctas, void* stream) {
+    if (!AB || !g || !dinv || !info || !workspace || n <= 0 || bw < 0 || ldab < bw + 1) return SB_ERR_ARG;
+    if (n_ctas < 3) return SB_ERR_ARG;
+    if (!sb_band3_fits(n, bw)) return SB_ERR_ARG;
+    if (ws_bytes < ws_bytes3(n, bw)) return SB_ERR_WORKSPACE;
+    static int max_ctas = 0;
+    static size_t configured = 0;
+    const size_t smem = smem_bytes3(n);
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(band_chol3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SB_ERR_CUDA;
+        configured = smem;
+    }
+    if (max_ctas == 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        max_ctas = sms;            // 1 CTA per SM (launch bounds): the cooperative launch checks co-residency
+    }
+    if (n_ctas > max_ctas) n_ctas = max_ctas;
+    Args3 a;
+    a.AB = AB; a.ldab = ldab; a.n = n; a.bw = bw; a.g = g; a.u = u; a.dinv = dinv; a.info = info;
+    a.NP = (n + NB - 1) / NB;
+    a.WB = (bw + NB - 1) / NB;
+    if (a.WB > a.NP - 1) a.WB = a.NP - 1 > 0 ? a.NP - 1 : 0;
+    const long long tiles = (long long)a.NP * (a.WB > 0 ? a.WB : 1);
+    a.LB = (double*)workspace;
+    a.LI = a.LB + tiles * T32;
+    a.flags = (int*)(a.LI + (long long)a.NP * T32);
+    a.prof = (long long*)((char*)workspace + ws_bytes3(n, bw) - 1024);
+    a.debug = g_debug3;
+    if (cudaMemsetAsync(a.flags, 0, 3 * (size_t)a.NP * sizeof(int), (cudaStream_t)stream) != cudaSuccess)
+        return SB_ERR_CUDA;
+    void* kargs[] = {(void*)&a};
+    if (cudaLaunchCooperativeKernel((const void*)band_chol3_kernel, dim3(n_ctas), dim3(THREADS), kargs, smem,
+                                    (cudaStream_t)stream) != cudaSuccess)
+        return SB_ERR_CUDA;
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+}  // extern "C"

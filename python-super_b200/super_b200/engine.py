@@ -213,7 +213,7 @@ class Tracker:
         # "band": own cluster Cholesky in band storage (sb_band_solve); "dense": dense A + library Cholesky.
         # The default follows the faster one as measured on B200 (profiles/): see DESIGN.md section 5.
         self.solver = getattr(opt, "solver", os.environ.get("SB_SOLVER", "band"))
-        self.cluster_size = int(getattr(opt, "solver_ctas", os.environ.get("SB_SOLVER_CTAS", "64")))
+        self.cluster_size = int(getattr(opt, "solver_ctas", os.environ.get("SB_SOLVER_CTAS", "148")))
         self.band = None
         self.block_bw = torch.zeros(1, dtype=I32, device=self.dev)
         self._bw_pinned = torch.zeros(2, dtype=I32).pin_memory() if torch.cuda.is_available() else None

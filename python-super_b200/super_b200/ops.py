@@ -174,20 +174,29 @@ def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=N
 
 
 def band_solve(band, u_ptr=None, cluster_size=16, variant=None):
-    """(A + u I) x = g in place: band.AB <- L, band.g <- x (solver node order).  u_ptr: device address of u.
-    variant 2 (default): pipelined kernel sb_band_solve2; variant 1: barrier-per-panel kernel sb_band_solve."""
+    """(A + u I) x = g in place: band.g <- x (solver node order).  u_ptr: device address of u.
+    variant 3 (default): sb_band_solve3 (DMMA products with explicit block inverses, push-style back substitution);
+    variant 2: sb_band_solve2 (first pipelined kernel); variant 1: barrier-per-panel cluster kernel sb_band_solve."""
     import os
     if variant is None:
-        variant = int(os.environ.get("SB_BAND_VARIANT", "2"))
-    if variant == 2 and cluster_size >= 3 and lib.load().sb_band2_fits(band.n, band.bw):
+        variant = int(os.environ.get("SB_BAND_VARIANT", "3"))
+    l = lib.load()
+    if variant == 3 and cluster_size >= 3 and l.sb_band3_fits(band.n, band.bw):
+        if getattr(band, "ws3", None) is None:
+            band.ws3 = torch.zeros(int(l.sb_band3_workspace_bytes(band.n, band.bw)), dtype=torch.uint8,
+                                   device=band.AB.device)
+        call("sb_band_solve3", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
+             ptr(band.info), ptr(band.ws3), band.ws3.numel(), int(cluster_size), stream())
+    elif variant >= 2 and cluster_size >= 3 and l.sb_band2_fits(band.n, band.bw):
         if getattr(band, "ws2", None) is None:
-            band.ws2 = torch.zeros(int(lib.load().sb_band2_workspace_bytes2(band.n, band.ldab)), dtype=torch.uint8,
+            band.ws2 = torch.zeros(int(l.sb_band2_workspace_bytes2(band.n, band.ldab)), dtype=torch.uint8,
                                    device=band.AB.device)
         call("sb_band_solve2", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
-             ptr(band.info), ptr(band.ws2), band.ws2.numel(), int(cluster_size), stream())
+             ptr(band.info), ptr(band.ws2), band.ws2.numel(), int(min(cluster_size, 128)), stream())
     else:
+        cs = 16 if cluster_size >= 16 else 8 if cluster_size >= 8 else 4 if cluster_size >= 4 else 2 if cluster_size >= 2 else 1
         call("sb_band_solve", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
-             ptr(band.info), int(cluster_size), stream())
+             ptr(band.info), cs, stream())
 
 
 class LMState:

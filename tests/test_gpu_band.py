@@ -22,16 +22,19 @@ def _random_band_system(n, bw, seed):
     return A, b
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("n,bw,cluster", [(40, 5, 1), (97, 13, 2), (256, 40, 4), (1000, 150, 8), (1862, 300, 16),
                                           (1862, 300, 8), (333, 332, 8), (64, 0, 4), (31, 6, 16), (200, 31, 3),
-                                          (2000, 64, 16), (1862, 845, 16)])
+                                          (2000, 64, 16), (1862, 845, 16), (1862, 370, 128), (1862, 377, 64), (33, 32, 5),
+                                          (4000, 500, 148)])
 def test_band_solve_matches_dense(n, bw, cluster, variant):
-    if variant == 2 and cluster < 3:
-        pytest.skip("pipelined kernel needs >= 3 CTAs")
+    if variant >= 2 and cluster < 3:
+        pytest.skip("pipelined kernels need >= 3 CTAs")
     if variant == 1 and cluster not in (1, 2, 4, 8, 16):
         pytest.skip("barrier kernel takes power-of-two clusters")
-    from super_b200 import ops
+    from super_b200 import ops, lib
+    if variant == 2 and not lib.load().sb_band2_fits(n, bw):
+        pytest.skip("v2 shared-memory layout does not fit")
     A, b = _random_band_system(n, bw, seed=n + bw)
     band = ops.Band(n, bw, None, "cuda")
     AB = torch.zeros((n, bw + 1), dtype=torch.float64)
