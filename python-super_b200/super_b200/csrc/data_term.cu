@@ -42,7 +42,7 @@ struct Eval {
 
 // Per-surfel evaluation.  Returns true when the surfel has a valid projective correspondence
 // (the reference's valid_pair & intrpl_valid, loss.py:229-246).  jrow: 28 doubles when GRAD.
-template <bool GRAD>
+template <bool GRAD, bool CANON = false>
 __device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, double* jrow, int jstride) {
     const double* pp = a.points + 3 * (size_t)i;
     V3 p = v3(pp[0], pp[1], pp[2]);
@@ -134,7 +134,15 @@ __device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, 
             const double s = a.lambda * w[k];
             const double qd = dot3(qvk, dk), aq = dot3(av, qvk), ad = dot3(av, dk);
             const V3 axd = cross3(av, dk);
-            double* jr = jrow + 7 * k * jstride;
+            // CANON: the node blocks of the row are laid out in ascending node-id order, so that all surfels with the
+            // same node SET (any kNN order) share one Gram accumulator
+            int slot_k = k;
+            if (CANON) {
+                slot_k = 0;
+#pragma unroll
+                for (int j = 0; j < SB_KNN; ++j) slot_k += (ev.idx[j] < ev.idx[k]) ? 1 : 0;
+            }
+            double* jr = jrow + 7 * slot_k * jstride;
             jr[0] = s * 2.0 * dot3(av, cpk);
             jr[1 * jstride] = s * 2.0 * (qd * av.x + aq * dk.x - 2.0 * ad * qvk.x - qwk * axd.x);
             jr[2 * jstride] = s * 2.0 * (qd * av.y + aq * dk.y - 2.0 * ad * qvk.y - qwk * axd.y);
@@ -157,48 +165,71 @@ constexpr int JT_STRIDE = 36;           // doubles per panel column (32 surfels 
 constexpr int JT_DOUBLES = 32 * JT_STRIDE;
 constexpr int JTJ_WARPS = 4;
 
+// 4 node ids (distinct, < 65535) packed in ASCENDING order: the key of the node set
 __device__ __forceinline__ unsigned long long pack_key(const int* idx) {
-    return ((unsigned long long)(unsigned)idx[0] << 48) | ((unsigned long long)(unsigned)idx[1] << 32) |
-           ((unsigned long long)(unsigned)idx[2] << 16) | (unsigned long long)(unsigned)idx[3];
+    unsigned long long key = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rank += (idx[j] < idx[k]) ? 1 : 0;
+        key |= (unsigned long long)(unsigned)idx[k] << (48 - 16 * rank);
+    }
+    return key;
 }
 
+constexpr int FL_STRIDE = 33;            // flush scratch: 32x32 Gram matrix, one per warp
+constexpr int FL_DOUBLES = 32 * FL_STRIDE;
+
 // Flush one warp accumulator (10 tiles x 2 doubles per lane) into the lower-triangular A (dense or band,
-// common.cuh MatView), g (= -J^T r) and the optional sum r^2.
+// common.cuh MatView), g (= -J^T r) and the optional sum r^2.  The tiles go through a shared 32x32 scratch and
+// a run-time loop over the 29x29 upper triangle: the fully unrolled version was 2 x 2.4 k instructions and made
+// the kernel miss the instruction cache (ncu r1c: "no instruction" stalls 3.0 per issue, as much as memory).
 __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, const MatView& M,
-                                          double* g, double* loss_cur) {
-    int node[4] = {(int)(key >> 48) & 0xffff, (int)(key >> 32) & 0xffff, (int)(key >> 16) & 0xffff,
-                   (int)key & 0xffff};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) node[k] = M.pos(node[k]);
+                                          double* g, double* loss_cur, double* __restrict__ St) {
     int t = 0;
 #pragma unroll
-    for (int ti = 0; ti < 4; ++ti) {
+    for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
         for (int tj = ti; tj < 4; ++tj, ++t) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int m = 8 * ti + (lane >> 2);
-                const int n = 8 * tj + 2 * (lane & 3) + e;
-                const double val = acc[t][e];
-                acc[t][e] = 0.0;
-                if (m > n || n > 28 || val == 0.0) continue;
-                if (n == 28) {
-                    if (m == 28) { if (loss_cur) atomicAdd(loss_cur, val); }
-                    else atomicAdd(g + 7 * node[m / 7] + m % 7, -val);
-                    continue;
-                }
-                const int gm = 7 * node[m / 7] + m % 7, gn = 7 * node[n / 7] + n % 7;
-                M.add(max(gm, gn), min(gm, gn), val);
-            }
+            *reinterpret_cast<double*>(St + (8 * ti + (lane >> 2)) * FL_STRIDE + 8 * tj + 2 * (lane & 3)) = acc[t][0];
+            *reinterpret_cast<double*>(St + (8 * ti + (lane >> 2)) * FL_STRIDE + 8 * tj + 2 * (lane & 3) + 1) = acc[t][1];
+            acc[t][0] = acc[t][1] = 0.0;
         }
+    __syncwarp();
+    // the 435 entries (m <= n <= 28) of the upper triangle are dealt round-robin to the lanes (14 each);
+    // row m belongs to node m/7, component m%7; row/column 28 is the residual column.  Lane k < 4 looks up the
+    // solver position of node k once; the others fetch it by shuffle.
+    const int my_pos = (lane < 4) ? M.pos((int)(key >> (48 - 16 * lane)) & 0xffff) : 0;
+    for (int e0 = 0; e0 < 448; e0 += 32) {
+        const int e = e0 + lane;
+        int m = (int)((59.f - sqrtf(3481.f - 8.f * (float)min(e, 434))) * 0.5f);
+        while ((m + 1) * 29 - (m + 1) * m / 2 <= min(e, 434)) ++m;
+        while (m * 29 - m * (m - 1) / 2 > min(e, 434)) --m;
+        const int n = m + (min(e, 434) - (m * 29 - m * (m - 1) / 2));
+        const int km = (m * 37) >> 8, cm = m - 7 * km;                     // m/7, m%7 for m < 29  (km = 4 for m = 28)
+        const int kn = (n * 37) >> 8, cn = n - 7 * kn;
+        const int pm = __shfl_sync(0xffffffffu, my_pos, km & 3), pn = __shfl_sync(0xffffffffu, my_pos, kn & 3);
+        if (e >= 435) continue;
+        const double val = St[m * FL_STRIDE + n];
+        if (val == 0.0) continue;
+        if (n == 28) {
+            if (m == 28) { if (loss_cur) atomicAdd(loss_cur, val); }
+            else atomicAdd(g + 7 * pm + cm, -val);
+            continue;
+        }
+        const int gm = 7 * pm + cm, gn = 7 * pn + cn;
+        M.add(max(gm, gn), min(gm, gn), val);
     }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(JTJ_WARPS * 32)
 data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Jt = smem + warp * JT_DOUBLES;
+    double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
+    double* St = Jt + JT_DOUBLES;
     for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
 
     const int n = n_active(a.n_cap, a.n_dev);
@@ -214,31 +245,34 @@ data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur)
     unsigned long long acc_key = 0;
     bool have = false;
 
-    for (int c = c0; c < c1; ++c) {
+    // one extra "tail" pass with a sentinel key flushes the last accumulator through the same code as a tuple
+    // change inside the loop (a single inlined copy of the flush)
+    for (int c = c0; c <= c1; ++c) {
+        const bool tail = (c == c1);
         const int slot = c * 32 + lane;
         Eval ev;
         bool matched = false;
-        if (slot < n) {
+        if (!tail && slot < n) {
             const int sid = a.order ? a.order[slot] : slot;
-            matched = eval_surfel<true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
+            matched = eval_surfel<true, true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
         }
         if (matched) {
             Jt[28 * JT_STRIDE + lane] = ev.r;
-        } else {
+        } else if (!tail) {
 #pragma unroll
             for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
         }
         __syncwarp();
         const unsigned long long key = matched ? pack_key(ev.idx) : ~0ull;
-        unsigned remaining = __ballot_sync(0xffffffffu, matched);
+        unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
         while (remaining) {
             const int leader = __ffs(remaining) - 1;
-            const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);
-            const unsigned m = __ballot_sync(0xffffffffu, key == k) & remaining;
+            const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
+            const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
             if (!have || k != acc_key) {
-                if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur);
+                if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur, St);
                 acc_key = k;
-                have = true;
+                have = !tail;
             }
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -256,11 +290,10 @@ data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur)
 #pragma unroll
                     for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], x[ti], x[tj]);
             }
-            remaining &= ~m;
+            remaining = tail ? 0u : (remaining & ~m);
         }
         __syncwarp();
     }
-    if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur);
 }
 
 constexpr int LOSS_BLOCK = 256;
@@ -375,13 +408,15 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
     DataArgs a = make_args(points, knn_idx, knn_w, order, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
                            intr, lambda);
     const int n_chunks = (n_cap + 31) / 32;
-    const size_t smem = JTJ_WARPS * JT_DOUBLES * sizeof(double);
+    const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
     // exactly one wave: resident CTAs per SM x SM count (a partial second wave was a 40% tail, ncu r1)
     static int resident = 0;
     if (resident == 0) {
         int per_sm = 0, dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(data_jtj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SB_ERR_CUDA;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_jtj_kernel, JTJ_WARPS * 32, smem);
         resident = (per_sm > 0 ? per_sm : 1) * sms;
     }
