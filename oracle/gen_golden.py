@@ -89,5 +89,62 @@ def gen_lm(name, height, width, step, nframes, speed):
               f"N={len(fr['state']['points'])}")
 
 
+def gen_gf(name, height, width, step, nframes, speed, flags, opt_over, semantic=False, seg_speed=None):
+    """Autograd optimiser (GraphFit) fixtures: per tracked frame the 10 iterations' deform_verts, loss terms and the
+    gradient the optimiser consumed, the returned deform_verts, the state after Surfels.update and after the frame."""
+    frames = list(range(1, nframes + 1))
+    rec = run_reference.run(["--mesh_step_size", str(step)] + flags, frames, height, width, with_seg=semantic,
+                            semantic=semantic, speed=speed, seg_speed=seg_speed)
+    d = {}
+    meta = {"height": height, "width": width, "step": step, "frames": frames, "speed": speed, "seg_speed": seg_speed,
+            "semantic": semantic, "flags": flags, "opt": opt_over,
+            "reference": "ucsdarclab/Python-SuPer @ /root/reference (unmodified, CPU, shims)"}
+    for fr in rec.frames:
+        t = fr["t"]
+        nd = fr["new_data"]
+        for k in ("points", "norms"):
+            a32 = nd[k].astype(np.float32)
+            assert np.array_equal(a32.astype(np.float64), nd[k]), "new_data not f32-exact"
+            d[f"f{t}.nd.{k}"] = a32
+        d[f"f{t}.nd.valid"] = np.packbits(nd["valid"])
+        pack_state(d, f"f{t}.state", fr["state"])
+        its = fr.get("ag_iters")
+        if not its:
+            continue
+        d[f"f{t}.ag.deform_in"] = np.stack([it["deform_in"] for it in its])
+        d[f"f{t}.ag.loss"] = np.array([it["loss"] for it in its])
+        d[f"f{t}.ag.grad"] = np.stack([it["grad"] for it in its])
+        for k in sorted({k for it in its for k in it["losses"]}):
+            d[f"f{t}.ag.losses.{k}"] = np.array([it["losses"].get(k, np.nan) for it in its])
+        d[f"f{t}.beta"] = fr["beta"]
+        au = fr["after_update"]
+        for k in ("points", "norms", "ED_points", "ED_norms"):
+            d[f"f{t}.update.{k}"] = au[k]
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, meta=json.dumps(meta), **d)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, {len(d)} arrays")
+    for fr in rec.frames[1:]:
+        its = fr["ag_iters"]
+        print(f"  frame {fr['t']}: loss {its[0]['loss']:.6e} -> {its[-1]['loss']:.6e}  terms {its[-1]['losses']}  "
+              f"N={len(fr['state']['points'])}")
+
+
+GF_FLAGS = ["--sf_point_plane", "--mesh_rot", "--mesh_arap", "--mesh_face", "--optimizer", "Adam"]
+GF_OPT = dict(use_derived_gradient=False, mesh_face=True, optimizer="Adam")
+SEM_FLAGS = ["--load_seg", "--seg_dir", "seg", "--disable_ssim_conf", "--sf_soft_seg_point_plane", "--mesh_rot",
+             "--mesh_face", "--sf_bn_morph"]
+SEM_OPT = dict(use_derived_gradient=False, mesh_face=True, mesh_arap=False, sf_point_plane=False, optimizer="SGD",
+               method="semantic-super", data="superv2", num_classes=3, sf_soft_seg_point_plane=True,
+               sf_hard_seg_point_plane=False, sf_bn_morph=True, sf_bn_morph_weight=0.1, hard_seg=False,
+               del_seg_classes=[], disable_ssim_conf=True)
+
+
 if __name__ == "__main__":
-    gen_lm("lm_128x96", 96, 128, 16, 4, 3.0)
+    which = sys.argv[1:] or ["lm", "gf", "sem"]
+    if "lm" in which:
+        gen_lm("lm_128x96", 96, 128, 16, 4, 3.0)
+    if "gf" in which:
+        gen_gf("gf_128x96", 96, 128, 16, 3, 3.0, GF_FLAGS, GF_OPT)
+    if "sem" in which:
+        gen_gf("gf_sem_128x96", 96, 128, 16, 3, 3.0, SEM_FLAGS, SEM_OPT, semantic=True, seg_speed=15.0)

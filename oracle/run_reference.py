@@ -53,6 +53,9 @@ def snapshot_newdata(d):
     return out
 
 
+_CURRENT_REC = [None]
+
+
 class Recorder:
     """Per-frame records filled by the hooks below."""
 
@@ -67,13 +70,13 @@ class Recorder:
 
 
 def run(argv, frames, height, width, with_seg=False, semantic=False, record_matrices=False,
-        amp=None, quiet=True, time_only=False, tracking_gt=None, speed=1.0):
+        amp=None, quiet=True, time_only=False, tracking_gt=None, speed=1.0, seg_speed=None):
     """Run the reference over `frames` (list of ints; first = init frame).  Returns Recorder."""
     ref_shims.install()
     from super_b200 import synth
 
     tmp = tempfile.mkdtemp(prefix="super_ref_")
-    synth.write_sequence(tmp, frames, height, width, with_seg=with_seg, amp=amp, speed=speed)
+    synth.write_sequence(tmp, frames, height, width, with_seg=with_seg, amp=amp, speed=speed, seg_speed=seg_speed)
     if tracking_gt is not None:
         np.save(os.path.join(tmp, "gt.npy"), tracking_gt, allow_pickle=True)
 
@@ -98,6 +101,7 @@ def run(argv, frames, height, width, with_seg=False, semantic=False, record_matr
     torch.set_num_threads(os.cpu_count())
 
     rec = Recorder(record_matrices)
+    _CURRENT_REC[0] = rec
 
     if not time_only:
         # ---- hooks -------------------------------------------------------------------------
@@ -205,6 +209,25 @@ def run(argv, frames, height, width, with_seg=False, semantic=False, record_matr
                  "losses": {k: float(v) for k, v in losses.items()}})
             return loss, losses
         dm_mod.GraphFit.get_losses = get_losses_hook
+
+        # ... and the gradient the optimiser actually consumes (after grad[-1] /= J)
+        for opt_name in ("SGD", "Adam"):
+            base = getattr(torch.optim, opt_name)
+            if getattr(base, "_recording", False):
+                continue
+
+            def make(base_cls):
+                class Recording(base_cls):
+                    _recording = True
+
+                    def step(self, *a, **kw):
+                        p = self.param_groups[0]["params"][0]
+                        r = _CURRENT_REC[0]
+                        if r is not None and r.cur is not None and r.cur.get("ag_iters"):
+                            r.cur["ag_iters"][-1]["grad"] = _t2n(p.grad)
+                        return super().step(*a, **kw)
+                return Recording
+            setattr(torch.optim, opt_name, make(base))
 
     # ---- run -----------------------------------------------------------------------------------
     loader = init_dataset(opt)

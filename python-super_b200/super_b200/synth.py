@@ -70,7 +70,8 @@ def seg_logits_at(t: int, height: int, width: int) -> np.ndarray:
 
 
 def write_sequence(data_dir: str, frames, height: int, width: int, seed: int = 0,
-                   with_seg: bool = False, amp: float | None = None, speed: float = 1.0) -> None:
+                   with_seg: bool = False, amp: float | None = None, speed: float = 1.0,
+                   seg_speed: float | None = None) -> None:
     """Write the reference's on-disk layout (/root/reference/utils/data_loader.py:179-199):
     rgb/%06d-left.png (+right), depth/%06d.npy, seg/%06d-left.npy."""
     from PIL import Image
@@ -84,12 +85,13 @@ def write_sequence(data_dir: str, frames, height: int, width: int, seed: int = 0
         tex.save(os.path.join(data_dir, "rgb", f"{t:06d}-right.png"))
         np.save(os.path.join(data_dir, "depth", f"{t:06d}.npy"), disp_at(t * speed, height, width, amp))
         if with_seg:
-            np.save(os.path.join(data_dir, "seg", f"{t:06d}-left.npy"), seg_logits_at(t * speed, height, width))
+            np.save(os.path.join(data_dir, "seg", f"{t:06d}-left.npy"),
+                    seg_logits_at(t * (speed if seg_speed is None else seg_speed), height, width))
 
 
 def frame_inputs(t: int, height: int, width: int, data: str = "superv1", seed: int = 0,
                  with_seg: bool = False, amp: float | None = None, tex: np.ndarray | None = None,
-                 speed: float = 1.0) -> dict:
+                 speed: float = 1.0, seg_speed: float | None = None) -> dict:
     """One frame as the host-side arrays the loader would produce (before batching):
     color (3,H,W) f32 in [0,1], disp/depth (1,H,W) f32, K, inv_K (4,4) f32, filename, time."""
     if tex is None:
@@ -108,5 +110,5 @@ def frame_inputs(t: int, height: int, width: int, data: str = "superv1", seed: i
         "divterm": 1.0 / (2.0 * 0.6 * 0.6),
     }
     if with_seg:
-        out["seg_conf"] = seg_logits_at(t * speed, height, width).astype(np.float64)
+        out["seg_conf"] = seg_logits_at(t * (speed if seg_speed is None else seg_speed), height, width).astype(np.float64)
     return out

@@ -18,14 +18,16 @@ class Golden:
         self.meta = json.loads(str(self.z["meta"]))
         m = self.meta
         self.H, self.W, self.step, self.frames, self.speed = m["height"], m["width"], m["step"], m["frames"], m["speed"]
-        self.opt = so.default_opt(height=self.H, width=self.W, mesh_step_size=self.step)
+        self.semantic, self.seg_speed = bool(m.get("semantic", False)), m.get("seg_speed")
+        self.opt = so.default_opt(height=self.H, width=self.W, mesh_step_size=self.step, **m.get("opt", {}))
         self.tex = synth.texture(self.H, self.W)
 
     def __getitem__(self, k):
         return self.z[k]
 
     def frame(self, t):
-        return synth.frame_inputs(t, self.H, self.W, tex=self.tex, speed=self.speed)
+        return synth.frame_inputs(t, self.H, self.W, data=self.opt.data, tex=self.tex, speed=self.speed,
+                                  with_seg=self.semantic, seg_speed=self.seg_speed)
 
     def state(self, t):
         """Oracle-port state namespace holding the reference's state after frame t."""
@@ -47,7 +49,7 @@ class Golden:
         ed.param_num = 7 * ed.num
         sf.ED = ed
         sf.time = t
-        sf.semantic = False
+        sf.semantic = self.semantic
         sf.track_id = None
         return sf
 

@@ -99,3 +99,28 @@ def test_update_fuse_compact_match_reference(t):
     for k in ("points", "norms", "knn_w", "radii", "confs", "colors", "time_stamp", "projdata"):
         tol = 1e-5 if k == "projdata" else 1e-12
         _close(getattr(sf, k), getattr(ref, k).numpy(), tol, k)
+
+
+# ---- autograd optimiser (GraphFit) fixtures: configs 3b (Adam, LM terms + face) and 4 (semantic, SGD) ----------
+@pytest.mark.parametrize("name", ["gf_128x96", "gf_sem_128x96"])
+def test_graphfit_port_reproduces_reference(name):
+    """oracle/graphfit_oracle.py, teacher-forced with the reference's pre-frame state, reproduces the reference's
+    per-iteration deform_verts, loss terms, consumed gradient, result and Surfels.update output."""
+    import torch
+    from oracle import graphfit_oracle as gf
+    g = Golden(name)
+    for t in g.frames[1:]:
+        sf, nd = g.state(t - 1), g.new_data(t)
+        tr = []
+        dv = gf.graph_fit(g.opt, sf, nd, trace=tr)
+        assert np.abs(np.stack([x["deform_in"].numpy() for x in tr]) - g[f"f{t}.ag.deform_in"]).max() < 1e-13
+        gref = g[f"f{t}.ag.grad"]
+        assert np.abs(np.stack([x["grad"].numpy() for x in tr]) - gref).max() < 1e-10 * np.abs(gref).max()
+        for k in [k for k in g.z.files if k.startswith(f"f{t}.ag.losses.")]:
+            ref = g[k]
+            mine = np.array([x["losses"].get(k.split(".")[-1], np.nan) for x in tr])
+            assert np.allclose(mine, ref, rtol=1e-11, atol=0, equal_nan=True), k
+        assert np.abs(dv.numpy() - g[f"f{t}.beta"]).max() < 1e-13
+        so.update(g.opt, sf, dv)
+        for k, v in (("points", sf.points), ("norms", sf.norms), ("ED_points", sf.ED.points), ("ED_norms", sf.ED.norms)):
+            assert np.abs(v.numpy() - g[f"f{t}.update.{k}"]).max() < 1e-12, k
