@@ -179,6 +179,40 @@ int sb_lm_decide(void* state, const double* partials, int n_partials, double* lo
                  double* best, int n, void* stream);
 
 
+/* ---- autograd optimiser (GraphFit) as fused loss + analytic-gradient kernels ------------------------------
+ * /root/reference/super/deform_mesh.py:25-379 with the autograd forms of the terms in /root/reference/super/loss.py
+ * (:9-100 bilinear_sample, :293-401 DataLoss.autograd_forward, :458-473 ARAP, :502-505 Rot).
+ * dv (J+1,7) f64 deform_verts, row J = global transform.  grad (J+1,7) and acc[6] = {point_plane, arap, rot, face,
+ * morph_sum, morph_count} are ACCUMULATED (zero them before the first term; sb_gf_step re-zeroes them). */
+
+/* point-to-plane term; seg_mode 0 none | 1 soft (exp(-0.1 JSD)) | 2 hard (class equality); trg_seg_conf (P,C) dense map */
+int sb_gf_data(const double* points, const int* knn_idx, const double* knn_w, const unsigned char* stable, int n_cap,
+               const int* n_dev, const double* ed_points, int J, const double* dv, const float* vmap, const float* nmap,
+               int H, int W, const double* intr, double weight, int seg_mode, int C, const int* sf_seg,
+               const double* sf_seg_conf, const double* trg_seg_conf, double* grad, double* acc, void* stream);
+
+/* boundary-morph term: scores (C,H,W) f64 raw class scores of the new frame, edge_pts (E,2) f64 (x,y) of all classes
+ * concatenated, edge_off (C+1) i32.  grad_morph (J+1,7) holds the UN-normalised gradient (sb_gf_step divides by count) */
+int sb_gf_morph(const double* points, const int* knn_idx, const double* knn_w, const unsigned char* stable, int n_cap,
+                const int* n_dev, const double* ed_points, int J, const double* dv, int H, int W, const double* intr,
+                const double* scores, int C, const int* sf_seg, const double* edge_pts, const int* edge_off,
+                double* grad_morph, double* acc, void* stream);
+
+/* ARAP (knn_w weighted) + Rot (J+1 rows) + Face terms on the graph; triangles (3,F) i32 */
+int sb_gf_reg(const double* ed_points, const int* ed_knn, const double* ed_knn_w, int J, const int* triangles,
+              const double* areas, int F, const double* dv, double w_arap, double w_rot, double w_face, int use_arap,
+              int use_rot, int use_face, double* grad, double* acc, void* stream);
+
+/* grad[J] /= J; optimizer 0 = SGD(momentum 0.9) | 1 = Adam(0.9, 0.999, 1e-8); state 2*(J+1)*7 doubles; trace row
+ * `iter` (8 doubles): total, face, arap, rot, point_plane, bn_morph, morph_count, 0; grad_out (optional) = consumed grad */
+int sb_gf_step(double* dv, double* grad, double* grad_morph, double* acc, double w_morph, int use_morph, int J,
+               int optimizer, double lr, int iter, double* state, double* trace, double* grad_out, void* stream);
+
+/* the global-row part of Surfels.update (/root/reference/super/nodes.py:204-205,211-212,219-222), after sb_warp_update */
+int sb_gf_global_update(double* points, double* norms, int n_cap, const int* n_dev, double* ed_points, double* ed_norms,
+                        int J, const double* global_row, void* stream);
+
+
 /* ---- per-frame producer ---------------------------------------------------------------------------- */
 
 /* depth_preprocessing for --load_depth inputs: /root/reference/utils/data_loader.py:333-523 (getN :532-583,
