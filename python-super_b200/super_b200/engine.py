@@ -17,7 +17,7 @@ from types import SimpleNamespace as NS
 
 import torch
 
-from . import lib, ops, lm
+from . import lib, ops, lm, graphfit
 from .lib import call, ptr, stream
 
 F64, F32, I32, I64, U8 = torch.float64, torch.float32, torch.int32, torch.int64, torch.uint8
@@ -167,6 +167,7 @@ def build_graph(opt, frame):
     ta = torch.linalg.cross(g.points[f[:, 1]] - g.points[f[:, 0]], g.points[f[:, 2]] - g.points[f[:, 0]], dim=1)
     g.triangles_areas = 0.5 * torch.sqrt((ta ** 2).sum(1) + 1e-13)
     g.num, g.param_num = J, 7 * J
+    g.triangles_i32 = g.triangles.to(I32).contiguous()
     # Solver node order (no reference counterpart): nodes sorted along the LONGER image axis, so that the
     # block half-bandwidth of J^T J is ~3 grid lines of the shorter axis (measured 42 vs 57 blocks at C1).
     key = (u * (H + s) + v) if W >= H else (v * (W + s) + u)
@@ -313,12 +314,30 @@ class Tracker:
         self._refresh_bound()
         self._frames_since_known += 1
         sfv = self.view(self.n_bound)
-        order = ops.tuple_order(sfv.knn_indices, self.cur.n_dev, self.ED.node_pos, self.block_bw)
-        beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, n_dev=self.cur.n_dev,
-                                    order=order, band=self.band, cluster_size=self.cluster_size)
-        self.last_beta = beta
-        ops.warp_update(sfv.points, sfv.norms, sfv.knn_indices, sfv.knn_w, self.ED.points, self.ED.norms, beta,
-                        n_dev=self.cur.n_dev)
+        if getattr(opt, "use_derived_gradient", True):
+            order = ops.tuple_order(sfv.knn_indices, self.cur.n_dev, self.ED.node_pos, self.block_bw)
+            beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, n_dev=self.cur.n_dev,
+                                        order=order, band=self.band, cluster_size=self.cluster_size)
+            self.last_beta = beta
+            ops.warp_update(sfv.points, sfv.norms, sfv.knn_indices, sfv.knn_w, self.ED.points, self.ED.norms, beta,
+                            n_dev=self.cur.n_dev)
+        else:
+            # autograd configuration of the reference (GraphFit, super.py:70-71): fused loss+gradient kernels
+            if getattr(opt, "method", "super") == "semantic-super":
+                raise NotImplementedError("the device tracker does not carry per-surfel segmentation state yet: "
+                                          "call super_b200.graphfit.graph_fit with explicit seg arrays")
+            sfv.isStable = self.cur.stable[: self.n_bound]
+            sfv.ED = NS(points=self.ED.points, knn_indices=self.ED.knn_indices, knn_w=self.ED.knn_w,
+                        triangles=self.ED.triangles_i32, triangles_areas=self.ED.triangles_areas)
+            beta, self.gf_ws = graphfit.graph_fit(sfv, (frame.vmap, frame.nmap), frame.cam, opt,
+                                                  ws=getattr(self, "gf_ws", None), n_dev=self.cur.n_dev)
+            self.last_beta = beta
+            J = self.ED.num
+            ops.warp_update(self.cur.points[: self.n_bound], self.cur.norms[: self.n_bound],
+                            self.cur.knn_idx[: self.n_bound], self.cur.knn_w[: self.n_bound], self.ED.points,
+                            self.ED.norms, beta[:J], n_dev=self.cur.n_dev)
+            graphfit.update_global(self.cur.points[: self.n_bound], self.cur.norms[: self.n_bound], self.ED.points,
+                                   self.ED.norms, beta, n_dev=self.cur.n_dev)
         pr = SbFuseParams(opt.th_dist, opt.th_cosine_ang, float(frame.time), int(bool(opt.disable_merging_new_surfels)),
                           int(bool(opt.disable_merging_exist_surfels)), int(bool(opt.disable_adding_new_surfels)))
         call("sb_fuse", self.cur.ref(), frame.ref(), ptr(self.ED.points), ptr(self.ED.radii), self.ED.num,

@@ -4,7 +4,8 @@
 
 Host->device staging of the frame (super.py:31-34), producer, then init or fusion
 (LM -> update -> fuse -> compact), all through super_b200.engine.Tracker, i.e. libsuper_b200.so.
-Only the derived-gradient (LM) path is built in this round; the autograd GraphFit path raises.
+Both optimisers of the reference are available: the derived-gradient LM solver (--use_derived_gradient, super.py:68)
+and the autograd-style GraphFit with SGD/Adam (super.py:70-71), the latter for the non-semantic configuration.
 """
 from __future__ import annotations
 
@@ -20,12 +21,12 @@ class SuPer(torch.nn.Module):
         self.opt = opt
         self.sf = None
         self._trk = None
-        if not opt.use_derived_gradient:
-            raise NotImplementedError(
-                "super_b200 round 1 implements the derived-gradient LM path (--use_derived_gradient); "
-                "the autograd GraphFit path (super/deform_mesh.py) is the next SURVEY 8 row")
-        from .LM import LM_Solver
-        self.lm = LM_Solver(opt)
+        if opt.use_derived_gradient:
+            from .LM import LM_Solver
+            self.lm = LM_Solver(opt)
+        else:
+            from .deform_mesh import GraphFit
+            self.graph_fit = GraphFit(opt)
 
     def forward(self, models, inputs):
         dev = torch.device("cuda", torch.cuda.current_device())

@@ -82,3 +82,32 @@ def test_edge_points_match_oracle():
     off = off.cpu().tolist()
     for c in range(g.opt.num_classes):
         assert torch.equal(pts[off[c]:off[c + 1]].cpu(), ref[c])
+
+
+def test_free_running_autograd_tracker_follows_oracle():
+    """Config 3b shape (Adam, point-plane + ARAP + rot + face), device tracker vs the CPU port, free running:
+    per-frame final loss within 1e-4 relative (north_star), deform_verts within 1e-6, equal surfel counts."""
+    from oracle import graphfit_oracle as gfo
+    from super_b200 import engine, synth
+    H, W, step = 96, 128, 16
+    opt = so.default_opt(height=H, width=W, mesh_step_size=step, use_derived_gradient=False, mesh_face=True,
+                         optimizer="Adam")
+    tex = synth.texture(H, W)
+    trk = engine.Tracker(opt, device="cuda:0")
+    sf = None
+    for t in (1, 2, 3, 4):
+        fr = synth.frame_inputs(t, H, W, tex=tex, speed=3.0)
+        nd = so.preprocess(opt, fr)
+        beta = trk.step(torch.from_numpy(fr["depth"]).cuda(), torch.from_numpy(fr["color"]).cuda(),
+                        torch.from_numpy(fr["K"]), torch.from_numpy(fr["inv_K"]), fr["time"])
+        if sf is None:
+            sf = so.init_surfels(opt, nd, so.build_graph(opt, nd))
+            continue
+        tr = []
+        dv = gfo.graph_fit(opt, sf, nd, trace=tr)
+        so.update(opt, sf, dv); so.fuse(opt, sf, nd); so.compact(opt, sf, float(fr["time"]))
+        mine = trk.gf_ws.read_trace(opt.num_optimize_iterations)
+        rel = abs(mine[-1]["total"] - tr[-1]["loss"]) / tr[-1]["loss"]
+        assert rel < 1e-4, (t, mine[-1]["total"], tr[-1]["loss"])
+        assert (beta.cpu() - dv).abs().max() < 1e-6
+        assert trk.num_surfels() == len(sf.points)
