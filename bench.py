@@ -93,6 +93,37 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def solver_report(trk, solve_ms):
+    """The LM step solve (the frame's longest kernel; latency-bound pivot chain, not an HBM pass): measured time per
+    solve and the FP64 rate of its algorithmic flops n*bw^2 (band Cholesky) against the dense (7J)^3/3 the reference
+    pays in cuSOLVER."""
+    if not solve_ms or trk.band is None:
+        return {"kernel": "library dense Cholesky (torch.linalg / cuSOLVER)", "ms_per_solve": None}
+    n, bw = trk.band.n, trk.band.bw
+    ms = float(np.mean(solve_ms))
+    return {"kernel": "band_chol3_kernel (sb_band_solve3)", "n": n, "half_bandwidth": bw, "ms_per_solve": ms,
+            "solves_timed": len(solve_ms), "band_flops": float(n) * bw * bw, "dense_flops": float(n) ** 3 / 3.0,
+            "achieved_gflops_band": float(n) * bw * bw / (ms * 1e-3) / 1e9, "bound": "latency (sequential pivot chain)"}
+
+
+def reduce_over_ranks(total_ms, e2e_ms, info, world, device):
+    """The only cross-rank step of the benchmark (replicas are independent sequences): MAX of the timed
+    intervals over ranks and a gather of the per-rank summaries.  Backend-agnostic (NCCL on the GPUs, gloo in the
+    CPU test tests/test_multiprocess.py)."""
+    if world <= 1:
+        return total_ms, e2e_ms, None
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    gathered = [None] * world
+    torch.distributed.all_gather_object(gathered, info)
+    return float(t[0]), float(t[1]), gathered
+
+
+def aggregate_value(world, steps, total_ms):
+    """Whole-job frames/s: every rank tracked `steps` frames of its own sequence within the slowest rank's time."""
+    return world * steps / (total_ms / 1e3)
+
+
 # ----------------------------------------------------------------------------------------------------
 def run_cuda(args, rank, world, local_rank):
     from super_b200 import engine, lib
@@ -127,8 +158,8 @@ def run_cuda(args, rank, world, local_rank):
     sampler.start()
     lib.LAUNCHES = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = []          # (start, end) around the dominant data-term kernel, first LM iteration of each frame
-    lib.KERNEL_EVENTS = kev
+    kev, sev = [], []     # (start, end) events around every data-term J^T J launch / every banded solve
+    lib.KERNEL_EVENTS = {"sb_data_term_jtj": kev, "sb_band_solve3": sev}
     t_wall = time.perf_counter()
     for k in range(K):
         i = 1 + Wm + k
@@ -144,6 +175,7 @@ def run_cuda(args, rank, world, local_rank):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     jt_ms = [a.elapsed_time(b) for a, b in kev]
+    solve_ms = [a.elapsed_time(b) for a, b in sev]
     n_surf = trk.num_surfels()
     st = trk.ws.state.read()
     overflow = int(trk.overflow.item())
@@ -181,18 +213,12 @@ def run_cuda(args, rank, world, local_rank):
     e2e_wall = time.perf_counter() - t0
 
     # ---- reduce over ranks: max time, sum frames ----------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
-        gathered = [None] * world
-        torch.distributed.all_gather_object(gathered, {"rank": rank, "fps": K / (sum(step_ms) / 1e3), "surfels": n_surf})
-    else:
-        gathered = None
+    total_ms, e2e_ms, gathered = reduce_over_ranks(total_ms, e2e_ms, {"rank": rank, "fps": K / (sum(step_ms) / 1e3),
+                                                                     "surfels": n_surf}, world, dev)
     if rank != 0:
         return
 
-    value = world * K / (total_ms / 1e3)
+    value = aggregate_value(world, K, total_ms)
     N, P = n_surf, H * W
     b_pass = 44 * N + 28 * P                                 # algorithmic bytes of one surfel pass
     jt_avg_ms = float(np.mean(jt_ms)) if jt_ms else None
@@ -217,6 +243,7 @@ def run_cuda(args, rank, world, local_rank):
                      "frac": (achieved / peak) if achieved else None, "traffic": None,
                      "algorithmic_bytes": b_pass, "launch_ms": jt_avg_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+        "solver": solver_report(trk, solve_ms),
         "lm_trace_last_frame": {"loss": [float(x) for x in st["loss"]], "accept": [int(x) for x in st["accept"]]},
         "wall_s_timed_region": wall, "capacity_overflow": overflow,
     }

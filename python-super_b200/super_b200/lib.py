@@ -108,13 +108,17 @@ def call(name, *args):
     global LAUNCHES
     lib = load()
     ev = None
-    if KERNEL_EVENTS is not None and name == "sb_data_term_jtj":
+    sink = None
+    if KERNEL_EVENTS is not None:
+        # bench.py: either a list (events of sb_data_term_jtj) or a dict {entry point: list}
+        sink = KERNEL_EVENTS.get(name) if isinstance(KERNEL_EVENTS, dict) else (KERNEL_EVENTS if name == "sb_data_term_jtj" else None)
+    if sink is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     rc = getattr(lib, name)(*args)
     if ev is not None:
         ev[1].record()
-        KERNEL_EVENTS.append(ev)
+        sink.append(ev)
     if rc != 0:
         raise SuperB200Error(f"{name} failed: {_ERR.get(rc, rc)}")
     LAUNCHES += KERNELS_PER_CALL.get(name, 0)

@@ -108,3 +108,28 @@ def test_init_state_matches_reference():
     assert (trk.ED.knn_w.cpu() - ref.ED.knn_w).abs().max() < 1e-12
     assert torch.equal(trk.ED.edge_index.cpu(), ref.ED.edge_index)
     assert torch.equal(trk.ED.triangles.cpu(), ref.ED.triangles)
+
+
+def test_run_super_entry_point_on_disk_sequence(tmp_path):
+    """run_super.py (same flags as the reference's) over an on-disk synthetic sequence in the reference's layout
+    gives the same state as driving the Tracker directly."""
+    import sys, os
+    from super_b200 import synth, engine
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "python-super_b200")
+    sys.path.insert(0, root)
+    import run_super
+    H, W = 96, 128
+    synth.write_sequence(str(tmp_path), [1, 2, 3], H, W, speed=3.0)
+    models = run_super.main(["--model_name", "t", "--data_dir", str(tmp_path), "--start_id", "1", "--end_id", "4",
+                             "--height", str(H), "--width", str(W), "--load_depth", "--mesh_step_size", "16",
+                             "--sf_point_plane", "--mesh_rot", "--mesh_arap", "--use_derived_gradient"])
+    n_entry = models.super.sf.sf_num
+    opt = so.default_opt(height=H, width=W, mesh_step_size=16)
+    trk = engine.Tracker(opt, device="cuda:0")
+    tex = synth.texture(H, W)
+    for t in (1, 2, 3):
+        fr = synth.frame_inputs(t, H, W, tex=tex, speed=3.0)
+        trk.step(torch.from_numpy(fr["depth"]).cuda(), torch.from_numpy(fr["color"]).cuda(),
+                 torch.from_numpy(fr["K"]), torch.from_numpy(fr["inv_K"]), fr["time"])
+    assert n_entry == trk.num_surfels()
+    assert torch.allclose(models.super.sf.points, trk.cur.points[:n_entry], atol=1e-9)
