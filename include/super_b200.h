@@ -40,6 +40,10 @@ typedef struct SbSurfels {
     unsigned char* stable;  /* (cap,)  bool */
     int cap;
     int* n_dev;             /* device row counter */
+    /* Semantic-SuPer state (NULL / 0 when absent): /root/reference/super/nodes.py:58-66 */
+    int* seg;               /* (cap,)   i32 class (reference: i64) */
+    double* seg_conf;       /* (cap,C)  f64 class probabilities */
+    int n_classes;          /* C <= 8 */
 } SbSurfels;
 
 /* One preprocessed input frame as dense per-pixel images (P = H*W). */
@@ -51,6 +55,8 @@ typedef struct SbFrame {
     const float* color;     /* (3,P) f32 planar             = inputs[("color",0)] */
     int H, W;
     double fx, fy, cx, cy;  /* K[0,0], K[1,1], K[0,2], K[1,2] (float32 values promoted) */
+    const int* seg;         /* (P,)   i32 argmax class per pixel, or NULL     = new_data.seg scattered */
+    const double* seg_conf; /* (P,C)  f64 softmax(scores) per pixel, or NULL  = new_data.seg_conf scattered */
 } SbFrame;
 
 typedef struct SbFuseParams {
@@ -58,6 +64,9 @@ typedef struct SbFuseParams {
     double th_cos;          /* opt.th_cosine_ang 0.4 */
     float time_now;         /* sfdata.time */
     int disable_merging_new, disable_merging_exist, disable_adding_new;
+    int class_gate;         /* merges need equal classes: (hard_seg or data == superv1) and seg present, nodes.py:314-316 */
+    int semantic_weights;   /* kNN weights softmax(sqrt(exp(-JSD)) sqrt(exp(-d/r))), nodes.py:183-189,466-484,505-511 */
+    const double* ed_seg_conf;  /* (J,C) f64 node class probabilities (semantic_weights) */
 } SbFuseParams;
 
 int sb_version(void);
@@ -79,6 +88,12 @@ int sb_knn_weights(const double* dist, const int* idx, int n_cap, const int* n_d
 /* Weights of existing surfels from current positions and old indices: /root/reference/super/nodes.py:480-484 */
 int sb_reweight(const double* points, const int* idx, int n_cap, const int* n_dev, const double* ed_points,
                 const double* radii, double* w, void* stream);
+
+/* Semantic variant of the weights (/root/reference/super/nodes.py:183-189, power_arg (1/2,1/2)):
+ * w = softmax_k( sqrt(exp(-JSD(ed_seg_conf[idx_k], seg_conf_i))) * sqrt(exp(-d_k / r_{idx_k})) ), d from the positions */
+int sb_reweight_semantic(const double* points, const int* idx, int n_cap, const int* n_dev, const double* ed_points,
+                         const double* radii, const double* ed_seg_conf, const double* seg_conf, int C, double* w,
+                         void* stream);
 
 /* Surfels.update (LM form): /root/reference/super/nodes.py:193-223 with Trans_points/transformQuatT
  * (/root/reference/super/utils.py:17-57).  In place on points, norms, ed_points, ed_norms. */
@@ -223,6 +238,10 @@ int sb_gf_global_update(double* points, double* norms, int n_cap, const int* n_d
 int sb_preprocess(const float* depth, const float* color, const unsigned char* inval, const float* inv_K3x3,
                   float fx, float divterm, int superv2, int H, int W, float* pcd_scratch, float* vmap, float* nmap,
                   double* radii, float* confs, int* valid_i32, void* stream);
+
+/* Per-pixel segmentation maps of a frame: seg = argmax_c scores, seg_conf = softmax_c scores
+ * (/root/reference/utils/data_loader.py:229-231,457).  scores (C,H,W) f64 -> seg (P,) i32, seg_conf (P,C) f64 */
+int sb_seg_maps(const double* scores, int C, int H, int W, int* seg, double* seg_conf, void* stream);
 
 /* ---- fusion / compaction ------------------------------------------------------------------------- */
 

@@ -99,6 +99,8 @@ __global__ void fill_kernel(int n_cap, const int* n_dev, const int* __restrict__
 struct Sample {
     double p[3], n[3], r;
     float c[3], w;
+    int cls;                 // class (semantic state) or -1
+    const double* conf;      // row of class probabilities or nullptr
 };
 
 __device__ __forceinline__ Sample load_surfel(const SbSurfels& sf, int i) {
@@ -110,6 +112,8 @@ __device__ __forceinline__ Sample load_surfel(const SbSurfels& sf, int i) {
     }
     s.r = sf.radii[i];
     s.w = sf.confs[i];
+    s.cls = sf.seg ? sf.seg[i] : -1;
+    s.conf = sf.seg_conf ? sf.seg_conf + (size_t)i * sf.n_classes : nullptr;
     return s;
 }
 
@@ -123,14 +127,17 @@ __device__ __forceinline__ Sample load_new(const SbFrame& fr, int p) {
     for (int k = 0; k < 3; ++k) s.c[k] = fr.color[k * P + p];
     s.r = fr.radii[p];
     s.w = fr.confs[p];
+    s.cls = fr.seg ? fr.seg[p] : -1;
+    s.conf = nullptr;        // set by the caller (needs the class count)
     return s;
 }
 
 // merge_data (nodes.py:301-355): test, then confidence-weighted blend written into surfel `dst`.
 // float32 quantities (confidence, colour, blend weights) are float here too.
 __device__ __forceinline__ bool try_merge(const SbSurfels& sf, int dst, const Sample& b, double th_dist,
-                                          double th_cos, float time_now, bool add_new) {
+                                          double th_cos, float time_now, bool add_new, bool class_gate) {
     const Sample a = load_surfel(sf, dst);
+    if (class_gate && sf.seg && b.cls >= 0 && a.cls != b.cls) return false;            // nodes.py:314-316
     const double dx = a.p[0] - b.p[0], dy = a.p[1] - b.p[1], dz = a.p[2] - b.p[2];
     const double dist = sqrt(dx * dx + dy * dy + dz * dz);
     const double cosang = (a.n[0] * b.n[0] + a.n[1] * b.n[1]) + a.n[2] * b.n[2];
@@ -158,6 +165,18 @@ __device__ __forceinline__ bool try_merge(const SbSurfels& sf, int dst, const Sa
             sf.colors[3 * (size_t)dst + k] = __fadd_rn(__fmul_rn(wa, a.c[k]), __fmul_rn(wb, b.c[k]));
     }
     sf.time_stamp[dst] = time_now;
+    if (sf.seg_conf && b.conf) {   // class probabilities: confidence-weighted, renormalised; class = argmax (nodes.py:345-353)
+        double sc[8], sum = 0.0;
+        const int C = sf.n_classes;
+        for (int q = 0; q < C; ++q) { sc[q] = (double)wa * a.conf[q] + (double)wb * b.conf[q]; sum += sc[q]; }
+        int am = 0;
+        for (int q = 0; q < C; ++q) {
+            sc[q] /= sum;
+            sf.seg_conf[(size_t)dst * C + q] = sc[q];
+            if (sc[q] > sc[am]) am = q;
+        }
+        sf.seg[dst] = am;
+    }
     return true;
 }
 
@@ -199,10 +218,11 @@ __global__ void fuse_pixels_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, co
 
     // ---- merge the new sample into the first layer that accepts it (nodes.py:409-422)
     if (new_valid && !pr.disable_merging_new) {
-        const Sample nw = load_new(fr, p);
+        Sample nw = load_new(fr, p);
+        if (fr.seg_conf) nw.conf = fr.seg_conf + (size_t)p * sf.n_classes;
         bool merged = false;
         for (int l = 0; l < m && !merged; ++l)
-            merged = try_merge(sf, ids[l], nw, pr.th_dist, pr.th_cos, pr.time_now, true);
+            merged = try_merge(sf, ids[l], nw, pr.th_dist, pr.th_cos, pr.time_now, true, pr.class_gate != 0);
         want_add = merged ? 0 : 1;
     }
     add_flag[p] = want_add;
@@ -217,7 +237,7 @@ __global__ void fuse_pixels_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, co
                 cur = cur && present[j];       // cumulative mask: val_map &= val_maps[j]
                 if (!cur) break;
                 const Sample sj = load_surfel(sf, ids[j]);
-                if (try_merge(sf, ids[i], sj, pr.th_dist, pr.th_cos, pr.time_now, false)) {
+                if (try_merge(sf, ids[i], sj, pr.th_dist, pr.th_cos, pr.time_now, false, pr.class_gate != 0)) {
                     present[j] = false;
                     sf.stable[ids[j]] = 0;
                     for (int k = 0; k < n_track; ++k)
@@ -303,10 +323,22 @@ __global__ void add_write_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, cons
     if (dst >= sf.cap) return;
     const Sample s = load_new(fr, p);
     double e[SB_KNN], mx = -INFINITY, sum = 0.0;
+    const int C = sf.n_classes;
+    const double* qc = fr.seg_conf ? fr.seg_conf + (size_t)p * C : nullptr;
     for (int k = 0; k < SB_KNN; ++k) {
         const int n_ = add_idx[4 * (size_t)p + k];
         sf.knn_idx[4 * (size_t)dst + k] = n_;
         e[k] = exp(-add_dist[4 * (size_t)p + k] / ed_radii[n_]);
+        if (pr.semantic_weights && qc) {                                 // nodes.py:505-509
+            const double* P = pr.ed_seg_conf + (size_t)n_ * C;
+            double k1 = 0.0, k2 = 0.0;
+            for (int q = 0; q < C; ++q) {
+                const double m = 0.5 * (P[q] + qc[q]);
+                k1 += P[q] * log(P[q] / (m + 1e-13) + 1e-13);
+                k2 += qc[q] * log(qc[q] / (m + 1e-13) + 1e-13);
+            }
+            e[k] = sqrt(exp(-0.5 * (k1 + k2))) * sqrt(e[k]);
+        }
         mx = fmax(mx, e[k]);
     }
     for (int k = 0; k < SB_KNN; ++k) { e[k] = exp(e[k] - mx); sum += e[k]; }
@@ -320,6 +352,9 @@ __global__ void add_write_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, cons
     sf.confs[dst] = s.w;
     sf.time_stamp[dst] = pr.time_now;
     sf.stable[dst] = 1;
+    if (sf.seg && fr.seg) sf.seg[dst] = fr.seg[p];
+    if (sf.seg_conf && qc)
+        for (int q = 0; q < C; ++q) sf.seg_conf[(size_t)dst * C + q] = qc[q];
 }
 
 // n_out = n when nothing is added
@@ -365,6 +400,9 @@ __global__ void compact_scatter_kernel(SbSurfels src, SbSurfels dst, SbFrame fr,
     dst.projdata[2 * (size_t)d] = (float)u;
     dst.projdata[2 * (size_t)d + 1] = (float)v;
     dst.stable[d] = disable_removing ? src.stable[i] : 1;
+    if (src.seg && dst.seg) dst.seg[d] = src.seg[i];
+    if (src.seg_conf && dst.seg_conf)
+        for (int q = 0; q < src.n_classes; ++q) dst.seg_conf[(size_t)d * src.n_classes + q] = src.seg_conf[(size_t)i * src.n_classes + q];
 }
 
 __global__ void track_remap_kernel(long long* track_id, int n_track, const int* keep, const int* pos, int disable) {
@@ -403,7 +441,14 @@ int sb_fuse(const SbSurfels* sfp, const SbFrame* frp, const double* ed_points, c
     fuse_pixels_kernel<<<gp, 256, 0, s>>>(sf, fr, pr, w.offsets, w.seg, w.add_flag, track_id, track_id ? n_track : 0);
     SB_CHECK_LAUNCH();
     // weights of ALL existing surfels from their fused positions and old indices (nodes.py:480-484)
-    int rc = sb_reweight(sf.points, sf.knn_idx, sf.cap, sf.n_dev, ed_points, ed_radii, sf.knn_w, stream);
+    int rc;
+    if (pr.semantic_weights) {
+        if (!pr.ed_seg_conf || !sf.seg_conf) return SB_ERR_ARG;
+        rc = sb_reweight_semantic(sf.points, sf.knn_idx, sf.cap, sf.n_dev, ed_points, ed_radii, pr.ed_seg_conf, sf.seg_conf,
+                                  sf.n_classes, sf.knn_w, stream);
+    } else {
+        rc = sb_reweight(sf.points, sf.knn_idx, sf.cap, sf.n_dev, ed_points, ed_radii, sf.knn_w, stream);
+    }
     if (rc) return rc;
     if (!pr.disable_adding_new && !pr.disable_merging_new) {
         add_knn_kernel<<<(P + ADD_BLOCK - 1) / ADD_BLOCK, ADD_BLOCK, 0, s>>>(fr, ed_points, ed_radii, J, w.add_flag,

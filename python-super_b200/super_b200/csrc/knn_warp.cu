@@ -158,6 +158,39 @@ __global__ void warp_surfels_kernel(double* __restrict__ points, double* __restr
     norms[3 * (size_t)i] = Nn.x / nn; norms[3 * (size_t)i + 1] = Nn.y / nn; norms[3 * (size_t)i + 2] = Nn.z / nn;
 }
 
+// JSD of two class distributions (utils/utils.py:244-254): KL(P|Q) = sum P log(P/(Q+eps)+eps), eps = 1e-13
+__device__ __forceinline__ double jsd_dev(const double* __restrict__ P, const double* __restrict__ Q, int C) {
+    double k1 = 0.0, k2 = 0.0;
+    for (int q = 0; q < C; ++q) {
+        const double m = 0.5 * (P[q] + Q[q]);
+        k1 += P[q] * log(P[q] / (m + 1e-13) + 1e-13);
+        k2 += Q[q] * log(Q[q] / (m + 1e-13) + 1e-13);
+    }
+    return 0.5 * (k1 + k2);
+}
+
+// semantic kNN weights (nodes.py:183-189): softmax_k( exp(-JSD)^(1/2) * exp(-d/r)^(1/2) )
+__global__ void reweight_semantic_kernel(const double* __restrict__ points, const int* __restrict__ idx, int n_cap,
+                                         const int* n_dev, const double* __restrict__ ed_points,
+                                         const double* __restrict__ radii, const double* __restrict__ ed_seg_conf,
+                                         const double* __restrict__ seg_conf, int C, double* __restrict__ w) {
+    const int n = n_active(n_cap, n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double e[SB_KNN], mx = -INFINITY, sum = 0.0;
+    for (int k = 0; k < SB_KNN; ++k) {
+        const int n_ = idx[4 * (size_t)i + k];
+        const double dx = points[3 * (size_t)i] - ed_points[3 * n_], dy = points[3 * (size_t)i + 1] - ed_points[3 * n_ + 1],
+                     dz = points[3 * (size_t)i + 2] - ed_points[3 * n_ + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        const double js = jsd_dev(ed_seg_conf + (size_t)n_ * C, seg_conf + (size_t)i * C, C);
+        e[k] = sqrt(exp(-js)) * sqrt(exp(-d / radii[n_]));
+        mx = fmax(mx, e[k]);
+    }
+    for (int k = 0; k < SB_KNN; ++k) { e[k] = exp(e[k] - mx); sum += e[k]; }
+    for (int k = 0; k < SB_KNN; ++k) w[4 * (size_t)i + k] = e[k] / sum;
+}
+
 // ED nodes: points += b; norms <- normalize(R(q) n)          (nodes.py:215-223)
 __global__ void warp_nodes_kernel(double* __restrict__ ed_points, double* __restrict__ ed_norms,
                                   const double* __restrict__ beta, int J) {
@@ -209,6 +242,17 @@ int sb_reweight(const double* points, const int* idx, int n_cap, const int* n_de
     if (n_cap <= 0) return SB_OK;
     reweight_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, idx, n_cap, n_dev, ed_points,
                                                                           radii, w);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_reweight_semantic(const double* points, const int* idx, int n_cap, const int* n_dev, const double* ed_points,
+                         const double* radii, const double* ed_seg_conf, const double* seg_conf, int C, double* w,
+                         void* stream) {
+    if (!points || !idx || !ed_points || !radii || !ed_seg_conf || !seg_conf || !w || C < 1 || C > 8) return SB_ERR_ARG;
+    if (n_cap <= 0) return SB_OK;
+    reweight_semantic_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, idx, n_cap, n_dev, ed_points,
+                                                                                   radii, ed_seg_conf, seg_conf, C, w);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

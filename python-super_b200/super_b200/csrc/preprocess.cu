@@ -119,9 +119,35 @@ __global__ void normals_kernel(PreArgs a, const float4* __restrict__ pcd, float4
     if (valid_i32) valid_i32[p] = valid ? 1 : 0;
 }
 
+// seg = argmax_c scores (first maximum), seg_conf = softmax_c scores     (data_loader.py:229-231,457)
+__global__ void seg_maps_kernel(const double* __restrict__ scores, int C, int P, int* __restrict__ seg,
+                                double* __restrict__ conf) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double mx = -INFINITY;
+    int am = 0;
+    for (int c = 0; c < C; ++c) {
+        const double v = scores[(size_t)c * P + p];
+        if (v > mx) { mx = v; am = c; }
+    }
+    double sum = 0.0, e[8];
+    for (int c = 0; c < C; ++c) { e[c] = exp(scores[(size_t)c * P + p] - mx); sum += e[c]; }
+    for (int c = 0; c < C; ++c) conf[(size_t)p * C + c] = e[c] / sum;
+    seg[p] = am;
+}
+
 }  // namespace
 
 extern "C" {
+
+int sb_seg_maps(const double* scores, int C, int H, int W, int* seg, double* seg_conf, void* stream) {
+    if (!scores || !seg || !seg_conf || C < 1 || C > 8 || H <= 0 || W <= 0) return SB_ERR_ARG;
+    const int P = H * W;
+    seg_maps_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scores, C, P, seg, seg_conf);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
 
 int sb_preprocess(const float* depth, const float* color, const unsigned char* inval, const float* inv_K3x3,
                   float fx, float divterm, int superv2, int H, int W, float* pcd_scratch, float* vmap, float* nmap,

@@ -27,18 +27,21 @@ F64, F32, I32, I64, U8 = torch.float64, torch.float32, torch.int32, torch.int64,
 class SbSurfels(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("points", "norms", "colors", "confs", "radii", "time_stamp",
                                                "knn_idx", "knn_w", "projdata", "stable")] + \
-               [("cap", ctypes.c_int), ("n_dev", ctypes.c_void_p)]
+               [("cap", ctypes.c_int), ("n_dev", ctypes.c_void_p), ("seg", ctypes.c_void_p),
+                ("seg_conf", ctypes.c_void_p), ("n_classes", ctypes.c_int)]
 
 
 class SbFrame(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("vmap", "nmap", "radii", "confs", "color")] + \
-               [("H", ctypes.c_int), ("W", ctypes.c_int)] + [(n, ctypes.c_double) for n in ("fx", "fy", "cx", "cy")]
+               [("H", ctypes.c_int), ("W", ctypes.c_int)] + [(n, ctypes.c_double) for n in ("fx", "fy", "cx", "cy")] + \
+               [("seg", ctypes.c_void_p), ("seg_conf", ctypes.c_void_p)]
 
 
 class SbFuseParams(ctypes.Structure):
     _fields_ = [("th_dist", ctypes.c_double), ("th_cos", ctypes.c_double), ("time_now", ctypes.c_float),
                 ("disable_merging_new", ctypes.c_int), ("disable_merging_exist", ctypes.c_int),
-                ("disable_adding_new", ctypes.c_int)]
+                ("disable_adding_new", ctypes.c_int), ("class_gate", ctypes.c_int), ("semantic_weights", ctypes.c_int),
+                ("ed_seg_conf", ctypes.c_void_p)]
 
 
 SURFEL_FIELDS = (("points", 3, F64), ("norms", 3, F64), ("colors", 3, F32), ("confs", 0, F32), ("radii", 0, F64),
@@ -49,13 +52,17 @@ SURFEL_FIELDS = (("points", 3, F64), ("norms", 3, F64), ("colors", 3, F32), ("co
 class SurfelBuffers:
     """One capacity-sized set of surfel arrays + its device row counter."""
 
-    def __init__(self, cap, device):
+    def __init__(self, cap, device, n_classes=0):
         self.cap = int(cap)
         for name, width, dt in SURFEL_FIELDS:
             shape = (self.cap, width) if width else (self.cap,)
             setattr(self, name, torch.zeros(shape, dtype=dt, device=device))
         self.n_dev = torch.zeros(1, dtype=I32, device=device)
-        self.c = SbSurfels(*[ptr(getattr(self, n)) for n, _, _ in SURFEL_FIELDS], self.cap, ptr(self.n_dev))
+        self.n_classes = int(n_classes)
+        self.seg = torch.zeros(self.cap, dtype=I32, device=device) if n_classes else None          # Semantic-SuPer state
+        self.seg_conf = torch.zeros((self.cap, n_classes), dtype=F64, device=device) if n_classes else None
+        self.c = SbSurfels(*[ptr(getattr(self, n)) for n, _, _ in SURFEL_FIELDS], self.cap, ptr(self.n_dev),
+                           ptr(self.seg), ptr(self.seg_conf), self.n_classes)
 
     def ref(self):
         return ctypes.byref(self.c)
@@ -77,11 +84,14 @@ class Frame:
         self.cam = None
         self.time = 0.0
         self.c = None
+        self.seg = None          # (P,) i32, (P,C) f64, (C,H,W) f64 scores: semantic inputs (preprocess fills them)
+        self.seg_conf = None
+        self.scores = None
 
     def bind(self, color, cam, time):
         self.color, self.cam, self.time = color, cam, float(time)
         self.c = SbFrame(ptr(self.vmap), ptr(self.nmap), ptr(self.radii), ptr(self.confs), ptr(color), self.H,
-                         self.W, cam.fx, cam.fy, cam.cx, cam.cy)
+                         self.W, cam.fx, cam.fy, cam.cx, cam.cy, ptr(self.seg), ptr(self.seg_conf))
 
     def ref(self):
         return ctypes.byref(self.c)
@@ -91,7 +101,8 @@ class Frame:
         return self.vmap[:, 3] != 0
 
 
-def preprocess(opt, depth, color, K, inv_K, time, frame=None, inval=None, divterm=1.0 / (2.0 * 0.6 * 0.6)):
+def preprocess(opt, depth, color, K, inv_K, time, frame=None, inval=None, divterm=1.0 / (2.0 * 0.6 * 0.6),
+               seg_scores=None):
     """depth_preprocessing (/root/reference/utils/data_loader.py:333-523) on the device.
     depth (H,W) f32, color (3,H,W) f32 CUDA tensors; K, inv_K (4,4) f32 host or device tensors."""
     H, W = opt.height, opt.width
@@ -107,6 +118,16 @@ def preprocess(opt, depth, color, K, inv_K, time, frame=None, inval=None, divter
     call("sb_preprocess", ptr(depth), ptr(color), ptr(inval), ik, float(Kh[0, 0]), float(divterm),
          1 if opt.data == "superv2" else 0, H, W, ptr(frame.pcd), ptr(frame.vmap), ptr(frame.nmap), ptr(frame.radii),
          ptr(frame.confs), ptr(frame.valid_i32), stream())
+    if seg_scores is not None:           # inputs[("seg_conf", 0)]: (C,H,W) f64 class scores
+        sc = seg_scores.reshape(-1, H, W).to(F64).contiguous()
+        C = sc.shape[0]
+        if frame.seg is None or frame.seg_conf.shape[1] != C:
+            frame.seg = torch.zeros(frame.P, dtype=I32, device=dev)
+            frame.seg_conf = torch.zeros((frame.P, C), dtype=F64, device=dev)
+        frame.scores = sc
+        call("sb_seg_maps", ptr(sc), C, H, W, ptr(frame.seg), ptr(frame.seg_conf), stream())
+    else:
+        frame.seg = frame.seg_conf = frame.scores = None
     frame.bind(color, cam, time)
     return frame
 
@@ -155,6 +176,12 @@ def build_graph(opt, frame):
     g = NS()
     g.points = frame.vmap[pix, :3].to(F64).contiguous()
     g.norms = frame.nmap[pix, :3].to(F64).contiguous()
+    if frame.seg_conf is not None:                       # graph_encoder.py:134-150,190-192
+        g.seg_conf = frame.seg_conf[pix].contiguous()
+        g.seg = torch.argmax(g.seg_conf, dim=1)
+        if getattr(opt, "hard_seg", False) and opt.mesh_face:   # no edges / faces across classes
+            e = e[g.seg[e[:, 0]] == g.seg[e[:, 1]]]
+            f = f[(g.seg[f[:, 0]] == g.seg[f[:, 1]]) & (g.seg[f[:, 0]] == g.seg[f[:, 2]])]
     g.edge_index, g.triangles = e.t().contiguous(), f.t().contiguous()
     lens = torch.linalg.norm(g.points[e[:, 0]] - g.points[e[:, 1]], dim=1)
     ssum = torch.zeros(J, dtype=F64, device=dev).index_add_(0, e.reshape(-1), lens.repeat_interleave(2))
@@ -264,7 +291,10 @@ class Tracker:
         """Surfels.__init__ + update_sfed_knn + first compaction (nodes.py:93-191, super.py:60-63)."""
         opt, dev = self.opt, self.dev
         self.ED = build_graph(opt, frame)
-        self.cur, self.alt = SurfelBuffers(self.cap, dev), SurfelBuffers(self.cap, dev)
+        self.semantic = frame.seg_conf is not None
+        C = frame.seg_conf.shape[1] if self.semantic else 0
+        self.sem_weights = self.semantic and getattr(opt, "method", "super") == "semantic-super"
+        self.cur, self.alt = SurfelBuffers(self.cap, dev, C), SurfelBuffers(self.cap, dev, C)
         self.fuse_ws = torch.zeros(int(lib.load().sb_fuse_workspace_bytes(self.H, self.W, self.cap)), dtype=U8, device=dev)
         valid = frame.valid
         n = int(valid.sum())                               # init only: a sync is fine here
@@ -281,7 +311,13 @@ class Tracker:
         b.n_dev.fill_(n)
         dist, idx = ops.knn(b.points[:n], self.ED.points, opt.num_neighbors)
         b.knn_idx[:n] = idx
-        b.knn_w[:n] = ops.knn_weights(dist, idx, self.ED.radii, 0, b.stable)
+        b.knn_w[:n] = ops.knn_weights(dist, idx, self.ED.radii, 0, b.stable)      # also clears stable (radius test)
+        if self.semantic:
+            b.seg[:n] = frame.seg[valid]
+            b.seg_conf[:n] = frame.seg_conf[valid]
+            if self.sem_weights and not getattr(opt, "hard_seg", False):          # nodes.py:183-189
+                call("sb_reweight_semantic", ptr(b.points), ptr(b.knn_idx), n, None, ptr(self.ED.points),
+                     ptr(self.ED.radii), ptr(self.ED.seg_conf), ptr(b.seg_conf), C, ptr(b.knn_w), stream())
         # projdata of the init frame = pixel coordinates (x,y) of the valid pixels (nodes.py:143-145)
         pix = valid.nonzero()[:, 0]
         b.projdata[:n, 0] = (pix % self.W).to(F32)
@@ -323,14 +359,19 @@ class Tracker:
                             n_dev=self.cur.n_dev)
         else:
             # autograd configuration of the reference (GraphFit, super.py:70-71): fused loss+gradient kernels
-            if getattr(opt, "method", "super") == "semantic-super":
-                raise NotImplementedError("the device tracker does not carry per-surfel segmentation state yet: "
-                                          "call super_b200.graphfit.graph_fit with explicit seg arrays")
+            seg = None
+            if self.semantic and (getattr(opt, "sf_soft_seg_point_plane", False) or
+                                  getattr(opt, "sf_hard_seg_point_plane", False) or getattr(opt, "sf_bn_morph", False)):
+                seg = NS(sf_seg=self.cur.seg[: self.n_bound], sf_seg_conf=self.cur.seg_conf[: self.n_bound],
+                         trg_seg_conf=frame.seg_conf, scores=frame.scores, edge_pts=None, edge_off=None)
+                if getattr(opt, "sf_bn_morph", False):
+                    seg.edge_pts, seg.edge_off = graphfit.edge_points(frame.seg.view(self.H, self.W), opt.num_classes,
+                                                                      self.H, self.W)
             sfv.isStable = self.cur.stable[: self.n_bound]
             sfv.ED = NS(points=self.ED.points, knn_indices=self.ED.knn_indices, knn_w=self.ED.knn_w,
                         triangles=self.ED.triangles_i32, triangles_areas=self.ED.triangles_areas)
             beta, self.gf_ws = graphfit.graph_fit(sfv, (frame.vmap, frame.nmap), frame.cam, opt,
-                                                  ws=getattr(self, "gf_ws", None), n_dev=self.cur.n_dev)
+                                                  ws=getattr(self, "gf_ws", None), n_dev=self.cur.n_dev, seg=seg)
             self.last_beta = beta
             J = self.ED.num
             ops.warp_update(self.cur.points[: self.n_bound], self.cur.norms[: self.n_bound],
@@ -338,8 +379,7 @@ class Tracker:
                             self.ED.norms, beta[:J], n_dev=self.cur.n_dev)
             graphfit.update_global(self.cur.points[: self.n_bound], self.cur.norms[: self.n_bound], self.ED.points,
                                    self.ED.norms, beta, n_dev=self.cur.n_dev)
-        pr = SbFuseParams(opt.th_dist, opt.th_cosine_ang, float(frame.time), int(bool(opt.disable_merging_new_surfels)),
-                          int(bool(opt.disable_merging_exist_surfels)), int(bool(opt.disable_adding_new_surfels)))
+        pr = self.fuse_params(frame)
         call("sb_fuse", self.cur.ref(), frame.ref(), ptr(self.ED.points), ptr(self.ED.radii), self.ED.num,
              ctypes.byref(pr), ptr(self.track_id), 0 if self.track_id is None else self.track_id.numel(),
              ptr(self.n_tmp), ptr(self.overflow), ptr(self.fuse_ws), self.fuse_ws.numel(), stream())
@@ -350,14 +390,26 @@ class Tracker:
         self._publish_count()
         return beta
 
+    def fuse_params(self, frame):
+        """merge thresholds + the semantic switches of fuseInputData (nodes.py:314-316,466-484,505-511)."""
+        opt = self.opt
+        sem = bool(getattr(self, "semantic", False))
+        gate = sem and (bool(getattr(opt, "hard_seg", False)) or opt.data == "superv1")
+        semw = sem and bool(getattr(self, "sem_weights", False))
+        return SbFuseParams(opt.th_dist, opt.th_cosine_ang, float(frame.time), int(bool(opt.disable_merging_new_surfels)),
+                            int(bool(opt.disable_merging_exist_surfels)), int(bool(opt.disable_adding_new_surfels)),
+                            int(gate), int(semw), ptr(self.ED.seg_conf) if semw else None)
+
     def view(self, n):
         """Views of the first n rows of the current buffers, in the layouts the LM solver takes."""
         b = self.cur
         return NS(points=b.points[:n], norms=b.norms[:n], knn_indices=b.knn_idx[:n], knn_w=b.knn_w[:n], ED=self.ED)
 
-    def step(self, depth, color, K, inv_K, time, inval=None):
-        """One SuPer.forward: preprocess + (init | track).  Returns beta or None."""
-        frame = preprocess(self.opt, depth, color, K, inv_K, time, frame=self.next_frame(), inval=inval)
+    def step(self, depth, color, K, inv_K, time, inval=None, seg_scores=None):
+        """One SuPer.forward: preprocess + (init | track).  Returns beta or None.  seg_scores: (C,H,W) class scores
+        (inputs[("seg_conf",0)]) for the Semantic-SuPer configuration."""
+        frame = preprocess(self.opt, depth, color, K, inv_K, time, frame=self.next_frame(), inval=inval,
+                           seg_scores=seg_scores)
         if self.cur is None:
             self.init(frame)
             return None
@@ -370,4 +422,7 @@ class Tracker:
         out = {name: getattr(b, name)[:n].clone() for name, _, _ in SURFEL_FIELDS}
         out["knn_indices"] = out.pop("knn_idx").to(I64)
         out["isStable"] = out.pop("stable").bool()
+        if b.seg is not None:
+            out["seg"] = b.seg[:n].to(I64)
+            out["seg_conf"] = b.seg_conf[:n].clone()
         return out

@@ -47,6 +47,14 @@ class Surfels:
         return self._trk.cur.knn_idx[: self._trk.num_surfels()].to(torch.int64)
 
     @property
+    def seg(self):
+        return self._trk.cur.seg[: self._trk.num_surfels()].to(torch.int64)
+
+    @property
+    def seg_conf(self):
+        return self._trk.cur.seg_conf[: self._trk.num_surfels()]
+
+    @property
     def isStable(self):
         return self._trk.cur.stable[: self._trk.num_surfels()].bool()
 

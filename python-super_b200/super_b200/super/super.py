@@ -50,7 +50,8 @@ class SuPer(torch.nn.Module):
         inval = engine.extra_invalid_mask(self.opt, depth, seg=seg, mask=inputs.get("valid_mask"))
         frame = engine.preprocess(self.opt, depth, color, inputs["K"], inputs["inv_K"], time,
                                   frame=self._trk.next_frame(), inval=inval,
-                                  divterm=inputs.get("divterm", 1.0 / (2.0 * 0.6 * 0.6)))
+                                  divterm=inputs.get("divterm", 1.0 / (2.0 * 0.6 * 0.6)),
+                                  seg_scores=inputs.get(("seg_conf", 0)))
         self.last_frame = frame
         if self._trk.cur is None:
             self._trk.init(frame)

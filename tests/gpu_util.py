@@ -45,6 +45,13 @@ def frame_from_newdata(nd, frame_np, H, W, dev="cuda"):
     fr.radii[valid] = nd.radii.to(dev)
     fr.confs[valid] = nd.confs.to(dev)
     color = torch.from_numpy(frame_np["color"]).to(dev).contiguous()
+    if hasattr(nd, "seg_conf"):
+        C = nd.seg_conf.shape[1]
+        fr.seg = torch.zeros(H * W, dtype=torch.int32, device=dev)
+        fr.seg_conf = torch.zeros((H * W, C), dtype=torch.float64, device=dev)
+        fr.seg[valid] = nd.seg.to(torch.int32).to(dev)
+        fr.seg_conf[valid] = nd.seg_conf.to(dev)
+        fr.scores = nd.seg_conf_in[0].to(dev).contiguous()
     fr.bind(color, camera(nd, H, W), float(frame_np["time"]))
     return fr
 
@@ -54,16 +61,23 @@ def tracker_from_state(opt, sf, dev="cuda"):
     from super_b200 import engine, lib
     trk = engine.Tracker(opt, device=dev)
     n = len(sf.points)
-    trk.cur, trk.alt = engine.SurfelBuffers(trk.cap, trk.dev), engine.SurfelBuffers(trk.cap, trk.dev)
+    C = sf.seg_conf.shape[1] if hasattr(sf, "seg_conf") else 0
+    trk.semantic = C > 0
+    trk.sem_weights = trk.semantic and getattr(opt, "method", "super") == "semantic-super"
+    trk.cur, trk.alt = engine.SurfelBuffers(trk.cap, trk.dev, C), engine.SurfelBuffers(trk.cap, trk.dev, C)
     trk.fuse_ws = torch.zeros(int(lib.load().sb_fuse_workspace_bytes(trk.H, trk.W, trk.cap)), dtype=torch.uint8, device=dev)
     b = trk.cur
     b.points[:n] = sf.points.to(dev); b.norms[:n] = sf.norms.to(dev); b.colors[:n] = sf.colors.to(dev)
     b.confs[:n] = sf.confs.to(dev); b.radii[:n] = sf.radii.to(dev); b.time_stamp[:n] = sf.time_stamp.to(dev)
     b.knn_idx[:n] = sf.knn_indices.to(torch.int32).to(dev); b.knn_w[:n] = sf.knn_w.to(dev)
     b.projdata[:n] = sf.projdata.to(dev); b.stable[:n] = sf.isStable.to(torch.uint8).to(dev)
+    if C:
+        b.seg[:n] = sf.seg.to(torch.int32).to(dev); b.seg_conf[:n] = sf.seg_conf.to(dev)
     b.n_dev.fill_(n)
     trk.n_bound = n
     trk.ED = to_device_state(sf).ED
+    if C:
+        trk.ED.seg_conf = sf.ED.seg_conf.to(dev).contiguous()
     trk.ED.num = sf.ED.num
     trk.ED.node_pos = None
     trk._publish_count()

@@ -111,3 +111,67 @@ def test_free_running_autograd_tracker_follows_oracle():
         assert rel < 1e-4, (t, mine[-1]["total"], tr[-1]["loss"])
         assert (beta.cpu() - dv).abs().max() < 1e-6
         assert trk.num_surfels() == len(sf.points)
+
+
+def test_semantic_fuse_and_compact_match_reference():
+    """Semantic-SuPer state through fusion and compaction, teacher-forced with the reference's pre-frame state and
+    deform_verts (gf_sem fixture): class probabilities are merged with the confidences, classes follow the argmax,
+    the kNN weights are the JSD-modulated ones (nodes.py:183-189,345-353,466-484,505-511)."""
+    import ctypes
+    from super_b200 import graphfit, ops
+    from super_b200.lib import call, ptr, stream
+    from gpu_util import frame_from_newdata, tracker_from_state
+    g = Golden("gf_sem_128x96")
+    for t in g.frames[1:]:
+        sf, nd = g.state(t - 1), g.new_data(t)
+        trk = tracker_from_state(g.opt, sf)
+        fr = frame_from_newdata(nd, g.frame(t), g.H, g.W)
+        dv = torch.from_numpy(g[f"f{t}.beta"].copy()).cuda()
+        v = trk.view(trk.n_bound)
+        ops.warp_update(v.points, v.norms, v.knn_indices, v.knn_w, trk.ED.points, trk.ED.norms, dv[:-1].contiguous(),
+                        n_dev=trk.cur.n_dev)
+        graphfit.update_global(v.points, v.norms, trk.ED.points, trk.ED.norms, dv, n_dev=trk.cur.n_dev)
+        pr = trk.fuse_params(fr)
+        assert pr.semantic_weights == 1 and pr.class_gate == 0          # superv2, no --hard_seg
+        call("sb_fuse", trk.cur.ref(), fr.ref(), ptr(trk.ED.points), ptr(trk.ED.radii), trk.ED.num, ctypes.byref(pr),
+             None, 0, ptr(trk.n_tmp), ptr(trk.overflow), ptr(trk.fuse_ws), trk.fuse_ws.numel(), stream())
+        trk.cur.n_dev.copy_(trk.n_tmp)
+        trk._compact(fr)
+        ref = g.state(t)
+        snap = trk.snapshot()
+        assert len(snap["points"]) == len(ref.points)
+        assert torch.equal(snap["knn_indices"].cpu(), ref.knn_indices)
+        assert torch.equal(snap["seg"].cpu(), ref.seg)
+        for k, tol in (("points", 1e-13), ("norms", 1e-13), ("knn_w", 1e-12), ("seg_conf", 1e-13), ("confs", 1e-6)):
+            err = float((snap[k].cpu().double() - getattr(ref, k).double()).abs().max())
+            assert err <= tol, f"frame {t} {k}: max|d| = {err:g}"
+
+
+def test_free_running_semantic_tracker_follows_oracle():
+    """Config 4 shape end to end on the device (superv2, SGD, soft-seg point-plane + rot + face + boundary-morph,
+    semantic kNN weights and fusion) against the CPU port, free running."""
+    from oracle import graphfit_oracle as gfo
+    from super_b200 import engine, synth
+    g = Golden("gf_sem_128x96")
+    opt, H, W = g.opt, g.H, g.W
+    trk = engine.Tracker(opt, device="cuda:0")
+    sf = None
+    for t in (1, 2, 3):
+        fr = g.frame(t)
+        nd = so.preprocess(opt, fr)
+        beta = trk.step(torch.from_numpy(fr["depth"]).cuda(), torch.from_numpy(fr["color"]).cuda(),
+                        torch.from_numpy(fr["K"]), torch.from_numpy(fr["inv_K"]), fr["time"],
+                        seg_scores=torch.from_numpy(fr["seg_conf"]).cuda())
+        if sf is None:
+            sf = so.init_surfels(opt, nd, so.build_graph(opt, nd))
+            assert trk.num_surfels() == len(sf.points)
+            assert (trk.cur.knn_w[: len(sf.points)].cpu() - sf.knn_w).abs().max() < 1e-12
+            continue
+        tr = []
+        dv = gfo.graph_fit(opt, sf, nd, trace=tr)
+        so.update(opt, sf, dv); so.fuse(opt, sf, nd); so.compact(opt, sf, float(fr["time"]))
+        mine = trk.gf_ws.read_trace(opt.num_optimize_iterations)
+        rel = abs(mine[-1]["total"] - tr[-1]["loss"]) / tr[-1]["loss"]
+        assert rel < 1e-4, (t, mine[-1], tr[-1])
+        assert (beta.cpu() - dv).abs().max() < 1e-6
+        assert trk.num_surfels() == len(sf.points)
