@@ -224,6 +224,13 @@ def run_cuda(args, rank, world, local_rank):
     jt_avg_ms = float(np.mean(jt_ms)) if jt_ms else None
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = (b_pass / 1e9) / (jt_avg_ms / 1e3) if jt_avg_ms else None
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1c_jtj_traffic.json")
+    if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_note = (f"ncu capture at {tj['surfels_at_capture']} surfels (algorithmic bytes there "
+                        f"{tj['algorithmic_bytes_at_capture']}): {tj['source']}")
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "ms_per_lm_iteration": (total_ms / K) / LM_ITERS,
@@ -240,7 +247,7 @@ def run_cuda(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"kernel": "data_jtj_kernel (fused warp+project+bilinear+Jacobian+J^T J, one LM iteration)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
                      "algorithmic_bytes": b_pass, "launch_ms": jt_avg_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
         "solver": solver_report(trk, solve_ms),
