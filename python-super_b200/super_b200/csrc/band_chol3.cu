@@ -270,28 +270,32 @@ __device__ __forceinline__ bool warp_potrf_blocked(double* __restrict__ D, doubl
         __syncwarp();
         if (ts) { if (x[7] + p[7] != 1.2345e300) q1 = clock64(); ts[5] += q1 - tbase; tbase = q1; }
         if (b < 3) {
-            // D[i][j] -= sum_{t in block b} L[i][t] L[j][t] for every lower 8x8 block right of b, all at once: the
-            // (up to six) accumulator chains are independent, so the whole update costs one LDS -> 2 DMMA -> RMW
-            // round instead of one per block column
+            // D[i][b+1] -= sum_{t in block b} L[i][t] L[b+1][t] for the NEXT block column only (rows b+1..3); the helper
+            // warps update the block columns further right behind us and have finished the previous round (barrier 4+b)
+            bar_sync(4 + b, 128);
             double af[3][2];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) af[r][ks] = (r + 1 > b) ? Lcol[(c0 + 4 * ks + fc) * S36 + 8 * (r + 1) + fr] : 0.0;
-            double acc[6][2];
+            double acc[3][2];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q][0] = acc[q][1] = 0.0;
+            for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-                for (int q = 0; q < 6; ++q)
-                    if (pair_j(q) > b) dmma884(acc[q][0], acc[q][1], af[pair_i(q) - 1][ks], af[pair_j(q) - 1][ks]);
+                for (int r = 0; r < 3; ++r)
+                    if (r + 1 > b) {
+                        // rows block r+1, columns block b+1: operand B = rows of block b+1 = af[b] (b is a run-time value)
+                        const double bf = (b == 0) ? af[0][ks] : (b == 1) ? af[1][ks] : af[2][ks];
+                        dmma884(acc[r][0], acc[r][1], af[r][ks], bf);
+                    }
 #pragma unroll
-            for (int q = 0; q < 6; ++q)
-                if (pair_j(q) > b) {
-                    double* dd = D + (8 * pair_i(q) + fr) * S33 + 8 * pair_j(q) + 2 * fc;
-                    dd[0] -= acc[q][0];
-                    dd[1] -= acc[q][1];
+            for (int r = 0; r < 3; ++r)
+                if (r + 1 > b) {
+                    double* dd = D + (8 * (r + 1) + fr) * S33 + 8 * (b + 1) + 2 * fc;
+                    dd[0] -= acc[r][0];
+                    dd[1] -= acc[r][1];
                 }
             __syncwarp();
         }
@@ -438,6 +442,55 @@ __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const vola
 #undef WPROF
 }
 
+// D[8bi.., 8bj..] -= Lx[8bi..] Lx[8bj..]^T for up to two lower blocks (bi0,bj0), (bi1,bj1) (bi1 < 0: one block), with the
+// damping / identity padding on diagonal entries; the two accumulator chains are interleaved
+__device__ __forceinline__ void syrk_blocks(const double* __restrict__ Lx, double* __restrict__ D, bool has_prev, int bi0,
+                                            int bj0, int bi1, int bj1, int k, int n, double u, int lane) {
+    const int fr = lane >> 2, fc = lane & 3;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    if (has_prev) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            dmma884(a0, a1, Lx[(8 * bi0 + fr) * S36 + 4 * ks + fc], Lx[(8 * bj0 + fr) * S36 + 4 * ks + fc]);
+            if (bi1 >= 0) dmma884(b0, b1, Lx[(8 * bi1 + fr) * S36 + 4 * ks + fc], Lx[(8 * bj1 + fr) * S36 + 4 * ks + fc]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q == 1 && bi1 < 0) break;
+        const int i = 8 * (q ? bi1 : bi0) + fr, j = 8 * (q ? bj1 : bj0) + 2 * fc, gi = NB * k + i;
+        double v0 = D[i * S33 + j] - (q ? b0 : a0), v1 = D[i * S33 + j + 1] - (q ? b1 : a1);
+        if (i == j) v0 = (gi < n) ? v0 + u : 1.0;
+        if (i == j + 1) v1 = (gi < n) ? v1 + u : 1.0;
+        D[i * S33 + j] = v0;
+        D[i * S33 + j + 1] = v1;
+    }
+}
+
+// helper warp: once block column b of L exists (its last pivot is the ready flag), D[8oi.., 8oj..] -= L[8oi.., blk b] L[8oj.., blk b]^T
+__device__ __forceinline__ void helper_trailing(double* __restrict__ D, const double* Lcol, const volatile double* dinvs, int b,
+                                                int oi, int oj, int lane, bool active) {
+    const int fr = lane >> 2, fc = lane & 3, c0 = 8 * b;
+    int spins = 0;
+    double dq = dinvs[c0 + 7];
+    while (dq != dq && ++spins < (1 << 20)) dq = dinvs[c0 + 7];
+    asm volatile("" ::: "memory");
+    if (!active) return;
+    for (int tries = 0; tries < 4; ++tries) {
+        double c0_ = 0.0, c1_ = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            dmma884(c0_, c1_, ((const volatile double*)Lcol)[(c0 + 4 * ks + fc) * S36 + 8 * oi + fr],
+                    ((const volatile double*)Lcol)[(c0 + 4 * ks + fc) * S36 + 8 * oj + fr]);
+        if (__any_sync(FULL, (c0_ != c0_) || (c1_ != c1_)) && tries < 3) continue;     // a value not yet visible: re-read
+        double* dd = D + (8 * oi + fr) * S33 + 8 * oj + 2 * fc;
+        dd[0] -= c0_;
+        dd[1] -= c1_;
+        break;
+    }
+    __syncwarp();
+}
+
 // =====================================================================================================
 // P: the pivot chain.  Warp roles: 0 Cholesky (+DMMA), 1 inverse builder, {0,2,3,5} DMMA products,
 // {4,6,7} I/O (flags, L(k,k-1) store, staging of the next panel's tiles).
@@ -506,47 +559,25 @@ __device__ void role_P(const Args3& a, double* smem) {
             bar_sync(2, 128);
             bar_arrive(1, 224);                            // I/O warps may store L(k,k-1)
             PROF(2);
-            {
-                // lower 8x8 blocks dealt 3,3,2,2; the accumulator chains of a warp's blocks are interleaved
-                const int nblk = (cw < 2) ? 3 : 2;
-                const int bis[4][3] = {{0, 2, 3}, {1, 2, 3}, {1, 3, 0}, {2, 3, 0}};
-                const int bjs[4][3] = {{0, 1, 2}, {0, 2, 3}, {1, 0, 0}, {0, 1, 0}};
-                const int fr = lane >> 2, fc = lane & 3;
-                int bi[3], bj[3];
-                double acc[3][2];
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    bi[b] = bj[b] = 0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c == cw) { bi[b] = bis[c][b]; bj[b] = bjs[c][b]; }
-                    acc[b][0] = acc[b][1] = 0.0;
-                }
-                if (k >= 1) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                        for (int b = 0; b < 3; ++b)
-                            if (b < nblk)
-                                dmma884(acc[b][0], acc[b][1], Lx[(8 * bi[b] + fr) * S36 + 4 * ks + fc],
-                                        Lx[(8 * bj[b] + fr) * S36 + 4 * ks + fc]);
-                }
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    if (b >= nblk) break;
-                    const int i = 8 * bi[b] + fr, j = 8 * bj[b] + 2 * fc, gi = NB * k + i;
-                    double v0 = D[i * S33 + j] - acc[b][0], v1 = D[i * S33 + j + 1] - acc[b][1];
-                    if (i == j) v0 = (gi < n) ? v0 + u : 1.0;
-                    if (i == j + 1) v1 = (gi < n) ? v1 + u : 1.0;
-                    D[i * S33 + j] = v0;
-                    D[i * S33 + j + 1] = v1;
-                }
-            }
+            // D -= L(k,k-1) L(k,k-1)^T (+ damping): only block column 0 is needed before the pivot chain can start, so the
+            // four warps do (cw,0) first; the other six lower blocks follow on the helper warps behind the chain
+            syrk_blocks(Lx, D, k >= 1, cw, 0, -1, -1, k, n, u, lane);
             bar_sync(2, 128);
             PROF(3);
             if (warp == 0) {
                 if (warp_potrf_blocked(D, Lc, dv, Linv + (k & 1) * T36, lane, prof ? tsacc : nullptr, tA)) *a.info = 1;
                 PROF(4);
+            } else {
+                // helper h = cw owns blocks (h,1) [syrk only] and (2,2) | (3,2) | (3,3): rest of the syrk, then the
+                // non-urgent part of the Cholesky's trailing updates (block columns right of the next one).
+                // One barrier id per phase: a helper may reach its next arrive before warp 0 has consumed the previous one.
+                const int oi = (cw == 1) ? 2 : 3, oj = (cw == 3) ? 3 : 2;
+                syrk_blocks(Lx, D, k >= 1, cw, 1, oi, oj, k, n, u, lane);
+                bar_arrive(4, 128);                                   // phase 0: warp 0 may update block column 1
+                helper_trailing(D, Lc, dv, 0, oi, oj, lane, true);
+                bar_arrive(5, 128);                                   // phase 1: ... block column 2
+                helper_trailing(D, Lc, dv, 1, oi, oj, lane, cw == 3);
+                bar_arrive(6, 128);                                   // phase 2: ... block (3,3)
             }
         } else if (warp == 1) {
             // ---- L(k,k)^-1 behind the Cholesky; publish to shared (next panel's product) and global (U, R) ----
