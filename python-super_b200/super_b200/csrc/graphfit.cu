@@ -90,29 +90,64 @@ __device__ __forceinline__ bool gf_warp(const GfArgs& a, int i, Warped& s) {
     return true;
 }
 
-// back-propagate a = dl/dp' of one surfel into the shared node table and the thread's global-row partial
-__device__ __forceinline__ void gf_backprop(const GfArgs& a, const Warped& s, const V3& g, double* __restrict__ tab,
-                                            double (&gl_acc)[7]) {
-    const double* gl = a.dv + 7 * a.J;
-    const double gw0 = gl[0];
-    const V3 gqv = v3(gl[1], gl[2], gl[3]);
-    double qgw; V3 qgv;
-    qgrad(s.T, gw0, gqv, g, qgw, qgv);
-    gl_acc[0] += qgw; gl_acc[1] += qgv.x; gl_acc[2] += qgv.y; gl_acc[3] += qgv.z;
-    gl_acc[4] += g.x; gl_acc[5] += g.y; gl_acc[6] += g.z;
-    const V3 aT = qrot_t(g, gw0, gqv);
+constexpr int GF_STAGE = 28 * 33;      // per-warp staging: 28 node-gradient entries x 32 lanes (+1 pad)
+
+// Back-propagate a = dl/dp' of the warp's 32 surfels (ok = lane takes part) into the shared node table and the
+// thread's global-row partial.  A lane's 28 node-gradient entries (4 nodes x [q(4) b(3)], node slots in ASCENDING
+// node-id order) are staged in shared memory; lanes that share the node SET are summed by 28 lanes (one entry each,
+// 32 conflict-free loads) and leave as 28 shared atomics on distinct addresses.  (One atomic per entry and surfel
+// was 28 same-address atomics per warp instruction: 340 us per pass, ncu launch list r1d.)
+__device__ __forceinline__ void gf_backprop_warp(const GfArgs& a, const Warped& s, const V3& g, bool ok,
+                                                 double* __restrict__ tab, double* __restrict__ stage,
+                                                 double (&gl_acc)[7]) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long key = ~0ull;
+    if (ok) {
+        const double* gl = a.dv + 7 * a.J;
+        const double gw0 = gl[0];
+        const V3 gqv = v3(gl[1], gl[2], gl[3]);
+        double qgw; V3 qgv;
+        qgrad(s.T, gw0, gqv, g, qgw, qgv);
+        gl_acc[0] += qgw; gl_acc[1] += qgv.x; gl_acc[2] += qgv.y; gl_acc[3] += qgv.z;
+        gl_acc[4] += g.x; gl_acc[5] += g.y; gl_acc[6] += g.z;
+        const V3 aT = qrot_t(g, gw0, gqv);
+        key = 0;
 #pragma unroll
-    for (int k = 0; k < SB_KNN; ++k) {
-        const double* gp = a.ed_points + 3 * s.idx[k];
-        const double* b = a.dv + 7 * s.idx[k];
-        const V3 dk = v3(s.p.x - __ldg(gp), s.p.y - __ldg(gp + 1), s.p.z - __ldg(gp + 2));
-        double kw; V3 kv;
-        qgrad(dk, __ldg(b), v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3)), aT, kw, kv);
-        double* t = tab + 7 * s.idx[k];
-        const double wk = s.w[k];
-        atomicAdd(t + 0, wk * kw); atomicAdd(t + 1, wk * kv.x); atomicAdd(t + 2, wk * kv.y); atomicAdd(t + 3, wk * kv.z);
-        atomicAdd(t + 4, wk * aT.x); atomicAdd(t + 5, wk * aT.y); atomicAdd(t + 6, wk * aT.z);
+        for (int k = 0; k < SB_KNN; ++k) {
+            const double* gp = a.ed_points + 3 * s.idx[k];
+            const double* b = a.dv + 7 * s.idx[k];
+            const V3 dk = v3(s.p.x - __ldg(gp), s.p.y - __ldg(gp + 1), s.p.z - __ldg(gp + 2));
+            double kw; V3 kv;
+            qgrad(dk, __ldg(b), v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3)), aT, kw, kv);
+            int slot = 0;
+#pragma unroll
+            for (int j = 0; j < SB_KNN; ++j) slot += (s.idx[j] < s.idx[k]) ? 1 : 0;
+            key |= (unsigned long long)(unsigned)s.idx[k] << (48 - 16 * slot);
+            const double wk = s.w[k];
+            double* st = stage + (7 * slot) * 33 + lane;
+            st[0 * 33] = wk * kw; st[1 * 33] = wk * kv.x; st[2 * 33] = wk * kv.y; st[3 * 33] = wk * kv.z;
+            st[4 * 33] = wk * aT.x; st[5 * 33] = wk * aT.y; st[6 * 33] = wk * aT.z;
+        }
     }
+    __syncwarp();
+    unsigned remaining = __ballot_sync(0xffffffffu, ok);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const unsigned long long kk = __shfl_sync(0xffffffffu, key, leader);
+        const unsigned m = __ballot_sync(0xffffffffu, key == kk) & remaining;
+        if (lane < 28) {
+            const double* row = stage + lane * 33;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l)
+                if ((m >> l) & 1u) acc += row[l];
+            const int slot = lane / 7, comp = lane - 7 * slot;
+            const int node = (int)(kk >> (48 - 16 * slot)) & 0xffff;
+            atomicAdd(tab + 7 * node + comp, acc);
+        }
+        remaining &= ~m;
+    }
+    __syncwarp();
 }
 
 // projection (Z + 1e-8 everywhere: this is what autograd differentiates) and its gradient rows
@@ -167,14 +202,19 @@ gf_data_kernel(GfArgs a, const float4* __restrict__ vmap, const float4* __restri
     const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
     const int H = a.cam.H, W = a.cam.W;
     double gl_acc[7] = {0, 0, 0, 0, 0, 0, 0}, loss = 0.0;
-    for (int i = i0 + threadIdx.x; i < i1; i += GF_BLOCK) {
+    double* stage = tab + 7 * a.J + (threadIdx.x >> 5) * GF_STAGE;
+    for (int ib = i0; ib < i1; ib += GF_BLOCK) {          // warp-uniform trip count: the back-propagation is cooperative
+        const int i = ib + threadIdx.x;
         Warped s;
-        if (!gf_warp(a, i, s)) continue;
+        V3 g = v3(0, 0, 0);
+        bool live = false;
+        do {
+        if (i >= i1 || !gf_warp(a, i, s)) break;
         double u, v; V3 du, dv_;
         gf_project(s.pp, a.cam, u, v, du, dv_);
-        if (!(fabs(u) < 1e9 && fabs(v) < 1e9)) continue;
+        if (!(fabs(u) < 1e9 && fabs(v) < 1e9)) break;
         const long long ur = round_ll(u), vr = round_ll(v);
-        if (vr < 1 || vr >= H - 2 || ur < 1 || ur >= W - 2) continue;          // pcd2depth valid_margin = 1
+        if (vr < 1 || vr >= H - 2 || ur < 1 || ur >= W - 2) break;             // pcd2depth valid_margin = 1
         const double fv = floor(v), cv = ceil(v), fu = floor(u), cu = ceil(u);
         const int iy[2] = {(int)fv, (int)cv}, ix[2] = {(int)fu, (int)cu};
         const double dy[2] = {fv - v, cv - v}, dx[2] = {fu - u, cu - u};
@@ -207,7 +247,7 @@ gf_data_kernel(GfArgs a, const float4* __restrict__ vmap, const float4* __restri
                 for (int q = 0; q < sg.C; ++q) sc[q] += tc[q] * wgt;
             }
         }
-        if (!ok) continue;
+        if (!ok) break;
         double omega = 1.0;
         if (sg.mode) {
             // softmax of the sampled (already soft-maxed) confidences: loss.py:357
@@ -235,9 +275,11 @@ gf_data_kernel(GfArgs a, const float4* __restrict__ vmap, const float4* __restri
         loss += weight * omega * r * r;
         const double cu_ = dot3(diff, n_u) - dot3(nn, o_u), cv_ = dot3(diff, n_v) - dot3(nn, o_v);
         const double f = 2.0 * weight * omega * r;
-        const V3 g = v3(f * (nn.x + cu_ * du.x + cv_ * dv_.x), f * (nn.y + cu_ * du.y + cv_ * dv_.y),
-                        f * (nn.z + cu_ * du.z + cv_ * dv_.z));
-        gf_backprop(a, s, g, tab, gl_acc);
+        g = v3(f * (nn.x + cu_ * du.x + cv_ * dv_.x), f * (nn.y + cu_ * du.y + cv_ * dv_.y),
+               f * (nn.z + cu_ * du.z + cv_ * dv_.z));
+        live = true;
+        } while (false);
+        gf_backprop_warp(a, s, g, live, tab, stage, gl_acc);
     }
     gf_finish(tab, a.J, gl_acc, loss, 0.0, grad, loss_out, nullptr, red);
 }
@@ -274,18 +316,23 @@ gf_morph_kernel(GfArgs a, const double* __restrict__ scores, int C, const int* _
     const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
     const int H = a.cam.H, W = a.cam.W;
     double gl_acc[7] = {0, 0, 0, 0, 0, 0, 0}, loss = 0.0, cnt = 0.0;
-    for (int i = i0 + threadIdx.x; i < i1; i += GF_BLOCK) {
+    double* stage = tab + 7 * a.J + (threadIdx.x >> 5) * GF_STAGE;
+    for (int ib = i0; ib < i1; ib += GF_BLOCK) {
+        const int i = ib + threadIdx.x;
         Warped s;
-        if (!gf_warp(a, i, s)) continue;
+        V3 g = v3(0, 0, 0);
+        bool live = false;
+        do {
+        if (i >= i1 || !gf_warp(a, i, s)) break;
         double x, y; V3 dx_, dy_;
         gf_project(s.pp, a.cam, x, y, dx_, dy_);
         const double sx = x / W * 2.0 - 1.0, sy = y / H * 2.0 - 1.0;
-        if (!(sx > -1.0 && sx < 1.0 && sy > -1.0 && sy < 1.0)) continue;
+        if (!(sx > -1.0 && sx < 1.0 && sy > -1.0 && sy < 1.0)) break;
         const int cls = sf_seg[i];
-        if (cls < 0 || cls >= C) continue;
-        if (morph_class(scores, C, H, W, x, y) == cls) continue;
+        if (cls < 0 || cls >= C) break;
+        if (morph_class(scores, C, H, W, x, y) == cls) break;
         const int e0 = edge_off[cls], e1 = edge_off[cls + 1];
-        if (e1 - e0 < 2) continue;
+        if (e1 - e0 < 2) break;
         // two nearest edge pixels of the surfel's own class (ties -> lower index)
         double b0 = INFINITY, b1 = INFINITY;
         int j0 = -1, j1 = -1;
@@ -299,14 +346,16 @@ gf_morph_kernel(GfArgs a, const double* __restrict__ scores, int C, const int* _
         }
         // dropped when an edge pixel is farther than the image border
         const double d2e = fmin(fmin(fmin(x, y), (double)W - x), (double)H - y);
-        if (sqrt(b1) > d2e || sqrt(b0) > d2e) continue;
+        if (sqrt(b1) > d2e || sqrt(b0) > d2e) break;
         const double m = 0.5 * (b0 + b1);
-        if (!(m > 15.0)) continue;
+        if (!(m > 15.0)) break;
         loss += m;
         cnt += 1.0;
         const double gx = 2.0 * x - (edge_pts[2 * j0] + edge_pts[2 * j1]), gy = 2.0 * y - (edge_pts[2 * j0 + 1] + edge_pts[2 * j1 + 1]);
-        const V3 g = v3(gx * dx_.x + gy * dy_.x, gx * dx_.y + gy * dy_.y, gx * dx_.z + gy * dy_.z);
-        gf_backprop(a, s, g, tab, gl_acc);
+        g = v3(gx * dx_.x + gy * dy_.x, gx * dx_.y + gy * dy_.y, gx * dx_.z + gy * dy_.z);
+        live = true;
+        } while (false);
+        gf_backprop_warp(a, s, g, live, tab, stage, gl_acc);
     }
     gf_finish(tab, a.J, gl_acc, loss, cnt, grad_m, acc, acc + 1, red);
 }
@@ -486,14 +535,14 @@ int sb_gf_data(const double* points, const int* knn_idx, const double* knn_w, co
                int H, int W, const double* intr, double weight, int seg_mode, int C, const int* sf_seg,
                const double* sf_seg_conf, const double* trg_seg_conf, double* grad, double* acc, void* stream) {
     if (!points || !knn_idx || !knn_w || !ed_points || !dv || !vmap || !nmap || !grad || !acc) return SB_ERR_ARG;
-    if (J <= 0 || (size_t)7 * J * sizeof(double) > 200 * 1024) return SB_ERR_ARG;
+    if (J <= 0 || ((size_t)7 * J + (GF_BLOCK / 32) * GF_STAGE) * sizeof(double) > 220 * 1024 || J > 65534) return SB_ERR_ARG;
     if (seg_mode && (C < 1 || C > GF_MAXC || !trg_seg_conf || (seg_mode == 1 && !sf_seg_conf) || (seg_mode == 2 && !sf_seg)))
         return SB_ERR_ARG;
     if (n_cap <= 0) return SB_OK;
     GfArgs a = make_gf(points, knn_idx, knn_w, stable, n_cap, n_dev, ed_points, J, dv, H, W, intr);
     SegArgs sg;
     sg.mode = seg_mode; sg.C = C; sg.sf_seg = sf_seg; sg.sf_seg_conf = sf_seg_conf; sg.trg_seg_conf = trg_seg_conf;
-    const size_t smem = (size_t)7 * J * sizeof(double);
+    const size_t smem = ((size_t)7 * J + (GF_BLOCK / 32) * GF_STAGE) * sizeof(double);
     if (gf_set_smem(gf_data_kernel, smem) != SB_OK) return SB_ERR_CUDA;
     gf_data_kernel<<<gf_grid(n_cap), GF_BLOCK, smem, (cudaStream_t)stream>>>(
         a, reinterpret_cast<const float4*>(vmap), reinterpret_cast<const float4*>(nmap), sg, weight, grad, acc);
@@ -508,10 +557,10 @@ int sb_gf_morph(const double* points, const int* knn_idx, const double* knn_w, c
     if (!points || !knn_idx || !knn_w || !ed_points || !dv || !scores || !sf_seg || !edge_pts || !edge_off ||
         !grad_morph || !acc)
         return SB_ERR_ARG;
-    if (J <= 0 || (size_t)7 * J * sizeof(double) > 200 * 1024 || C < 1 || C > GF_MAXC) return SB_ERR_ARG;
+    if (J <= 0 || ((size_t)7 * J + (GF_BLOCK / 32) * GF_STAGE) * sizeof(double) > 220 * 1024 || J > 65534 || C < 1 || C > GF_MAXC) return SB_ERR_ARG;
     if (n_cap <= 0) return SB_OK;
     GfArgs a = make_gf(points, knn_idx, knn_w, stable, n_cap, n_dev, ed_points, J, dv, H, W, intr);
-    const size_t smem = (size_t)7 * J * sizeof(double);
+    const size_t smem = ((size_t)7 * J + (GF_BLOCK / 32) * GF_STAGE) * sizeof(double);
     if (gf_set_smem(gf_morph_kernel, smem) != SB_OK) return SB_ERR_CUDA;
     gf_morph_kernel<<<gf_grid(n_cap), GF_BLOCK, smem, (cudaStream_t)stream>>>(a, scores, C, sf_seg, edge_pts, edge_off,
                                                                              grad_morph, acc + 4);
