@@ -262,6 +262,12 @@ int sb_compact(const SbSurfels* src, const SbSurfels* dst, const SbFrame* frame,
                int th_time_steps, int disable_removing, long long* track_id, int n_track, void* workspace,
                long long ws_bytes, void* stream);
 
+/* Tracked-point bookkeeping after compaction: update_track_pts + init_track_pts as prepareStableIndexNSwapAllModel
+ * calls them (/root/reference/super/nodes.py:225-265,594-599) for a frame that has labels.  gt (T,3) i32 [x,y,valid],
+ * track_id (T,) i64 in/out (-1 not started, -2 lost), out (T,3) f32 = track_rsts[filename] ([u, v, 1] per point). */
+int sb_track_points(const double* points, const unsigned char* stable, const float* projdata, int n_cap, const int* n_dev,
+                    const float* vmap, int H, int W, const int* gt, int T, long long* track_id, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

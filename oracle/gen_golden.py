@@ -130,6 +130,30 @@ def gen_gf(name, height, width, step, nframes, speed, flags, opt_over, semantic=
               f"N={len(fr['state']['points'])}")
 
 
+TRACK_PTS = [[20, 20, 1], [40, 30, 1], [64, 48, 1], [90, 60, 1], [110, 80, 1], [0, 0, 1], [30, 70, 0]]
+
+
+def gen_track(name, height, width, step, nframes, speed):
+    """Tracked-point bookkeeping (nodes.py:225-265,443-458,576-599): per frame the tracked surfel ids and the
+    recorded reprojections track_rsts[filename] (T,3), for --tracking_gt_file labels given on every frame."""
+    frames = list(range(1, nframes + 1))
+    pts = np.array(TRACK_PTS, dtype=np.int64)
+    gt = {"gt": {f"{t:06d}": pts.copy() for t in frames}}
+    rec = run_reference.run(["--mesh_step_size", str(step)] + LM_FLAGS, frames, height, width, speed=speed, tracking_gt=gt)
+    sf = rec.models.super.sf
+    d = {"gt": pts}
+    for fr in rec.frames:
+        t = fr["t"]
+        d[f"f{t}.track_id"] = fr["state"]["track_id"]
+        d[f"f{t}.track_rsts"] = sf.track_rsts[f"{t:06d}"].cpu().numpy()
+        d[f"f{t}.N"] = np.array(len(fr["state"]["points"]))
+    meta = {"height": height, "width": width, "step": step, "frames": frames, "speed": speed, "flags": LM_FLAGS,
+            "reference": "ucsdarclab/Python-SuPer @ /root/reference (unmodified, CPU, shims)"}
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, meta=json.dumps(meta), **d)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} KB; ids per frame {[d[f'f{t}.track_id'].tolist() for t in frames]}")
+
+
 GF_FLAGS = ["--sf_point_plane", "--mesh_rot", "--mesh_arap", "--mesh_face", "--optimizer", "Adam"]
 GF_OPT = dict(use_derived_gradient=False, mesh_face=True, optimizer="Adam")
 SEM_FLAGS = ["--load_seg", "--seg_dir", "seg", "--disable_ssim_conf", "--sf_soft_seg_point_plane", "--mesh_rot",
@@ -141,10 +165,12 @@ SEM_OPT = dict(use_derived_gradient=False, mesh_face=True, mesh_arap=False, sf_p
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lm", "gf", "sem"]
+    which = sys.argv[1:] or ["lm", "gf", "sem", "track"]
     if "lm" in which:
         gen_lm("lm_128x96", 96, 128, 16, 4, 3.0)
     if "gf" in which:
         gen_gf("gf_128x96", 96, 128, 16, 3, 3.0, GF_FLAGS, GF_OPT)
+    if "track" in which:
+        gen_track("track_128x96", 96, 128, 16, 4, 3.0)
     if "sem" in which:
         gen_gf("gf_sem_128x96", 96, 128, 16, 3, 3.0, SEM_FLAGS, SEM_OPT, semantic=True, seg_speed=15.0)

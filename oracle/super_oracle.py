@@ -772,6 +772,49 @@ def fuse(opt, sf, nd, max_layers=16):
 
 
 # ----------------------------------------------------------------------------------------------
+# tracked points (evaluation bookkeeping that rides on the state)
+# ----------------------------------------------------------------------------------------------
+def init_track_pts(sf, nd, gt_row, th=0.2):
+    """Surfels.init_track_pts (/root/reference/super/nodes.py:225-249).  gt_row (T,3) int [x, y, valid].  Quirks
+    kept: the result row is projdata[track_id[k]] AFTER this call's assignment (the loop variable is a view), with
+    negative ids indexing from the end (-1 -> last surfel); `gt_id > 0` drops the first valid pixel; a lost id (-2)
+    masks surfel N-2."""
+    T = len(sf.track_id)
+    rst = torch.zeros((T, 3))
+    gt = torch.as_tensor(gt_row, dtype=torch.int)
+    for k in range(T):
+        tid = sf.track_id[k]                       # a view: follows the assignment below, as in the reference
+        x, y, v = gt[k]
+        gt_id = nd.index_map[y, x]
+        if tid < 0 and gt_id > 0 and v == 1:
+            dists = torch.linalg.norm(sf.points - nd.points[gt_id], dim=-1)
+            inval = sf.track_id[(sf.track_id >= 0) | (sf.track_id == -2)]
+            if len(inval) > 0:
+                dists[inval.long()] = 1e13
+                dists[~sf.isStable] = 1e13
+            if torch.min(dists) < th:
+                sf.track_id[k] = torch.argmin(dists)
+        rst[k, 0:2] = sf.projdata[tid.long()]
+        rst[k, 2] = 1
+    return rst
+
+
+def track_points(sf, nd, filename, gt, track_rsts):
+    """The tracking part of prepareStableIndexNSwapAllModel (/root/reference/super/nodes.py:594-599) with
+    update_track_pts (:251-265).  gt: {filename: (T,3)}; track_rsts: dict filled in place."""
+    if (sf.track_id >= 0).count_nonzero() > 0 and filename in gt:                  # update_track_pts
+        if filename not in track_rsts:
+            track_rsts[filename] = init_track_pts(sf, nd, gt[filename], th=1e-2)
+        else:
+            for k in range(len(sf.track_id)):
+                if sf.track_id[k] >= 0:
+                    track_rsts[filename][k, 0:2] = sf.projdata[sf.track_id[k]]
+                    track_rsts[filename][k, 2] = 1
+    if (sf.track_id == -1).count_nonzero() > 0 and filename in gt:
+        track_rsts[filename] = init_track_pts(sf, nd, gt[filename], th=0.2)
+
+
+# ----------------------------------------------------------------------------------------------
 # whole frame
 # ----------------------------------------------------------------------------------------------
 def default_opt(**kw):
@@ -792,9 +835,10 @@ def default_opt(**kw):
 class Tracker:
     """SuPer.forward (/root/reference/super/super.py:23-83) for the LM configuration."""
 
-    def __init__(self, opt, assemble="blocks"):
+    def __init__(self, opt, assemble="blocks", gt=None):
         self.opt, self.sf, self.assemble = opt, None, assemble
         self.trace = None
+        self.gt, self.track_rsts = gt, {}       # gt: {"%06d": (T,3) int [x,y,valid]}  (--tracking_gt_file)
 
     def step(self, frame, trace=False):
         nd = preprocess(self.opt, frame)
@@ -802,6 +846,10 @@ class Tracker:
         if self.sf is None:
             graph = build_graph(self.opt, nd)
             self.sf = init_surfels(self.opt, nd, graph)
+            if self.gt is not None:              # Surfels.__init__ :124 + the first prepareStable... (super.py:63)
+                T = len(next(iter(self.gt.values())))
+                self.sf.track_id = -torch.ones(T, dtype=torch.long)
+                track_points(self.sf, nd, frame["filename"], self.gt, self.track_rsts)
             return None
         tr = [] if trace else None
         beta = lm_solve(self.opt, self.sf, nd, assemble=self.assemble, trace=tr)
@@ -809,4 +857,6 @@ class Tracker:
         update(self.opt, self.sf, beta)
         fuse(self.opt, self.sf, nd)
         compact(self.opt, self.sf, float(frame["time"]))
+        if self.gt is not None:
+            track_points(self.sf, nd, frame["filename"], self.gt, self.track_rsts)
         return beta

@@ -412,9 +412,128 @@ __global__ void track_remap_kernel(long long* track_id, int n_track, const int* 
     if (id >= 0) track_id[t] = keep[id] ? pos[id] : -1;     // nodes.py:576-580 (id_map is -1 for dropped rows)
 }
 
+// ---- tracked points -------------------------------------------------------------------------------------
+// init_track_pts / update_track_pts as called from prepareStableIndexNSwapAllModel (nodes.py:225-265,594-599), one
+// CTA: the labelled points are few (20) and the search is one pass over the surfels per unassigned point.
+constexpr int TRK_BLOCK = 1024;
+constexpr int TRK_MAX = 64;
+
+struct TrackArgs {
+    const double* points; const unsigned char* stable; const float* projdata; int n_cap; const int* n_dev;
+    const float4* vmap; int H, W;
+    const int* gt;            // (T,3) i32 [x, y, valid]
+    int T;
+    long long* track_id;      // (T,) i64: >= 0 surfel row, -1 not started, -2 lost
+    float* out;               // (T,3) f32 track_rsts[filename]
+};
+
+__device__ void track_init(const TrackArgs& a, int n, int first_valid, double th, double* sd, int* si, long long* ids) {
+    const int tid_ = threadIdx.x;
+    for (int k = 0; k < a.T; ++k) {
+        __syncthreads();
+        if (tid_ < a.T) ids[tid_] = a.track_id[tid_];
+        __syncthreads();
+        const long long cur = ids[k];
+        const int x = a.gt[3 * k], y = a.gt[3 * k + 1], v = a.gt[3 * k + 2];
+        const int pix = y * a.W + x;
+        const bool in_img = x >= 0 && x < a.W && y >= 0 && y < a.H;
+        const float4 q = in_img ? a.vmap[pix] : make_float4(0, 0, 0, 0);
+        // gt_id > 0: a valid pixel that is not the first valid pixel of the frame (index_map value 0), nodes.py:240
+        if (cur < 0 && in_img && q.w != 0.f && pix != first_valid && v == 1) {
+            bool any_inval = false, lost = false;
+            for (int j = 0; j < a.T; ++j) { any_inval |= ids[j] >= 0 || ids[j] == -2; lost |= ids[j] == -2; }
+            double best = INFINITY;
+            int besti = 0x7fffffff;
+            for (int i = tid_; i < n; i += TRK_BLOCK) {
+                const double dx = a.points[3 * (size_t)i] - (double)q.x, dy = a.points[3 * (size_t)i + 1] - (double)q.y,
+                             dz = a.points[3 * (size_t)i + 2] - (double)q.z;
+                double d = sqrt(dx * dx + dy * dy + dz * dz);
+                if (any_inval) {                                       // nodes.py:242-245
+                    bool ex = !a.stable[i] || (lost && i == n - 2);    // dists[-2] = 1e13: the reference indexes with the id -2
+                    for (int j = 0; j < a.T && !ex; ++j) ex = ids[j] == i;
+                    if (ex) d = 1e13;
+                }
+                if (d < best) { best = d; besti = i; }                 // ascending i per thread: first minimum
+            }
+            sd[tid_] = best; si[tid_] = besti;
+            __syncthreads();
+            for (int o = TRK_BLOCK / 2; o > 0; o >>= 1) {
+                if (tid_ < o) {
+                    const double d2 = sd[tid_ + o];
+                    const int i2 = si[tid_ + o];
+                    if (d2 < sd[tid_] || (d2 == sd[tid_] && i2 < si[tid_])) { sd[tid_] = d2; si[tid_] = i2; }
+                }
+                __syncthreads();
+            }
+            if (tid_ == 0 && sd[0] < th) a.track_id[k] = si[0];
+        }
+    }
+    __syncthreads();
+    if (tid_ < a.T) {   // rows from projdata[track_id] (negative ids index from the end, as in the reference)
+        long long id = a.track_id[tid_];
+        if (id < 0) id += n;
+        const bool okid = id >= 0 && id < n;
+        a.out[3 * tid_] = okid ? a.projdata[2 * id] : 0.f;
+        a.out[3 * tid_ + 1] = okid ? a.projdata[2 * id + 1] : 0.f;
+        a.out[3 * tid_ + 2] = 1.f;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TRK_BLOCK) track_points_kernel(TrackArgs a) {
+    __shared__ double sd[TRK_BLOCK];
+    __shared__ int si[TRK_BLOCK];
+    __shared__ long long ids[TRK_MAX];
+    __shared__ int flags[2];
+    const int n = n_active(a.n_cap, a.n_dev);
+    // first valid pixel of the frame (index_map == 0)
+    int fv = 0x7fffffff;
+    for (int p = threadIdx.x; p < a.H * a.W; p += TRK_BLOCK)
+        if (a.vmap[p].w != 0.f) { fv = p; break; }
+    si[threadIdx.x] = fv;
+    __syncthreads();
+    for (int o = TRK_BLOCK / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) si[threadIdx.x] = min(si[threadIdx.x], si[threadIdx.x + o]);
+        __syncthreads();
+    }
+    const int first_valid = si[0];
+    __syncthreads();
+    if (threadIdx.x < 3 * a.T) a.out[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) {
+        bool any_tracked = false, any_new = false;
+        for (int j = 0; j < a.T; ++j) { any_tracked |= a.track_id[j] >= 0; any_new |= a.track_id[j] == -1; }
+        flags[0] = any_tracked; flags[1] = any_new;
+    }
+    __syncthreads();
+    // update_track_pts: first record for this filename -> init_track_pts with th = 1e-2 (nodes.py:256-258)
+    if (flags[0]) track_init(a, n, first_valid, 1e-2, sd, si, ids);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool any_new = false;
+        for (int j = 0; j < a.T; ++j) any_new |= a.track_id[j] == -1;
+        flags[1] = any_new;
+    }
+    __syncthreads();
+    if (flags[1]) {                                  // init_track_pts(th = 0.2) re-creates the record (nodes.py:233)
+        if (threadIdx.x < 3 * a.T) a.out[threadIdx.x] = 0.f;
+        track_init(a, n, first_valid, 0.2, sd, si, ids);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int sb_track_points(const double* points, const unsigned char* stable, const float* projdata, int n_cap, const int* n_dev,
+                    const float* vmap, int H, int W, const int* gt, int T, long long* track_id, float* out, void* stream) {
+    if (!points || !stable || !projdata || !vmap || !gt || !track_id || !out || T < 1 || T > TRK_MAX) return SB_ERR_ARG;
+    TrackArgs a;
+    a.points = points; a.stable = stable; a.projdata = projdata; a.n_cap = n_cap; a.n_dev = n_dev;
+    a.vmap = reinterpret_cast<const float4*>(vmap); a.H = H; a.W = W; a.gt = gt; a.T = T; a.track_id = track_id; a.out = out;
+    track_points_kernel<<<1, TRK_BLOCK, 0, (cudaStream_t)stream>>>(a);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
 
 long long sb_fuse_workspace_bytes(int H, int W, int cap) { return (long long)carve(nullptr, nullptr, H * W, cap); }
 

@@ -390,6 +390,24 @@ class Tracker:
         self._publish_count()
         return beta
 
+    def enable_tracking(self, gt):
+        """--tracking_gt_file: gt = {"%06d": (T,3) int array [x, y, valid]} (utils/utils.py:383-391).  Tracked surfel ids
+        live on the device (nodes.py:124); the recorded reprojections are in self.track_rsts[filename] (T,3) f32."""
+        self.gt = {k: torch.as_tensor(v, dtype=I32).to(self.dev).contiguous() for k, v in gt.items()}
+        T = next(iter(self.gt.values())).shape[0]
+        self.track_id = -torch.ones(T, dtype=I64, device=self.dev)
+        self.track_rsts = {}
+
+    def _track_points(self, frame, filename):
+        """update_track_pts / init_track_pts (nodes.py:225-265,594-599): one launch, no host sync."""
+        if getattr(self, "gt", None) is None or filename not in self.gt:
+            return
+        b = self.cur
+        out = torch.zeros((self.track_id.numel(), 3), dtype=F32, device=self.dev)
+        call("sb_track_points", ptr(b.points), ptr(b.stable), ptr(b.projdata), b.cap, ptr(b.n_dev), ptr(frame.vmap),
+             self.H, self.W, ptr(self.gt[filename]), self.track_id.numel(), ptr(self.track_id), ptr(out), stream())
+        self.track_rsts[filename] = out
+
     def fuse_params(self, frame):
         """merge thresholds + the semantic switches of fuseInputData (nodes.py:314-316,466-484,505-511)."""
         opt = self.opt
@@ -405,15 +423,20 @@ class Tracker:
         b = self.cur
         return NS(points=b.points[:n], norms=b.norms[:n], knn_indices=b.knn_idx[:n], knn_w=b.knn_w[:n], ED=self.ED)
 
-    def step(self, depth, color, K, inv_K, time, inval=None, seg_scores=None):
+    def step(self, depth, color, K, inv_K, time, inval=None, seg_scores=None, filename=None):
         """One SuPer.forward: preprocess + (init | track).  Returns beta or None.  seg_scores: (C,H,W) class scores
         (inputs[("seg_conf",0)]) for the Semantic-SuPer configuration."""
         frame = preprocess(self.opt, depth, color, K, inv_K, time, frame=self.next_frame(), inval=inval,
                            seg_scores=seg_scores)
+        if filename is None:
+            filename = f"{int(time):06d}"
         if self.cur is None:
             self.init(frame)
+            self._track_points(frame, filename)
             return None
-        return self.track(frame)
+        beta = self.track(frame)
+        self._track_points(frame, filename)
+        return beta
 
     def snapshot(self):
         """Exact-size copies of the state in the reference's layouts (synchronises)."""

@@ -47,6 +47,14 @@ class Surfels:
         return self._trk.cur.knn_idx[: self._trk.num_surfels()].to(torch.int64)
 
     @property
+    def track_id(self):
+        return self._trk.track_id
+
+    @property
+    def track_rsts(self):
+        return self._trk.track_rsts
+
+    @property
     def seg(self):
         return self._trk.cur.seg[: self._trk.num_surfels()].to(torch.int64)
 

@@ -32,6 +32,12 @@ class SuPer(torch.nn.Module):
         dev = torch.device("cuda", torch.cuda.current_device())
         if self._trk is None:
             self._trk = engine.Tracker(self.opt, device=dev)
+            if getattr(self.opt, "tracking_gt_file", None):          # nodes.py:96,115-126, utils/utils.py:383-391
+                import os
+                import numpy as np
+                gt = np.load(os.path.join(os.path.expanduser(self.opt.data_dir), self.opt.tracking_gt_file),
+                             allow_pickle=True).tolist()["gt"]
+                self._trk.enable_tracking({f"{int(k):06d}": np.asarray(v) for k, v in gt.items()})
         staged = {}
         for key, ipt in inputs.items():                          # super.py:31-34
             if torch.is_tensor(ipt):
@@ -53,12 +59,14 @@ class SuPer(torch.nn.Module):
                                   divterm=inputs.get("divterm", 1.0 / (2.0 * 0.6 * 0.6)),
                                   seg_scores=inputs.get(("seg_conf", 0)))
         self.last_frame = frame
+        fname = inputs["filename"][0] if "filename" in inputs else f"{int(time):06d}"
         if self._trk.cur is None:
             self._trk.init(frame)
             self.sf = Surfels(self.opt, self._trk)
             deform_param = None
         else:
             deform_param = self.fusion(models, inputs, frame)
+        self._trk._track_points(frame, fname)
         return deform_param
 
     def fusion(self, models, inputs, sfdata):

@@ -133,3 +133,27 @@ def test_run_super_entry_point_on_disk_sequence(tmp_path):
                  torch.from_numpy(fr["K"]), torch.from_numpy(fr["inv_K"]), fr["time"])
     assert n_entry == trk.num_surfels()
     assert torch.allclose(models.super.sf.points, trk.cur.points[:n_entry], atol=1e-9)
+
+
+def test_tracked_points_follow_reference():
+    """north_star's third criterion: tracked-point reprojections (projdata[track_id], recorded per labelled frame) within
+    0.1 px of the reference over the sequence; the tracked surfel ids themselves are integers and must be equal."""
+    import json, os
+    from golden_util import GOLDEN_DIR
+    from super_b200 import engine, synth
+    z = np.load(os.path.join(GOLDEN_DIR, "track_128x96.npz"))
+    m = json.loads(str(z["meta"]))
+    H, W = m["height"], m["width"]
+    opt = so.default_opt(height=H, width=W, mesh_step_size=m["step"])
+    trk = engine.Tracker(opt, device="cuda:0")
+    trk.enable_tracking({f"{t:06d}": z["gt"] for t in m["frames"]})
+    tex = synth.texture(H, W)
+    for t in m["frames"]:
+        fr = synth.frame_inputs(t, H, W, tex=tex, speed=m["speed"])
+        trk.step(torch.from_numpy(fr["depth"]).cuda(), torch.from_numpy(fr["color"]).cuda(), torch.from_numpy(fr["K"]),
+                 torch.from_numpy(fr["inv_K"]), fr["time"], filename=fr["filename"])
+        assert trk.num_surfels() == int(z[f"f{t}.N"])
+        assert np.array_equal(trk.track_id.cpu().numpy(), z[f"f{t}.track_id"]), t
+        err = np.abs(trk.track_rsts[fr["filename"]].cpu().numpy() - z[f"f{t}.track_rsts"]).max()
+        assert err < 0.1, (t, err)
+        assert err < 1e-3            # in fact far inside the tolerance

@@ -124,3 +124,24 @@ def test_graphfit_port_reproduces_reference(name):
         so.update(g.opt, sf, dv)
         for k, v in (("points", sf.points), ("norms", sf.norms), ("ED_points", sf.ED.points), ("ED_norms", sf.ED.norms)):
             assert np.abs(v.numpy() - g[f"f{t}.update.{k}"]).max() < 1e-12, k
+
+
+def test_tracked_points_port_reproduces_reference():
+    """Tracked-point ids and recorded reprojections of the reference (run with --tracking_gt_file) over 4 frames."""
+    import json
+    import os
+    from golden_util import GOLDEN_DIR
+    from super_b200 import synth
+    z = np.load(os.path.join(GOLDEN_DIR, "track_128x96.npz"))
+    m = json.loads(str(z["meta"]))
+    H, W = m["height"], m["width"]
+    opt = so.default_opt(height=H, width=W, mesh_step_size=m["step"])
+    gt = {f"{t:06d}": z["gt"] for t in m["frames"]}
+    trk = so.Tracker(opt, gt=gt)
+    tex = synth.texture(H, W)
+    for t in m["frames"]:
+        fr = synth.frame_inputs(t, H, W, tex=tex, speed=m["speed"])
+        trk.step(fr)
+        assert len(trk.sf.points) == int(z[f"f{t}.N"])
+        assert np.array_equal(trk.sf.track_id.numpy(), z[f"f{t}.track_id"])
+        assert np.abs(trk.track_rsts[fr["filename"]].numpy() - z[f"f{t}.track_rsts"]).max() < 1e-5
