@@ -578,6 +578,15 @@ __device__ void role_P(const Args3& a, double* smem) {
                 bar_arrive(5, 128);                                   // phase 1: ... block column 2
                 helper_trailing(D, Lc, dv, 1, oi, oj, lane, cw == 3);
                 bar_arrive(6, 128);                                   // phase 2: ... block (3,3)
+                // idle from here on: help the I/O warps stage the next panel's tiles (six warps, 12 loads per thread)
+                if (k + 1 < NP) {
+                    if (k >= 1 && NU > 0) {
+                        if (lane == 0) spin_until(upd_done + (k - 1), NU);
+                        __syncwarp();
+                    }
+                    load_ab_tiles2<192>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
+                                        Xbuf + ((k + 1) & 1) * T36, S36, (2 + cw) * 32 + lane);
+                }
             }
         } else if (warp == 1) {
             // ---- L(k,k)^-1 behind the Cholesky; publish to shared (next panel's product) and global (U, R) ----
@@ -628,8 +637,8 @@ __device__ void role_P(const Args3& a, double* smem) {
                     __syncwarp();
                     IOPROF(4);
                 }
-                load_ab_tiles2<96>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
-                                   Xbuf + ((k + 1) & 1) * T36, S36, it);
+                load_ab_tiles2<192>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
+                                    Xbuf + ((k + 1) & 1) * T36, S36, it);      // threads 0..95; the helper warps are 96..191
                 IOPROF(5);
             }
         }
@@ -795,6 +804,9 @@ __device__ void role_U(const Args3& a, double* smem) {
     double* LIs = Bs + T36;
     double* LJs = LIs + T36;
     const int fr = lane >> 2, fc = lane & 3;
+    const bool uprof = (a.debug & 4) && ui == 1;
+    long long ut[6] = {0, 0, 0, 0, 0, 0}, u0 = clock64(), u1;
+#define UPROF(slot) do { if (uprof) { if (*(volatile double*)LinvS != 1.2345e300) u1 = clock64(); ut[slot] += u1 - u0; u0 = u1; } } while (0)
 
     for (int p = 0; p < NP; ++p) {
         const int last = min(NP - 1, p + WB);
@@ -811,8 +823,10 @@ __device__ void role_U(const Args3& a, double* smem) {
             const int I = p + 1 + ri, J = p + 1 + (t - ri * (ri + 1) / 2);
             if (NB * (I - J) - (NB - 1) > bw) continue;                   // entirely outside the band
             const bool diag = (I == J);
+            UPROF(5);
             if (first && p >= 1) cta_wait(upd_done + (p - 1), NU);       // every tile carries panels <= p-1
             else __syncthreads();                                        // shared buffers of the previous tile are free
+            UPROF(0);
             load_ab_tiles2<THREADS>(a, I, p, As, S36, diag ? -1 : J, p, Bs, S36, tid);
             // old values of my two 8x8 output blocks (fragment layout), issued with the operand loads
             const int bi = warp >> 1;
@@ -827,7 +841,9 @@ __device__ void role_U(const Args3& a, double* smem) {
                 }
             }
             if (first) {
+                UPROF(1);
                 cta_wait(diag_done + p, 1);
+                UPROF(2);
                 load_g_tile(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS);
                 first = false;
             }
@@ -865,6 +881,7 @@ __device__ void role_U(const Args3& a, double* smem) {
             }
         }
         __syncthreads();
+        UPROF(3);
         if (tid == 0) {
             // one release fence for both counters
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -872,7 +889,10 @@ __device__ void role_U(const Args3& a, double* smem) {
             if (rows_written)
                 asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(rows_done + p), "r"(rows_written) : "memory");
         }
+        UPROF(4);
     }
+    if (uprof && tid == 0) for (int q = 0; q < 6; ++q) a.prof[52 + q] = ut[q];
+#undef UPROF
 }
 
 __global__ void __launch_bounds__(THREADS, 1) band_chol3_kernel(Args3 a) {

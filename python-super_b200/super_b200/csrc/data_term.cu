@@ -178,8 +178,7 @@ __device__ __forceinline__ unsigned long long pack_key(const int* idx) {
     return key;
 }
 
-constexpr int FL_STRIDE = 33;            // flush scratch: 32x32 Gram matrix, one per warp
-constexpr int FL_DOUBLES = 32 * FL_STRIDE;
+constexpr int FL_DOUBLES = 436;          // flush scratch: packed upper triangle (m <= n <= 28) of the Gram matrix, one per warp
 
 // Flush one warp accumulator (10 tiles x 2 doubles per lane) into the lower-triangular A (dense or band,
 // common.cuh MatView), g (= -J^T r) and the optional sum r^2.  The tiles go through a shared 32x32 scratch and
@@ -192,9 +191,13 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
     for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
         for (int tj = ti; tj < 4; ++tj, ++t) {
-            *reinterpret_cast<double*>(St + (8 * ti + (lane >> 2)) * FL_STRIDE + 8 * tj + 2 * (lane & 3)) = acc[t][0];
-            *reinterpret_cast<double*>(St + (8 * ti + (lane >> 2)) * FL_STRIDE + 8 * tj + 2 * (lane & 3) + 1) = acc[t][1];
-            acc[t][0] = acc[t][1] = 0.0;
+            const int m = 8 * ti + (lane >> 2);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = 8 * tj + 2 * (lane & 3) + e;
+                if (m <= n && n <= 28) St[m * 29 - m * (m - 1) / 2 + (n - m)] = acc[t][e];     // packed row m, column n
+                acc[t][e] = 0.0;
+            }
         }
     __syncwarp();
     // the 435 entries (m <= n <= 28) of the upper triangle are dealt round-robin to the lanes (14 each);
@@ -211,7 +214,7 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
         const int kn = (n * 37) >> 8, cn = n - 7 * kn;
         const int pm = __shfl_sync(0xffffffffu, my_pos, km & 3), pn = __shfl_sync(0xffffffffu, my_pos, kn & 3);
         if (e >= 435) continue;
-        const double val = St[m * FL_STRIDE + n];
+        const double val = St[e];
         if (val == 0.0) continue;
         if (n == 28) {
             if (m == 28) { if (loss_cur) atomicAdd(loss_cur, val); }
@@ -224,7 +227,7 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(JTJ_WARPS * 32)
+__global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
 data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

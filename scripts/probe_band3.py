@@ -40,7 +40,7 @@ g = torch.Generator().manual_seed(0)
 AB = torch.randn((n, bw + 1), generator=g, dtype=torch.float64); AB[:, bw] = AB.abs().sum(1) * 2 + 1.0
 band = ops.Band(n, bw, None, "cuda"); ABd = AB.cuda(); rd = torch.randn(n, generator=g, dtype=torch.float64).cuda()
 NP = (n + 31) // 32
-for flags in (5,):
+for flags in (4,):
     L.sb_band3_debug(flags)
     for _ in range(2):
         band.AB.copy_(ABd); band.g.copy_(rd); ops.band_solve(band, None, 128, variant=3); torch.cuda.synchronize()
@@ -51,5 +51,6 @@ for flags in (5,):
           "| R fwd end - P end", int(prof[10] - prof[9]), "| backsub", int(prof[11] - prof[10]),
           "\n   io warps [release diag, arm+wait Lx, store Lx, release rows, spin upd, stage]:", [[int(v) // NP for v in prof[12 + 6 * w:18 + 6 * w]] for w in range(3)],
           "| warp1 busy", int(prof[30]) // NP, "[wait prev block, S products, T_b rows, M products, publish]", [int(v) // NP for v in prof[31:36]],
-          "\n   block-end times after BAR_A [potrf], [T], [M+publish]:", [[int(v) // NP for v in prof[36 + 4 * w:40 + 4 * w]] for w in range(3)], "| potrf parts [load, chain+T, dmma update]", [int(v) // NP for v in prof[48:51]])
+          "\n   block-end times after BAR_A [potrf], [T], [M+publish]:", [[int(v) // NP for v in prof[36 + 4 * w:40 + 4 * w]] for w in range(3)], "| potrf parts [load, chain+T, dmma update]", [int(v) // NP for v in prof[48:51]],
+          "\n   U (rank 3) per panel [wait upd(p-1), operand loads, wait diag(p), Linv load + products + stores, signal, idle]:", [int(v) // NP for v in prof[52:58]])
 L.sb_band3_debug(0)
