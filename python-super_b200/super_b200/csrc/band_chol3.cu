@@ -38,7 +38,7 @@ struct Args3 {
     double* g; const double* u; double* dinv; int* info;
     double* LB;      // L tiles below the diagonal, tile (I, d = I-J in 1..WB) at ((I*WB + d-1) * 1024), row-major 32x32
     double* LI;      // L(k,k)^-1, tile k at k*1024, row-major
-    int* flags;      // diag_done[NP] | rows_done[NP] | upd_done[NP]
+    int* flags;      // diag_done[NP] | rows_done[NP] | upd_done[NP] | hot_done[NP]
     int NP, WB;
     long long* prof;   // 32 counters (debug & 4)
     int debug;         // 1: U skips its tile work, 2: no back substitution, 4: cycle counters
@@ -501,7 +501,9 @@ __device__ void role_P(const Args3& a, double* smem) {
     int* diag_done = a.flags;
     int* rows_done = a.flags + NP;
     int* upd_done = a.flags + 2 * NP;
+    int* hot_done = a.flags + 3 * NP;      // the two tiles P stages next, signalled by their owners as soon as they are done
     const int NU = (int)gridDim.x - 2;
+    const int hot_expected = (WB >= 2) ? 2 : 0;
     const double u = a.u ? *a.u : 0.0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
@@ -581,7 +583,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                 // idle from here on: help the I/O warps stage the next panel's tiles (six warps, 12 loads per thread)
                 if (k + 1 < NP) {
                     if (k >= 1 && NU > 0) {
-                        if (lane == 0) spin_until(upd_done + (k - 1), NU);
+                        if (lane == 0) spin_until(hot_done + (k - 1), hot_expected);
                         __syncwarp();
                     }
                     load_ab_tiles2<192>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
@@ -633,7 +635,7 @@ __device__ void role_P(const Args3& a, double* smem) {
             }
             if (k + 1 < NP) {
                 if (k >= 1 && NU > 0) {
-                    if (lane == 0) spin_until(upd_done + (k - 1), NU);
+                    if (lane == 0) spin_until(hot_done + (k - 1), hot_expected);
                     __syncwarp();
                     IOPROF(4);
                 }
@@ -879,6 +881,10 @@ __device__ void role_U(const Args3& a, double* smem) {
                 store_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
                 ++rows_written;
             }
+            if (t == 1 || t == 2) {     // (p+2,p+1), (p+2,p+2): what P stages for panel p+2 -- do not make it wait for the stragglers
+                __syncthreads();
+                if (tid == 0) red_release(a.flags + 3 * NP + p, 1);
+            }
         }
         __syncthreads();
         UPROF(3);
@@ -914,7 +920,7 @@ size_t smem_bytes3(int n) {
 
 long long ws_bytes3(int n, int bw) {
     const long long NP = (n + NB - 1) / NB, WB = (bw + NB - 1) / NB;
-    return (NP * (WB > 0 ? WB : 1) + NP) * (long long)T32 * (long long)sizeof(double) + ((3 * NP * (long long)sizeof(int) + 255) & ~255LL) + 256 + 1024;
+    return (NP * (WB > 0 ? WB : 1) + NP) * (long long)T32 * (long long)sizeof(double) + ((4 * NP * (long long)sizeof(int) + 255) & ~255LL) + 256 + 1024;
 }
 
 int g_debug3 = 0;
@@ -966,7 +972,7 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
     a.flags = (int*)(a.LI + (long long)a.NP * T32);
     a.prof = (long long*)((char*)workspace + ws_bytes3(n, bw) - 1024);
     a.debug = g_debug3;
-    if (cudaMemsetAsync(a.flags, 0, 3 * (size_t)a.NP * sizeof(int), (cudaStream_t)stream) != cudaSuccess)
+    if (cudaMemsetAsync(a.flags, 0, 4 * (size_t)a.NP * sizeof(int), (cudaStream_t)stream) != cudaSuccess)
         return SB_ERR_CUDA;
     void* kargs[] = {(void*)&a};
     if (cudaLaunchCooperativeKernel((const void*)band_chol3_kernel, dim3(n_ctas), dim3(THREADS), kargs, smem,
