@@ -225,8 +225,10 @@ def run_cuda(args, rank, world, local_rank):
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = (b_pass / 1e9) / (jt_avg_ms / 1e3) if jt_avg_ms else None
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1c_jtj_traffic.json")
-    if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+    import glob
+    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_jtj_traffic.json")))
+    tpath = tpaths[-1] if tpaths else ""
+    if tpath:        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         traffic_note = (f"ncu capture at {tj['surfels_at_capture']} surfels (algorithmic bytes there "
