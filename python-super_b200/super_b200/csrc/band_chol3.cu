@@ -40,6 +40,7 @@ struct Args3 {
     double* LI;      // L(k,k)^-1, tile k at k*1024, row-major
     int* flags;      // diag_done[NP] | rows_done[NP] | upd_done[NP] | hot_done[NP]
     int NP, WB;
+    int two_phase;     // wide bands (more trailing tiles than update CTAs): L(I,p) once per row, then one product per tile
     long long* prof;   // 32 counters (debug & 4)
     int debug;         // 1: U skips its tile work, 2: no back substitution, 4: cycle counters
 };
@@ -901,10 +902,131 @@ __device__ void role_U(const Args3& a, double* smem) {
 #undef UPROF
 }
 
+// U for wide bands.  With more trailing tiles per panel than CTAs, recomputing the two "triangular solves" for
+// every tile triples the work (C3/C5: 300 tiles on 146 CTAs), and a barrier over all update CTAs per panel serialises
+// the panels.  Here every tile (I,J) has a FIXED owner CTA for its whole life (tile-owner data flow):
+//   panel p, phase 1: the owner of (I,p) -- which applied all its updates itself, in program order -- forms
+//                     L(I,p) = A(I,p) L(p,p)^-T once and stores it for everybody (rows_done[p]);
+//   panel p, phase 2: the owner of (I,J), J > p, applies A(I,J) -= L(I,p) L(J,p)^T from the stored tiles (one product),
+//                     next block column first.
+// The only cross-CTA dependencies are diag_done[p] and rows_done[p] (+ the hot flag for P): no per-panel barrier.
+__device__ __forceinline__ int tile_owner(int I, int J, int NU) { return (int)(((unsigned)I * 7u + (unsigned)J * 13u) % (unsigned)NU); }
+
+__device__ void role_U2(const Args3& a, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = a.NP, WB = a.WB, bw = a.bw;
+    int* diag_done = a.flags;
+    int* rows_done = a.flags + NP;
+    int* upd_done = a.flags + 2 * NP;
+    const int NU = (int)gridDim.x - 2, ui = (int)blockIdx.x - 2;
+    double* LinvS = smem;            // T36
+    double* As = LinvS + T36;
+    double* LIs = As + T36;
+    double* LJs = LIs + T36;
+    __shared__ int lst1[MAX_WB3 + 4], lst2[448], n1, n2;
+    const int fr = lane >> 2, fc = lane & 3;
+
+    for (int p = 0; p < NP; ++p) {
+        const int last = min(NP - 1, p + WB);
+        const int nrows = last - p;
+        if (a.debug & 1) {          // timing experiments: no trailing work, but P still waits for the hot flag
+            if (ui == 0 && tid == 0) red_release(a.flags + 3 * NP + p, 2);
+            continue;
+        }
+        // ---- my work of this panel: rows (phase 1) and tiles (phase 2, packed I<<16|J, sorted by J then I) ----
+        __syncthreads();
+        if (tid == 0) { n1 = 0; n2 = 0; }
+        __syncthreads();
+        for (int c = tid; c < nrows * (nrows + 1) / 2 + nrows; c += THREADS) {
+            if (c < nrows) {                                   // candidate row I = p+1+c of column p (row p+1 is P's)
+                const int I = p + 1 + c;
+                if (c >= 1 && tile_owner(I, p, NU) == ui) lst1[atomicAdd(&n1, 1)] = I;
+            } else {
+                const int t = c - nrows;
+                int ri = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+                while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
+                while (ri * (ri + 1) / 2 > t) --ri;
+                const int I = p + 1 + ri, J = p + 1 + (t - ri * (ri + 1) / 2);
+                if (t != 0 && NB * (I - J) - (NB - 1) <= bw && tile_owner(I, J, NU) == ui) lst2[atomicAdd(&n2, 1)] = (J << 16) | I;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {                                        // few entries: insertion sort by (J, I)
+            for (int x = 1; x < n2; ++x) {
+                const int v = lst2[x];
+                int y = x - 1;
+                while (y >= 0 && lst2[y] > v) { lst2[y + 1] = lst2[y]; --y; }
+                lst2[y + 1] = v;
+            }
+        }
+        __syncthreads();
+        const int m1 = n1, m2 = n2;
+        // ---- phase 1 ----
+        if (m1 > 0) {
+            cta_wait(diag_done + p, 1);
+            load_g_tile(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS);
+            for (int x = 0; x < m1; ++x) {
+                const int I = lst1[x];
+                __syncthreads();
+                load_ab_tiles2<THREADS>(a, I, p, As, S36, -1, p, As, S36, tid);
+                __syncthreads();
+                trsm_strip(As, LinvS, LIs, warp >> 1, (warp & 1) ? 0x6u : 0x9u, lane);
+                __syncthreads();
+                store_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
+            }
+            __syncthreads();
+            if (tid == 0) red_release(rows_done + p, m1);
+        }
+        // ---- phase 2 ----
+        if (m2 > 0) {
+            cta_wait(rows_done + p, nrows);                     // every L(.,p) is stored
+            for (int x = 0; x < m2; ++x) {
+                const int I = lst2[x] & 0xffff, J = lst2[x] >> 16;
+                const bool diag = (I == J);
+                __syncthreads();
+                load_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
+                if (!diag) load_g_tile(lb_tile(a, J, J - p), LJs, S36, tid, THREADS);
+                const int bi = warp >> 1, bj0 = 2 * (warp & 1);
+                double oldv[2][2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * (bj0 + q) + 2 * fc + e;
+                        oldv[q][e] = in_band(a, i, j) ? __ldcg(ab_at(a, i, j)) : 0.0;
+                    }
+                __syncthreads();
+                const double* Lb = diag ? LIs : LJs;
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                const bool skip1 = diag && (bj0 + 1 > bi), skip0 = diag && (bj0 > bi);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double af = LIs[(8 * bi + fr) * S36 + 4 * ks + fc];
+                    if (!skip0) dmma884(acc[0][0], acc[0][1], af, Lb[(8 * bj0 + fr) * S36 + 4 * ks + fc]);
+                    if (!skip1) dmma884(acc[1][0], acc[1][1], af, Lb[(8 * (bj0 + 1) + fr) * S36 + 4 * ks + fc]);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 0 ? skip0 : skip1) continue;
+                    const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * (bj0 + q) + 2 * fc;
+                    if (in_band(a, i, j)) __stcg(ab_at(a, i, j), oldv[q][0] - acc[q][0]);
+                    if (in_band(a, i, j + 1)) __stcg(ab_at(a, i, j + 1), oldv[q][1] - acc[q][1]);
+                }
+                if (I == p + 2 && (J == p + 1 || J == p + 2)) {   // what P stages for panel p+2
+                    __syncthreads();
+                    if (tid == 0) red_release(a.flags + 3 * NP + p, 1);
+                }
+            }
+        }
+    }
+    (void)upd_done;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) band_chol3_kernel(Args3 a) {
     extern __shared__ double smem[];
     if (blockIdx.x == 0) role_P(a, smem);
     else if (blockIdx.x == 1) role_R(a, smem);
+    else if (a.two_phase) role_U2(a, smem);
     else role_U(a, smem);
 }
 
@@ -970,6 +1092,7 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
     a.LB = (double*)workspace;
     a.LI = a.LB + tiles * T32;
     a.flags = (int*)(a.LI + (long long)a.NP * T32);
+    a.two_phase = (a.WB * (a.WB + 1) / 2 - 1 > n_ctas - 2 || (g_debug3 & 64)) ? 1 : 0;
     a.prof = (long long*)((char*)workspace + ws_bytes3(n, bw) - 1024);
     a.debug = g_debug3;
     if (cudaMemsetAsync(a.flags, 0, 4 * (size_t)a.NP * sizeof(int), (cudaStream_t)stream) != cudaSuccess)

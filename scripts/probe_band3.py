@@ -35,7 +35,7 @@ json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe_band3.json"), "w"), 
 # per-phase cycle counters (debug flag 4), with (4) and without (5) the trailing-update work, and without back substitution (6)
 import numpy as np
 L = lib.load()
-bw = 370
+bw = int(os.environ.get("PBW", "370"))
 g = torch.Generator().manual_seed(0)
 AB = torch.randn((n, bw + 1), generator=g, dtype=torch.float64); AB[:, bw] = AB.abs().sum(1) * 2 + 1.0
 band = ops.Band(n, bw, None, "cuda"); ABd = AB.cuda(); rd = torch.randn(n, generator=g, dtype=torch.float64).cuda()

@@ -59,6 +59,32 @@ def test_band_solve_matches_dense(n, bw, cluster, variant):
             assert (Lb[off:, d] - L_ref.diagonal(-off)).abs().max() < 1e-10
 
 
+@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (256, 40, 4), (97, 13, 3), (1000, 150, 64), (2000, 64, 16), (333, 332, 8)])
+def test_band_solve_v3_tile_owner_update_path(n, bw, ctas):
+    """The wide-band update role (fixed tile owners, L(I,p) formed once per row) forced on shapes that normally take
+    the one-tile-per-CTA role."""
+    from super_b200 import ops, lib
+    A, b = _random_band_system(n, bw, seed=n + bw + 1)
+    band = ops.Band(n, bw, None, "cuda")
+    AB = torch.zeros((n, bw + 1), dtype=torch.float64)
+    for d in range(bw + 1):
+        off = bw - d
+        if off < n:
+            AB[off:, d] = A.diagonal(-off)
+    band.AB.copy_(AB.cuda())
+    band.g.copy_(b.cuda())
+    u = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+    lib.load().sb_band3_debug(64)
+    try:
+        ops.band_solve(band, u.data_ptr(), ctas, variant=3)
+        x = band.g.cpu()
+    finally:
+        lib.load().sb_band3_debug(0)
+    x_ref = torch.linalg.solve(A + 0.5 * torch.eye(n, dtype=torch.float64), b)
+    assert int(band.info.item()) == 0
+    assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
+
+
 def test_band_solve_flags_indefinite_matrix():
     from super_b200 import ops
     n, bw = 64, 4
