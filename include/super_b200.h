@@ -65,8 +65,10 @@ typedef struct SbFuseParams {
     float time_now;         /* sfdata.time */
     int disable_merging_new, disable_merging_exist, disable_adding_new;
     int class_gate;         /* merges need equal classes: (hard_seg or data == superv1) and seg present, nodes.py:314-316 */
-    int semantic_weights;   /* kNN weights softmax(sqrt(exp(-JSD)) sqrt(exp(-d/r))), nodes.py:183-189,466-484,505-511 */
+    int semantic_weights;   /* kNN weights softmax(sqrt(exp(-JSD)) sqrt(exp(-d/r))): bit 0 = existing surfels every frame
+                             * (nodes.py:466-484), bit 1 = appended surfels (nodes.py:503-509, not under --hard_seg) */
     const double* ed_seg_conf;  /* (J,C) f64 node class probabilities (semantic_weights) */
+    const int* ed_seg;          /* (J,) i32 node classes: new surfels search their nodes inside their own class (--hard_seg, nodes.py:494-497) or NULL */
 } SbFuseParams;
 
 int sb_version(void);
@@ -78,6 +80,12 @@ int sb_version(void);
  * d2 = ((dx*dx + dy*dy) + dz*dz), ties -> lower index. */
 int sb_knn(const double* query, int nq_cap, const int* nq_dev, const double* ref, int nref, int dim, int K,
            double* out_dist, int* out_idx, void* stream);
+
+/* find_knn with num_classes > 0 (--hard_seg): /root/reference/utils/utils.py:222-242.  Neighbours are searched among the
+ * reference points whose class rseg[j] equals the query's class qseg[i]; indices stay global; 1e8 / -1 when the class
+ * has fewer than K points.  qseg == rseg == NULL: plain sb_knn. */
+int sb_knn_class(const double* query, int nq_cap, const int* nq_dev, const int* qseg, const double* ref, int nref,
+                 const int* rseg, int dim, int K, double* out_dist, int* out_idx, void* stream);
 
 /* softmax_k(exp(-d_k/r_k)) and the "no node within its radius" test:
  * /root/reference/super/nodes.py:164-167 (radius_mode 1: r = radii[i]) and :179-191 (mode 0: r = radii[idx]).

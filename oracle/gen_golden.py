@@ -164,13 +164,22 @@ SEM_OPT = dict(use_derived_gradient=False, mesh_face=True, mesh_arap=False, sf_p
                del_seg_classes=[], disable_ssim_conf=True)
 
 
+HARD_FLAGS = ["--load_seg", "--seg_dir", "seg", "--disable_ssim_conf", "--hard_seg", "--sf_hard_seg_point_plane", "--mesh_rot",
+              "--mesh_face", "--mesh_arap"]
+HARD_OPT = dict(use_derived_gradient=False, mesh_face=True, mesh_arap=True, sf_point_plane=False, optimizer="SGD",
+                method="semantic-super", data="superv2", num_classes=3, sf_soft_seg_point_plane=False,
+                sf_hard_seg_point_plane=True, sf_bn_morph=False, hard_seg=True, del_seg_classes=[], disable_ssim_conf=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lm", "gf", "sem", "track"]
+    which = sys.argv[1:] or ["lm", "gf", "sem", "hard", "track"]
     if "lm" in which:
         gen_lm("lm_128x96", 96, 128, 16, 4, 3.0)
     if "gf" in which:
         gen_gf("gf_128x96", 96, 128, 16, 3, 3.0, GF_FLAGS, GF_OPT)
     if "track" in which:
         gen_track("track_128x96", 96, 128, 16, 4, 3.0)
+    if "hard" in which:
+        gen_gf("gf_hard_128x96", 96, 128, 16, 3, 3.0, HARD_FLAGS, HARD_OPT, semantic=True, seg_speed=15.0)
     if "sem" in which:
         gen_gf("gf_sem_128x96", 96, 128, 16, 3, 3.0, SEM_FLAGS, SEM_OPT, semantic=True, seg_speed=15.0)

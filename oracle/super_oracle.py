@@ -44,6 +44,23 @@ def knn(p1, p2, K, chunk=8192):
     return torch.sqrt(torch.cat(d_out)), torch.cat(i_out)
 
 
+def knn_class(p1, p2, K, seg1, seg2, num_classes):
+    """find_knn with num_classes > 0 (/root/reference/utils/utils.py:222-242, --hard_seg): neighbours are searched
+    among the reference points of the query's own class; indices are global; rows of an absent class keep 1e8 / -1."""
+    d = 1e8 * torch.ones((len(p1), K), dtype=F64)
+    idx = -torch.ones((len(p1), K), dtype=torch.long)
+    for c in range(num_classes):
+        m1 = seg1 == c
+        i2 = (seg2 == c).nonzero(as_tuple=True)[0]
+        if int(m1.sum()) == 0 and len(i2) == 0:
+            continue
+        assert int(m1.sum()) > 0 and len(i2) >= K
+        dc, ic = knn(p1[m1], p2[i2], K)
+        d[m1] = dc
+        idx[m1] = i2[ic]
+    return d, idx
+
+
 def kld(P, Q, eps=1e-13):
     """/root/reference/utils/utils.py:244-250"""
     return (P * (P / (Q + eps) + eps).log()).sum(-1)
@@ -338,12 +355,19 @@ def init_surfels(opt, nd, graph):
     sf.semantic = (opt.method == "semantic-super")
     sf.track_id = None
     # update_ed :154-168  (divides by the QUERY node's radius)
-    d, idx = knn(graph.points, graph.points, opt.num_ED_neighbors + 1)
+    hard = bool(getattr(opt, "hard_seg", False))
+    if hard:
+        d, idx = knn_class(graph.points, graph.points, opt.num_ED_neighbors + 1, graph.seg, graph.seg, opt.num_classes)
+    else:
+        d, idx = knn(graph.points, graph.points, opt.num_ED_neighbors + 1)
     d = d[:, 1:] / graph.radii[:, None]
     graph.knn_w = F.softmax(torch.exp(-d), dim=-1)
     graph.knn_indices = idx[:, 1:]
     # update_sfed_knn :170-191
-    d, sf.knn_indices = knn(sf.points, graph.points, opt.num_neighbors)
+    if hard:
+        d, sf.knn_indices = knn_class(sf.points, graph.points, opt.num_neighbors, sf.seg, graph.seg, opt.num_classes)
+    else:
+        d, sf.knn_indices = knn(sf.points, graph.points, opt.num_neighbors)
     r = graph.radii[sf.knn_indices]
     sf.isStable[~torch.any(d <= r, dim=1)] = False
     if sf.semantic and not getattr(opt, "hard_seg", False):
@@ -751,7 +775,10 @@ def fuse(opt, sf, nd, max_layers=16):
         addc = add_valid[nd.valid]
         if addc.count_nonzero() > 0:
             npts = nd.points[addc]
-            d, nidx = knn(npts, sf.ED.points, opt.num_neighbors)
+            if getattr(opt, "hard_seg", False):
+                d, nidx = knn_class(npts, sf.ED.points, opt.num_neighbors, nd.seg[addc], sf.ED.seg, opt.num_classes)
+            else:
+                d, nidx = knn(npts, sf.ED.points, opt.num_neighbors)
             r = sf.ED.radii[nidx]
             ok = torch.any(d <= r, dim=1)
             if sf.semantic and not getattr(opt, "hard_seg", False):

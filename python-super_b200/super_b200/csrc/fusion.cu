@@ -260,7 +260,8 @@ constexpr int ADD_TILE = 512;
 
 __global__ void __launch_bounds__(ADD_BLOCK)
 add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* __restrict__ ed_radii, int J,
-               int* __restrict__ add_flag, int* __restrict__ add_idx, double* __restrict__ add_dist) {
+               int* __restrict__ add_flag, int* __restrict__ add_idx, double* __restrict__ add_dist,
+               const int* __restrict__ ed_seg) {
     __shared__ double tile[ADD_TILE * 3];
     const int P = fr.H * fr.W;
     const int p = blockIdx.x * ADD_BLOCK + threadIdx.x;
@@ -270,9 +271,12 @@ add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* _
     int bi[SB_KNN];
     for (int k = 0; k < SB_KNN; ++k) { bd[k] = INFINITY; bi[k] = -1; }
     double qx = 0, qy = 0, qz = 0;
+    const bool by_class = ed_seg != nullptr && fr.seg != nullptr;
+    int qc = 0;
     if (active) {
         const float4 pv = reinterpret_cast<const float4*>(fr.vmap)[p];
         qx = pv.x; qy = pv.y; qz = pv.z;
+        if (by_class) qc = fr.seg[p];
     }
     for (int t0 = 0; t0 < J; t0 += ADD_TILE) {
         const int cnt = min(ADD_TILE, J - t0);
@@ -281,6 +285,7 @@ add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* _
         __syncthreads();
         if (active) {
             for (int j = 0; j < cnt; ++j) {
+                if (by_class && ed_seg[t0 + j] != qc) continue;
                 const double dx = subr(qx, tile[3 * j]), dy = subr(qy, tile[3 * j + 1]), dz = subr(qz, tile[3 * j + 2]);
                 const double d2 = addr(addr(mulr(dx, dx), mulr(dy, dy)), mulr(dz, dz));
                 if (d2 < bd[SB_KNN - 1]) {
@@ -298,6 +303,7 @@ add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* _
     if (!active) return;
     bool any = false;
     for (int k = 0; k < SB_KNN; ++k) {
+        if (bi[k] < 0) { bi[k] = 0; bd[k] = 1e16; }      // class with fewer than K nodes (the reference asserts)
         bd[k] = __dsqrt_rn(bd[k]);
         any |= bd[k] <= ed_radii[bi[k]];       // nodes.py:501-502
         add_idx[4 * (size_t)p + k] = bi[k];
@@ -329,7 +335,7 @@ __global__ void add_write_kernel(SbSurfels sf, SbFrame fr, SbFuseParams pr, cons
         const int n_ = add_idx[4 * (size_t)p + k];
         sf.knn_idx[4 * (size_t)dst + k] = n_;
         e[k] = exp(-add_dist[4 * (size_t)p + k] / ed_radii[n_]);
-        if (pr.semantic_weights && qc) {                                 // nodes.py:505-509
+        if ((pr.semantic_weights & 2) && qc) {                           // nodes.py:503-509 (not under --hard_seg)
             const double* P = pr.ed_seg_conf + (size_t)n_ * C;
             double k1 = 0.0, k2 = 0.0;
             for (int q = 0; q < C; ++q) {
@@ -561,7 +567,7 @@ int sb_fuse(const SbSurfels* sfp, const SbFrame* frp, const double* ed_points, c
     SB_CHECK_LAUNCH();
     // weights of ALL existing surfels from their fused positions and old indices (nodes.py:480-484)
     int rc;
-    if (pr.semantic_weights) {
+    if (pr.semantic_weights & 1) {                // all existing surfels: semantic-super, with or without --hard_seg
         if (!pr.ed_seg_conf || !sf.seg_conf) return SB_ERR_ARG;
         rc = sb_reweight_semantic(sf.points, sf.knn_idx, sf.cap, sf.n_dev, ed_points, ed_radii, pr.ed_seg_conf, sf.seg_conf,
                                   sf.n_classes, sf.knn_w, stream);
@@ -571,7 +577,7 @@ int sb_fuse(const SbSurfels* sfp, const SbFrame* frp, const double* ed_points, c
     if (rc) return rc;
     if (!pr.disable_adding_new && !pr.disable_merging_new) {
         add_knn_kernel<<<(P + ADD_BLOCK - 1) / ADD_BLOCK, ADD_BLOCK, 0, s>>>(fr, ed_points, ed_radii, J, w.add_flag,
-                                                                             w.add_idx, w.add_dist);
+                                                                             w.add_idx, w.add_dist, pr.ed_seg);
         SB_CHECK_LAUNCH();
         cudaMemsetAsync(w.add_flag + P, 0, sizeof(int), s);
         cb = w.cub_bytes;

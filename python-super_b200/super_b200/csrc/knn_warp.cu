@@ -19,7 +19,8 @@ constexpr int KNN_MAXK = 8;
 template <int K>
 __global__ void __launch_bounds__(KNN_BLOCK)
 knn_kernel(const double* __restrict__ q, int nq_cap, const int* nq_dev, const double* __restrict__ ref, int nref,
-           int dim, double* __restrict__ out_d, int* __restrict__ out_i) {
+           int dim, double* __restrict__ out_d, int* __restrict__ out_i, const int* __restrict__ qseg,
+           const int* __restrict__ rseg) {
     __shared__ double tile[KNN_TILE * 3];
     const int nq = n_active(nq_cap, nq_dev);
     const int i = blockIdx.x * KNN_BLOCK + threadIdx.x;
@@ -28,6 +29,7 @@ knn_kernel(const double* __restrict__ q, int nq_cap, const int* nq_dev, const do
 #pragma unroll
     for (int k = 0; k < K; ++k) { bd[k] = INFINITY; bi[k] = -1; }
     double qx = 0, qy = 0, qz = 0;
+    const int qc = (qseg && i < nq) ? qseg[i] : 0;      // --hard_seg: neighbours of the query's own class only
     if (i < nq) {
         qx = q[dim * (size_t)i];
         qy = q[dim * (size_t)i + 1];
@@ -40,6 +42,7 @@ knn_kernel(const double* __restrict__ q, int nq_cap, const int* nq_dev, const do
         __syncthreads();
         if (i < nq) {
             for (int j = 0; j < cnt; ++j) {
+                if (rseg && rseg[t0 + j] != qc) continue;
                 const double dx = subr(qx, tile[dim * j]), dy = subr(qy, tile[dim * j + 1]);
                 double d2 = addr(mulr(dx, dx), mulr(dy, dy));
                 if (dim > 2) {
@@ -63,8 +66,8 @@ knn_kernel(const double* __restrict__ q, int nq_cap, const int* nq_dev, const do
     if (i < nq) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            out_d[(size_t)i * K + k] = __dsqrt_rn(bd[k]);   // find_knn returns sqrt(d2)
-            out_i[(size_t)i * K + k] = bi[k];
+            out_d[(size_t)i * K + k] = (bi[k] >= 0) ? __dsqrt_rn(bd[k]) : 1e8;   // find_knn returns sqrt(d2); 1e8 / -1 when
+            out_i[(size_t)i * K + k] = bi[k];                                     // the class has fewer than K points
         }
     }
 }
@@ -210,13 +213,18 @@ extern "C" {
 
 int sb_knn(const double* query, int nq_cap, const int* nq_dev, const double* ref, int nref, int dim, int K,
            double* out_dist, int* out_idx, void* stream) {
-    if (!query || !ref || !out_dist || !out_idx) return SB_ERR_ARG;
+    return sb_knn_class(query, nq_cap, nq_dev, nullptr, ref, nref, nullptr, dim, K, out_dist, out_idx, stream);
+}
+
+int sb_knn_class(const double* query, int nq_cap, const int* nq_dev, const int* qseg, const double* ref, int nref,
+                 const int* rseg, int dim, int K, double* out_dist, int* out_idx, void* stream) {
+    if (!query || !ref || !out_dist || !out_idx || ((qseg == nullptr) != (rseg == nullptr))) return SB_ERR_ARG;
     if (K < 1 || K > KNN_MAXK || nref < K || (dim != 2 && dim != 3)) return SB_ERR_ARG;
     if (nq_cap <= 0) return SB_OK;
     const int blocks = (nq_cap + KNN_BLOCK - 1) / KNN_BLOCK;
     cudaStream_t s = (cudaStream_t)stream;
 #define SB_KNN_CASE(KK) \
-    case KK: knn_kernel<KK><<<blocks, KNN_BLOCK, 0, s>>>(query, nq_cap, nq_dev, ref, nref, dim, out_dist, out_idx); break;
+    case KK: knn_kernel<KK><<<blocks, KNN_BLOCK, 0, s>>>(query, nq_cap, nq_dev, ref, nref, dim, out_dist, out_idx, qseg, rseg); break;
     switch (K) {
         SB_KNN_CASE(1) SB_KNN_CASE(2) SB_KNN_CASE(3) SB_KNN_CASE(4) SB_KNN_CASE(5) SB_KNN_CASE(6) SB_KNN_CASE(7)
         SB_KNN_CASE(8)

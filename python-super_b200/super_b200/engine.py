@@ -41,7 +41,7 @@ class SbFuseParams(ctypes.Structure):
     _fields_ = [("th_dist", ctypes.c_double), ("th_cos", ctypes.c_double), ("time_now", ctypes.c_float),
                 ("disable_merging_new", ctypes.c_int), ("disable_merging_exist", ctypes.c_int),
                 ("disable_adding_new", ctypes.c_int), ("class_gate", ctypes.c_int), ("semantic_weights", ctypes.c_int),
-                ("ed_seg_conf", ctypes.c_void_p)]
+                ("ed_seg_conf", ctypes.c_void_p), ("ed_seg", ctypes.c_void_p)]
 
 
 SURFEL_FIELDS = (("points", 3, F64), ("norms", 3, F64), ("colors", 3, F32), ("confs", 0, F32), ("radii", 0, F64),
@@ -203,7 +203,10 @@ def build_graph(opt, frame):
     g.node_pos[order] = torch.arange(J, dtype=I32, device=dev)
     g.anchor_uv = torch.stack([u, v], 1)
     # update_ed (/root/reference/super/nodes.py:154-168): K+1 nearest, drop self, weights use the query radius
-    dist, idx = ops.knn(g.points, g.points, opt.num_ED_neighbors + 1)
+    g.seg_i32 = g.seg.to(I32).contiguous() if hasattr(g, "seg") else None
+    hard = bool(getattr(opt, "hard_seg", False)) and g.seg_i32 is not None
+    dist, idx = ops.knn(g.points, g.points, opt.num_ED_neighbors + 1, qseg=g.seg_i32 if hard else None,
+                        rseg=g.seg_i32 if hard else None)                  # nodes.py:157-163
     g.knn_indices = idx[:, 1:].contiguous()
     g.knn_w = ops.knn_weights(dist[:, 1:].contiguous(), g.knn_indices, g.radii, radius_mode=1)
     pos = g.node_pos.long()
@@ -309,12 +312,15 @@ class Tracker:
         b.time_stamp[:n] = frame.time
         b.stable[:n] = 1
         b.n_dev.fill_(n)
-        dist, idx = ops.knn(b.points[:n], self.ED.points, opt.num_neighbors)
-        b.knn_idx[:n] = idx
-        b.knn_w[:n] = ops.knn_weights(dist, idx, self.ED.radii, 0, b.stable)      # also clears stable (radius test)
+        hard = self.semantic and bool(getattr(opt, "hard_seg", False))
         if self.semantic:
             b.seg[:n] = frame.seg[valid]
             b.seg_conf[:n] = frame.seg_conf[valid]
+        dist, idx = ops.knn(b.points[:n], self.ED.points, opt.num_neighbors, qseg=b.seg[:n] if hard else None,
+                            rseg=self.ED.seg_i32 if hard else None)        # nodes.py:172-178
+        b.knn_idx[:n] = idx
+        b.knn_w[:n] = ops.knn_weights(dist, idx, self.ED.radii, 0, b.stable)      # also clears stable (radius test)
+        if self.semantic:
             if self.sem_weights and not getattr(opt, "hard_seg", False):          # nodes.py:183-189
                 call("sb_reweight_semantic", ptr(b.points), ptr(b.knn_idx), n, None, ptr(self.ED.points),
                      ptr(self.ED.radii), ptr(self.ED.seg_conf), ptr(b.seg_conf), C, ptr(b.knn_w), stream())
@@ -414,9 +420,12 @@ class Tracker:
         sem = bool(getattr(self, "semantic", False))
         gate = sem and (bool(getattr(opt, "hard_seg", False)) or opt.data == "superv1")
         semw = sem and bool(getattr(self, "sem_weights", False))
+        hard = sem and bool(getattr(opt, "hard_seg", False))
         return SbFuseParams(opt.th_dist, opt.th_cosine_ang, float(frame.time), int(bool(opt.disable_merging_new_surfels)),
                             int(bool(opt.disable_merging_exist_surfels)), int(bool(opt.disable_adding_new_surfels)),
-                            int(gate), int(semw), ptr(self.ED.seg_conf) if semw else None)
+                            int(gate), (1 if semw else 0) | (2 if semw and not hard else 0),
+                            ptr(self.ED.seg_conf) if semw else None,
+                            ptr(self.ED.seg_i32) if hard else None)
 
     def view(self, n):
         """Views of the first n rows of the current buffers, in the layouts the LM solver takes."""

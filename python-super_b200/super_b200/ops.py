@@ -26,13 +26,15 @@ def as_i32(idx):
 
 
 # ---- kNN / weights / warp ----------------------------------------------------------------------
-def knn(query, ref, K, n_dev=None):
-    """find_knn (/root/reference/utils/utils.py:212-220): (sqrt dists (N,K) f64, idx (N,K) i32)."""
+def knn(query, ref, K, n_dev=None, qseg=None, rseg=None):
+    """find_knn (/root/reference/utils/utils.py:212-242): (sqrt dists (N,K) f64, idx (N,K) i32).  qseg/rseg (i32):
+    the per-class search of --hard_seg."""
     query, ref = _dev(query).contiguous(), _dev(ref).contiguous()
     n, dim = query.shape
     dist = torch.empty((n, K), dtype=F64, device=query.device)
     idx = torch.empty((n, K), dtype=I32, device=query.device)
-    call("sb_knn", ptr(query), n, ptr(n_dev), ptr(ref), ref.shape[0], dim, K, ptr(dist), ptr(idx), stream())
+    call("sb_knn_class", ptr(query), n, ptr(n_dev), ptr(qseg), ptr(ref), ref.shape[0], ptr(rseg), dim, K, ptr(dist),
+         ptr(idx), stream())
     return dist, idx
 
 

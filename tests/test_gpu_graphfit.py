@@ -29,11 +29,12 @@ def _device_inputs(g, t):
         trg[nd.valid] = nd.seg_conf
         seg = NS(sf_seg=sf.seg.to(torch.int32).cuda(), sf_seg_conf=sf.seg_conf.cuda().contiguous(),
                  trg_seg_conf=trg.cuda(), scores=nd.seg_conf_in[0].cuda().contiguous())
-        seg.edge_pts, seg.edge_off = graphfit.edge_points(nd.seg_in[0, 0].cuda(), g.opt.num_classes, g.H, g.W)
+        if getattr(g.opt, "sf_bn_morph", False):
+            seg.edge_pts, seg.edge_off = graphfit.edge_points(nd.seg_in[0, 0].cuda(), g.opt.num_classes, g.H, g.W)
     return sf, nd, d, maps, cam, seg
 
 
-@pytest.mark.parametrize("name", ["gf_128x96", "gf_sem_128x96"])
+@pytest.mark.parametrize("name", ["gf_128x96", "gf_sem_128x96", "gf_hard_128x96"])
 def test_graphfit_matches_reference(name):
     """Per-iteration deform_verts, consumed gradient, loss terms and the result against the reference's autograd."""
     from super_b200 import graphfit
@@ -132,7 +133,7 @@ def test_semantic_fuse_and_compact_match_reference():
                         n_dev=trk.cur.n_dev)
         graphfit.update_global(v.points, v.norms, trk.ED.points, trk.ED.norms, dv, n_dev=trk.cur.n_dev)
         pr = trk.fuse_params(fr)
-        assert pr.semantic_weights == 1 and pr.class_gate == 0          # superv2, no --hard_seg
+        assert pr.semantic_weights == 3 and pr.class_gate == 0          # superv2, no --hard_seg
         call("sb_fuse", trk.cur.ref(), fr.ref(), ptr(trk.ED.points), ptr(trk.ED.radii), trk.ED.num, ctypes.byref(pr),
              None, 0, ptr(trk.n_tmp), ptr(trk.overflow), ptr(trk.fuse_ws), trk.fuse_ws.numel(), stream())
         trk.cur.n_dev.copy_(trk.n_tmp)
@@ -175,3 +176,28 @@ def test_free_running_semantic_tracker_follows_oracle():
         assert rel < 1e-4, (t, mine[-1], tr[-1])
         assert (beta.cpu() - dv).abs().max() < 1e-6
         assert trk.num_surfels() == len(sf.points)
+
+
+def test_hard_seg_tracker_follows_reference():
+    """--hard_seg end to end on the device: per-class kNN (graph, init, appended surfels), class-gated merges,
+    class-pruned graph, hard-seg point-plane weights -- state after every frame vs the reference's (teacher-forced by
+    construction: the device tracker free-runs from the same inputs and the integers must stay equal)."""
+    g = Golden("gf_hard_128x96")
+    from super_b200 import engine
+    trk = engine.Tracker(g.opt, device="cuda:0")
+    for t in g.frames:
+        fr = g.frame(t)
+        beta = trk.step(torch.from_numpy(fr["depth"]).cuda(), torch.from_numpy(fr["color"]).cuda(),
+                        torch.from_numpy(fr["K"]), torch.from_numpy(fr["inv_K"]), fr["time"],
+                        seg_scores=torch.from_numpy(fr["seg_conf"]).cuda())
+        ref = g.state(t)
+        snap = trk.snapshot()
+        assert len(snap["points"]) == len(ref.points), t
+        assert torch.equal(snap["knn_indices"].cpu(), ref.knn_indices), t
+        assert torch.equal(snap["seg"].cpu(), ref.seg), t
+        assert (snap["knn_w"].cpu() - ref.knn_w).abs().max() < 1e-6
+        if t == g.frames[0]:
+            assert torch.equal(trk.ED.knn_indices.cpu().long(), ref.ED.knn_indices)
+            assert torch.equal(trk.ED.triangles.cpu(), ref.ED.triangles)
+        else:
+            assert np.abs(beta.cpu().numpy() - g[f"f{t}.beta"]).max() < 1e-6

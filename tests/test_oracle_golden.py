@@ -102,7 +102,7 @@ def test_update_fuse_compact_match_reference(t):
 
 
 # ---- autograd optimiser (GraphFit) fixtures: configs 3b (Adam, LM terms + face) and 4 (semantic, SGD) ----------
-@pytest.mark.parametrize("name", ["gf_128x96", "gf_sem_128x96"])
+@pytest.mark.parametrize("name", ["gf_128x96", "gf_sem_128x96", "gf_hard_128x96"])
 def test_graphfit_port_reproduces_reference(name):
     """oracle/graphfit_oracle.py, teacher-forced with the reference's pre-frame state, reproduces the reference's
     per-iteration deform_verts, loss terms, consumed gradient, result and Surfels.update output."""
@@ -145,3 +145,23 @@ def test_tracked_points_port_reproduces_reference():
         assert len(trk.sf.points) == int(z[f"f{t}.N"])
         assert np.array_equal(trk.sf.track_id.numpy(), z[f"f{t}.track_id"])
         assert np.abs(trk.track_rsts[fr["filename"]].numpy() - z[f"f{t}.track_rsts"]).max() < 1e-5
+
+
+def test_hard_seg_state_port_reproduces_reference():
+    """--hard_seg: per-class kNN at init and for appended surfels, class-gated merges, class-pruned graph: the port,
+    free running on the fixture's inputs, reproduces the reference's state after every frame."""
+    from oracle import graphfit_oracle as gf
+    g = Golden("gf_hard_128x96")
+    sf = None
+    for t in g.frames:
+        nd = g.new_data(t)
+        if sf is None:
+            sf = so.init_surfels(g.opt, nd, so.build_graph(g.opt, nd))
+        else:
+            dv = gf.graph_fit(g.opt, sf, nd)
+            so.update(g.opt, sf, dv); so.fuse(g.opt, sf, nd); so.compact(g.opt, sf, float(t))
+        ref = g.state(t)
+        assert len(sf.points) == len(ref.points)
+        assert torch.equal(sf.knn_indices, ref.knn_indices) and torch.equal(sf.seg, ref.seg)
+        assert torch.equal(sf.ED.knn_indices, ref.ED.knn_indices) and torch.equal(sf.ED.triangles, ref.ED.triangles)
+        assert (sf.points - ref.points).abs().max() < 1e-12 and (sf.knn_w - ref.knn_w).abs().max() < 1e-12
