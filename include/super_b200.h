@@ -192,6 +192,12 @@ int sb_band3_debug(int flags); /* timing experiments only: 1 no trailing update,
 long long sb_band3_prof_offset(int n, int bw);
 int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                    void* workspace, long long ws_bytes, int n_ctas, void* stream);
+/* v4 = v3's pipeline run from BOTH ends of the band at once (two partial factorisations: top-down on the matrix, bottom-up on a
+ * reversed copy), the middle block (>= bw rows) solved last, two concurrent back substitutions outwards: the pivot chain --
+ * the solve's critical path -- is n/2 + bw/2 long instead of n.  Falls back to v3 for systems too small to split. */
+long long sb_band4_workspace_bytes(int n, int bw, int ldab);
+int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                   void* workspace, long long ws_bytes, int n_ctas, void* stream);
 int sb_band_max_bw(void);
 int sb_band_debug(int flags); /* timing experiments only: 1 skip trailing update, 2 skip back-substitution, 4 skip panel math */
 int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,

@@ -40,6 +40,9 @@ struct Args3 {
     double* LI;      // L(k,k)^-1, tile k at k*1024, row-major
     int* flags;      // diag_done[NP] | rows_done[NP] | upd_done[NP] | hot_done[NP]
     int NP, WB;
+    int ke;            // panels to eliminate: NP = full solve; < NP = partial factorisation (two-sided solve), the trailing
+                       // tiles keep the Schur complement and R stops after the forward substitution
+    int rank0, ncta;   // this instance's CTAs are blockIdx.x in [rank0, rank0 + ncta)
     int two_phase;     // wide bands (more trailing tiles than update CTAs): L(I,p) once per row, then one product per tile
     long long* prof;   // 32 counters (debug & 4)
     int debug;         // 1: U skips its tile work, 2: no back substitution, 4: cycle counters
@@ -446,7 +449,7 @@ __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const vola
 // D[8bi.., 8bj..] -= Lx[8bi..] Lx[8bj..]^T for up to two lower blocks (bi0,bj0), (bi1,bj1) (bi1 < 0: one block), with the
 // damping / identity padding on diagonal entries; the two accumulator chains are interleaved
 __device__ __forceinline__ void syrk_blocks(const double* __restrict__ Lx, double* __restrict__ D, bool has_prev, int bi0,
-                                            int bj0, int bi1, int bj1, int k, int n, double u, int lane) {
+                                            int bj0, int bi1, int bj1, int k, int n, double u, int lane, bool damp = true) {
     const int fr = lane >> 2, fc = lane & 3;
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     if (has_prev) {
@@ -461,8 +464,8 @@ __device__ __forceinline__ void syrk_blocks(const double* __restrict__ Lx, doubl
         if (q == 1 && bi1 < 0) break;
         const int i = 8 * (q ? bi1 : bi0) + fr, j = 8 * (q ? bj1 : bj0) + 2 * fc, gi = NB * k + i;
         double v0 = D[i * S33 + j] - (q ? b0 : a0), v1 = D[i * S33 + j + 1] - (q ? b1 : a1);
-        if (i == j) v0 = (gi < n) ? v0 + u : 1.0;
-        if (i == j + 1) v1 = (gi < n) ? v1 + u : 1.0;
+        if (damp && i == j) v0 = (gi < n) ? v0 + u : 1.0;
+        if (damp && i == j + 1) v1 = (gi < n) ? v1 + u : 1.0;
         D[i * S33 + j] = v0;
         D[i * S33 + j + 1] = v1;
     }
@@ -503,7 +506,8 @@ __device__ void role_P(const Args3& a, double* smem) {
     int* rows_done = a.flags + NP;
     int* upd_done = a.flags + 2 * NP;
     int* hot_done = a.flags + 3 * NP;      // the two tiles P stages next, signalled by their owners as soon as they are done
-    const int NU = (int)gridDim.x - 2;
+    const int NU = a.ncta - 2;
+    const int KE = a.ke;
     const int hot_expected = (WB >= 2) ? 2 : 0;
     const double u = a.u ? *a.u : 0.0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -537,7 +541,9 @@ __device__ void role_P(const Args3& a, double* smem) {
     // The volatile shared load below cannot, and the clock read is made control-dependent on its value.
 #define PROF(slot) do { if (prof) { if (*(volatile double*)dinvs != 1.2345e300) t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; } } while (0)
     if (prof && tid == 0) { a.prof[8] = clock64(); for (int q = 16; q < 24; ++q) a.prof[q] = 0; }
-    for (int k = 0; k < NP; ++k) {
+    // partial mode (KE < NP): one more, reduced, step k = KE forms L(KE,KE-1) and the un-damped D(KE,KE) and writes them back
+    for (int k = 0; k < NP && k <= KE; ++k) {
+        const bool tail = (k == KE);
         double* D = Dbuf + (k & 1) * T33;
         double* X = Xbuf + (k & 1) * T36;
         double* Lx = Lxbuf + (k & 1) * T36;
@@ -550,7 +556,7 @@ __device__ void role_P(const Args3& a, double* smem) {
         const long long tA = t0;
         if (cw >= 0) {
             // ---- L(k,k-1) = A(k,k-1) L(k-1,k-1)^-T, then D = A(k,k) - L(k,k-1) L(k,k-1)^T (+ u on the diagonal) ----
-            if (cw == 3) {   // warp "T": NaN-arm the diagonal blocks of this panel's inverse tile
+            if (cw == 3 && !tail) {   // warp "T": NaN-arm the diagonal blocks of this panel's inverse tile
                 double* Ls = Linv + (k & 1) * T36;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -564,10 +570,18 @@ __device__ void role_P(const Args3& a, double* smem) {
             PROF(2);
             // D -= L(k,k-1) L(k,k-1)^T (+ damping): only block column 0 is needed before the pivot chain can start, so the
             // four warps do (cw,0) first; the other six lower blocks follow on the helper warps behind the chain
-            syrk_blocks(Lx, D, k >= 1, cw, 0, -1, -1, k, n, u, lane);
+            syrk_blocks(Lx, D, k >= 1, cw, 0, -1, -1, k, n, u, lane, !tail);
             bar_sync(2, 128);
             PROF(3);
-            if (warp == 0) {
+            if (tail) {
+                // Schur complement of the first non-eliminated panel: the other six blocks, then back to the band storage
+                if (cw >= 1) syrk_blocks(Lx, D, k >= 1, cw, 1, (cw == 1) ? 2 : 3, (cw == 3) ? 3 : 2, k, n, u, lane, false);
+                bar_sync(2, 128);
+                for (int e = cw * 32 + lane; e < T32; e += 128) {
+                    const int r = e >> 5, c = e & 31, i = NB * k + r, j = NB * k + c;
+                    if (c <= r && in_band(a, i, j)) __stcg(ab_at(a, i, j), D[r * S33 + c]);
+                }
+            } else if (warp == 0) {
                 if (warp_potrf_blocked(D, Lc, dv, Linv + (k & 1) * T36, lane, prof ? tsacc : nullptr, tA)) *a.info = 1;
                 PROF(4);
             } else {
@@ -593,7 +607,7 @@ __device__ void role_P(const Args3& a, double* smem) {
             }
         } else if (warp == 1) {
             // ---- L(k,k)^-1 behind the Cholesky; publish to shared (next panel's product) and global (U, R) ----
-            {   // zero the inverse tile while the products of this panel run, then build it behind the Cholesky
+            if (!tail) {   // zero the inverse tile while the products of this panel run, then build it behind the Cholesky
                 long long w0 = prof ? clock64() : 0;
                 double* Ls = Linv + (k & 1) * T36;
                 for (int e = lane; e < T36; e += 32) {
@@ -605,7 +619,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                                   prof ? tsacc : nullptr, tA);
                 if (prof) w1acc += clock64() - w0;
             }
-            if (NB * k + lane < n) a.dinv[NB * k + lane] = dv[lane];
+            if (!tail && NB * k + lane < n) a.dinv[NB * k + lane] = dv[lane];
             if (linv_failed && lane == 0) *a.info = 1;
         } else {
             // ---- I/O warps ----
@@ -616,7 +630,7 @@ __device__ void role_P(const Args3& a, double* smem) {
             IOPROF(0);
             {   // NaN-arm the other column buffer for panel k+1 (its last reader finished before the barrier)
                 double* Ln = Lcol + ((k + 1) & 1) * T36;
-                if (!(a.debug & 32)) for (int e = it; e < T36; e += 96) Ln[e] = qnan;
+                if (!(a.debug & 32) && !tail) for (int e = it; e < T36; e += 96) Ln[e] = qnan;
                 if (it < NB) dinvs[((k + 1) & 1) * NB + it] = qnan;
             }
             bar_sync(1, 224);                                              // L(k,k-1) is complete
@@ -634,7 +648,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                     IOPROF(2);
                 }
             }
-            if (k + 1 < NP) {
+            if (k + 1 < NP && !tail) {
                 if (k >= 1 && NU > 0) {
                     if (lane == 0) spin_until(hot_done + (k - 1), hot_expected);
                     __syncwarp();
@@ -647,7 +661,7 @@ __device__ void role_P(const Args3& a, double* smem) {
         }
     }
     __syncthreads();
-    if (tid == 0) red_release(diag_done + (NP - 1), 1);
+    if (tid == 0 && KE >= NP) red_release(diag_done + (NP - 1), 1);      // partial mode: the reduced step released KE-1
     if (prof && tid == 0) {
         a.prof[9] = clock64();
         for (int q = 0; q < 5; ++q) a.prof[q] = tacc[q];
@@ -660,6 +674,75 @@ __device__ void role_P(const Args3& a, double* smem) {
     if (prof && tid == 0) for (int q = 4; q < 7; ++q) a.prof[44 + q] = tsacc[q];
 #undef PROF
 #undef IOPROF
+}
+
+// Push-style back substitution L^T x = y on one CTA; s (shared, NP*32) holds y on entry and x on return.
+// Panels k >= ke are NOT solved (their x is given in s: the middle block of the two-sided solve) but still pushed.
+__device__ void backsub(const Args3& a, double* s, int ke) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = a.NP, WB = a.WB;
+    // ---- back substitution L^T x = y, push style.  Register-prefetched operands: job A = tile d = warp+1 (all
+    // warps), job B = L(k,k)^-1 on warp 0 / tile d = warp+8 on warps 1..7; wider bands go on demand. ----
+    double pa[NB], pb[NB];
+    const int dA = warp + 1, dB = warp + 8;
+    auto prefetch = [&](int k) {
+        const int nd = min(WB, k);
+        if (dA <= nd) {
+            const double* G = lb_tile(a, k, dA);
+#pragma unroll
+            for (int r = 0; r < NB; ++r) pa[r] = __ldcg(G + r * NB + lane);
+        }
+        if (warp == 0 || dB <= nd) {
+            const double* G = (warp == 0) ? a.LI + (size_t)k * T32 : lb_tile(a, k, dB);
+#pragma unroll
+            for (int r = 0; r < NB; ++r) pb[r] = __ldcg(G + r * NB + lane);
+        }
+    };
+    __syncthreads();
+    prefetch(NP - 1);
+    for (int k = NP - 1; k >= 0; --k) {
+        const double* sk = s + NB * k;
+        if (warp == 0 && k < ke) {             // x_k = L(k,k)^-T s_k
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 4) {
+                x0 = fma(pb[r], sk[r], x0);
+                x1 = fma(pb[r + 1], sk[r + 1], x1);
+                x2 = fma(pb[r + 2], sk[r + 2], x2);
+                x3 = fma(pb[r + 3], sk[r + 3], x3);
+            }
+            __syncwarp();
+            s[NB * k + lane] = (x0 + x1) + (x2 + x3);
+        }
+        __syncthreads();
+        const int nd = min(WB, k);
+        if (dA <= nd && k - dA < ke) {         // s_{k-d} -= L(k,k-d)^T x_k   (targets that are given, not solved, stay)
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 2) {
+                c0 = fma(pa[r], sk[r], c0);
+                c1 = fma(pa[r + 1], sk[r + 1], c1);
+            }
+            s[NB * (k - dA) + lane] -= c0 + c1;
+        }
+        if (warp != 0 && dB <= nd && k - dB < ke) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r += 2) {
+                c0 = fma(pb[r], sk[r], c0);
+                c1 = fma(pb[r + 1], sk[r + 1], c1);
+            }
+            s[NB * (k - dB) + lane] -= c0 + c1;
+        }
+        for (int d = 16 + warp; d <= nd && k - d < ke; d += 8) {     // wide bands: remaining tiles on demand
+            const double* G = lb_tile(a, k, d);
+            double c0 = 0.0;
+            for (int r = 0; r < NB; ++r) c0 = fma(__ldcg(G + r * NB + lane), sk[r], c0);
+            s[NB * (k - d) + lane] -= c0;
+        }
+        if (k >= 1) prefetch(k - 1);
+        __syncthreads();
+    }
 }
 
 // =====================================================================================================
@@ -677,7 +760,7 @@ __device__ void role_R(const Args3& a, double* smem) {
 
     if (a.debug & 8) return;
     for (int i = tid; i < NP * NB; i += THREADS) s[i] = (i < n) ? __ldcg(a.g + i) : 0.0;
-    for (int p = 0; p < NP; ++p) {
+    for (int p = 0; p < NP && p < a.ke; ++p) {
         cta_wait(diag_done + p, 1);
         load_g_tile(a.LI + (size_t)p * T32, LinvS, S33, tid, THREADS);
         __syncthreads();
@@ -723,68 +806,12 @@ __device__ void role_R(const Args3& a, double* smem) {
         for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
         return;
     }
-    // ---- back substitution L^T x = y, push style.  Register-prefetched operands: job A = tile d = warp+1 (all
-    // warps), job B = L(k,k)^-1 on warp 0 / tile d = warp+8 on warps 1..7; wider bands go on demand. ----
-    double pa[NB], pb[NB];
-    const int dA = warp + 1, dB = warp + 8;
-    auto prefetch = [&](int k) {
-        const int nd = min(WB, k);
-        if (dA <= nd) {
-            const double* G = lb_tile(a, k, dA);
-#pragma unroll
-            for (int r = 0; r < NB; ++r) pa[r] = __ldcg(G + r * NB + lane);
-        }
-        if (warp == 0 || dB <= nd) {
-            const double* G = (warp == 0) ? a.LI + (size_t)k * T32 : lb_tile(a, k, dB);
-#pragma unroll
-            for (int r = 0; r < NB; ++r) pb[r] = __ldcg(G + r * NB + lane);
-        }
-    };
-    __syncthreads();
-    prefetch(NP - 1);
-    for (int k = NP - 1; k >= 0; --k) {
-        const double* sk = s + NB * k;
-        if (warp == 0) {                       // x_k = L(k,k)^-T s_k
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-#pragma unroll
-            for (int r = 0; r < NB; r += 4) {
-                x0 = fma(pb[r], sk[r], x0);
-                x1 = fma(pb[r + 1], sk[r + 1], x1);
-                x2 = fma(pb[r + 2], sk[r + 2], x2);
-                x3 = fma(pb[r + 3], sk[r + 3], x3);
-            }
-            __syncwarp();
-            s[NB * k + lane] = (x0 + x1) + (x2 + x3);
-        }
+    if (a.ke < NP) {                       // partial factorisation: y (eliminated panels) and the updated right-hand side below
         __syncthreads();
-        const int nd = min(WB, k);
-        if (dA <= nd) {                        // s_{k-d} -= L(k,k-d)^T x_k
-            double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-            for (int r = 0; r < NB; r += 2) {
-                c0 = fma(pa[r], sk[r], c0);
-                c1 = fma(pa[r + 1], sk[r + 1], c1);
-            }
-            s[NB * (k - dA) + lane] -= c0 + c1;
-        }
-        if (warp != 0 && dB <= nd) {
-            double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-            for (int r = 0; r < NB; r += 2) {
-                c0 = fma(pb[r], sk[r], c0);
-                c1 = fma(pb[r + 1], sk[r + 1], c1);
-            }
-            s[NB * (k - dB) + lane] -= c0 + c1;
-        }
-        for (int d = 16 + warp; d <= nd; d += 8) {     // wide bands: remaining tiles on demand
-            const double* G = lb_tile(a, k, d);
-            double c0 = 0.0;
-            for (int r = 0; r < NB; ++r) c0 = fma(__ldcg(G + r * NB + lane), sk[r], c0);
-            s[NB * (k - d) + lane] -= c0;
-        }
-        if (k >= 1) prefetch(k - 1);
-        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
+        return;
     }
+    backsub(a, s, NP);
     for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
     if ((a.debug & 4) && tid == 0) a.prof[11] = clock64();
 }
@@ -800,7 +827,7 @@ __device__ void role_U(const Args3& a, double* smem) {
     int* diag_done = a.flags;
     int* rows_done = a.flags + NP;
     int* upd_done = a.flags + 2 * NP;
-    const int NU = (int)gridDim.x - 2, ui = (int)blockIdx.x - 2;
+    const int NU = a.ncta - 2, ui = (int)blockIdx.x - a.rank0 - 2;
     double* LinvS = smem;            // T36
     double* As = LinvS + T36;
     double* Bs = As + T36;
@@ -811,7 +838,7 @@ __device__ void role_U(const Args3& a, double* smem) {
     long long ut[6] = {0, 0, 0, 0, 0, 0}, u0 = clock64(), u1;
 #define UPROF(slot) do { if (uprof) { if (*(volatile double*)LinvS != 1.2345e300) u1 = clock64(); ut[slot] += u1 - u0; u0 = u1; } } while (0)
 
-    for (int p = 0; p < NP; ++p) {
+    for (int p = 0; p < NP && p < a.ke; ++p) {
         const int last = min(NP - 1, p + WB);
         const int nrows = last - p;
         const int ntiles = nrows * (nrows + 1) / 2;
@@ -918,7 +945,7 @@ __device__ void role_U2(const Args3& a, double* smem) {
     int* diag_done = a.flags;
     int* rows_done = a.flags + NP;
     int* upd_done = a.flags + 2 * NP;
-    const int NU = (int)gridDim.x - 2, ui = (int)blockIdx.x - 2;
+    const int NU = a.ncta - 2, ui = (int)blockIdx.x - a.rank0 - 2;
     double* LinvS = smem;            // T36
     double* As = LinvS + T36;
     double* LIs = As + T36;
@@ -926,7 +953,7 @@ __device__ void role_U2(const Args3& a, double* smem) {
     __shared__ int lst1[MAX_WB3 + 4], lst2[448], n1, n2;
     const int fr = lane >> 2, fc = lane & 3;
 
-    for (int p = 0; p < NP; ++p) {
+    for (int p = 0; p < NP && p < a.ke; ++p) {
         const int last = min(NP - 1, p + WB);
         const int nrows = last - p;
         if (a.debug & 1) {          // timing experiments: no trailing work, but P still waits for the hot flag
@@ -1022,6 +1049,90 @@ __device__ void role_U2(const Args3& a, double* smem) {
     (void)upd_done;
 }
 
+__device__ __forceinline__ void run_roles(const Args3& a, double* smem) {
+    const int r = (int)blockIdx.x - a.rank0;
+    if (r == 0) role_P(a, smem);
+    else if (r == 1) role_R(a, smem);
+    else if (a.two_phase) role_U2(a, smem);
+    else role_U(a, smem);
+}
+
+// ---- two-sided solve (sb_band_solve4) ---------------------------------------------------------------------
+// The pivot chain is the solve's critical path, so it is cut in two: the top m panels are eliminated top-down and --
+// on a reversed copy of the matrix -- the bottom kB panels bottom-up, AT THE SAME TIME, by two instances of the
+// pipeline (each a partial factorisation that leaves its Schur complement in the trailing tiles); the middle block
+// (>= bw rows, so the two ends never couple directly) receives both complements and is solved last; the two back
+// substitutions run outwards from it, again concurrently.
+struct TwoSided {
+    int n, bw, ldab, m32, Lm, nB;       // rows: total, half bandwidth, band row length, 32*m, middle, bottom instance (= n - 32 m)
+};
+
+// AB2 = the rows >= 32 m of the matrix with both index directions reversed (lower band storage again), its middle block
+// zeroed (the bottom instance accumulates only its Schur complement there); g2 likewise.
+__global__ void band_reverse_kernel(const double* __restrict__ AB, const double* __restrict__ g, double* __restrict__ AB2,
+                                    double* __restrict__ g2, TwoSided t) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = t.nB * t.ldab;
+    if (e < t.nB) {
+        const int gi = t.n - 1 - e;                                   // original row
+        g2[e] = (gi >= t.m32 + t.Lm) ? g[gi] : 0.0;
+    }
+    if (e >= total) return;
+    const int ip = e / t.ldab, dc = e - ip * t.ldab;                  // reversed row i', band column (j' - i' + bw)
+    const int jp = ip - t.bw + dc;
+    double v = 0.0;
+    if (jp >= 0 && dc <= t.bw) {
+        const int gi = t.n - 1 - ip, gj = t.n - 1 - jp;               // original (row, col) with gi <= gj: stored at row gj
+        const bool mid_i = gi < t.m32 + t.Lm, mid_j = gj < t.m32 + t.Lm;
+        if (!(mid_i && mid_j)) v = AB[(size_t)gj * t.ldab + (gi - gj + t.bw)];
+    }
+    AB2[e] = v;
+}
+
+// middle system = the top instance's trailing block (original values + its complement) + the bottom instance's complement
+__global__ void band_combine_kernel(const double* __restrict__ AB, const double* __restrict__ g, const double* __restrict__ AB2,
+                                    const double* __restrict__ g2, double* __restrict__ ABm, double* __restrict__ gm, TwoSided t) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < t.Lm) gm[e] = g[t.m32 + e] + g2[t.n - 1 - (t.m32 + e)];
+    if (e >= t.Lm * t.ldab) return;
+    const int i = e / t.ldab, dc = e - i * t.ldab;
+    const int j = i - t.bw + dc;                                      // middle-local column
+    double v = 0.0;
+    if (j >= 0 && dc <= t.bw) {
+        const int gi = t.m32 + i, gj = t.m32 + j;
+        v = AB[(size_t)gi * t.ldab + dc] + AB2[(size_t)(t.n - 1 - gj) * t.ldab + dc];
+    }
+    ABm[e] = v;
+}
+
+// CTA 0: top instance, CTA 1: bottom instance (reversed).  s = y on the eliminated rows, x of the middle block on the others.
+__global__ void __launch_bounds__(THREADS, 1) band_backsub2_kernel(Args3 a0, Args3 a1, const double* __restrict__ xm,
+                                                                   double* __restrict__ gout, TwoSided t) {
+    extern __shared__ double smem[];
+    const bool top = blockIdx.x == 0;
+    const Args3& a = top ? a0 : a1;
+    double* s = smem;
+    const int ke32 = NB * a.ke;
+    for (int i = threadIdx.x; i < a.NP * NB; i += THREADS) {
+        double v = 0.0;
+        if (i < ke32) v = __ldcg(a.g + i);
+        else if (i < a.n) v = top ? xm[i - ke32] : xm[t.Lm - 1 - (i - ke32)];
+        s[i] = v;
+    }
+    backsub(a, s, a.ke);
+    __syncthreads();
+    if (top) {
+        for (int i = threadIdx.x; i < a.n; i += THREADS) gout[i] = s[i];             // rows [0, 32 m + Lm)
+    } else {
+        for (int i = threadIdx.x; i < ke32; i += THREADS) gout[t.n - 1 - i] = s[i];   // rows [32 m + Lm, n), un-reversed
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) band_chol3_dual_kernel(Args3 a0, Args3 a1) {
+    extern __shared__ double smem[];
+    run_roles((int)blockIdx.x < a1.rank0 ? a0 : a1, smem);
+}
+
 __global__ void __launch_bounds__(THREADS, 1) band_chol3_kernel(Args3 a) {
     extern __shared__ double smem[];
     if (blockIdx.x == 0) role_P(a, smem);
@@ -1093,6 +1204,7 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
     a.LI = a.LB + tiles * T32;
     a.flags = (int*)(a.LI + (long long)a.NP * T32);
     a.two_phase = (a.WB * (a.WB + 1) / 2 - 1 > n_ctas - 2 || (g_debug3 & 64)) ? 1 : 0;
+    a.ke = a.NP; a.rank0 = 0; a.ncta = n_ctas;
     a.prof = (long long*)((char*)workspace + ws_bytes3(n, bw) - 1024);
     a.debug = g_debug3;
     if (cudaMemsetAsync(a.flags, 0, 4 * (size_t)a.NP * sizeof(int), (cudaStream_t)stream) != cudaSuccess)
@@ -1101,6 +1213,121 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
     if (cudaLaunchCooperativeKernel((const void*)band_chol3_kernel, dim3(n_ctas), dim3(THREADS), kargs, smem,
                                     (cudaStream_t)stream) != cudaSuccess)
         return SB_ERR_CUDA;
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+
+/* ---- two-sided solve ------------------------------------------------------------------------------------ */
+static void fill_args3(Args3& a, double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                       void* ws, int ke, int rank0, int ncta) {
+    a.AB = AB; a.ldab = ldab; a.n = n; a.bw = bw; a.g = g; a.u = u; a.dinv = dinv; a.info = info;
+    a.NP = (n + NB - 1) / NB;
+    a.WB = (bw + NB - 1) / NB;
+    if (a.WB > a.NP - 1) a.WB = a.NP - 1 > 0 ? a.NP - 1 : 0;
+    const long long tiles = (long long)a.NP * (a.WB > 0 ? a.WB : 1);
+    a.LB = (double*)ws;
+    a.LI = a.LB + tiles * T32;
+    a.flags = (int*)(a.LI + (long long)a.NP * T32);
+    a.two_phase = (a.WB * (a.WB + 1) / 2 - 1 > ncta - 2 || (g_debug3 & 64)) ? 1 : 0;
+    a.ke = ke < 0 ? a.NP : ke; a.rank0 = rank0; a.ncta = ncta;
+    a.prof = (long long*)((char*)ws + ws_bytes3(n, bw) - 1024);
+    a.debug = g_debug3 & ~4;
+}
+
+/* split: m panels eliminated from the top, m from the bottom, the middle Lm = n - 64 m >= bw rows; 0 = do not split */
+static int two_sided_m(int n, int bw) {
+    const int need = (bw > 64 ? bw : 64);
+    int m = (n - need) / 64;
+    while (m > 0 && n - 64 * m < need) --m;
+    return m >= 4 ? m : 0;
+}
+
+static long long align256(long long x) { return (x + 255) & ~255LL; }
+
+long long sb_band4_workspace_bytes(int n, int bw, int ldab) {
+    const int m = two_sided_m(n, bw);
+    if (m == 0) return ws_bytes3(n, bw);
+    const int Lm = n - 64 * m, nA = 32 * m + Lm;
+    return 2 * align256(ws_bytes3(nA, bw)) + align256(ws_bytes3(Lm, bw < Lm - 1 ? bw : Lm - 1)) +
+           align256((long long)nA * ldab * 8) + align256((long long)nA * 8) + align256((long long)Lm * ldab * 8) +
+           align256((long long)Lm * 8) + 2 * align256((long long)n * 8) + 1024;
+}
+
+int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                   void* workspace, long long ws_bytes, int n_ctas, void* stream) {
+    if (!AB || !g || !dinv || !info || !workspace || n <= 0 || bw < 0 || ldab < bw + 1) return SB_ERR_ARG;
+    const int m = two_sided_m(n, bw);
+    if (m == 0 || n_ctas < 8)
+        return sb_band_solve3(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream);
+    if (ws_bytes < sb_band4_workspace_bytes(n, bw, ldab)) return SB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        max_ctas = sms;
+    }
+    if (n_ctas > max_ctas) n_ctas = max_ctas;
+    TwoSided t;
+    t.n = n; t.bw = bw; t.ldab = ldab; t.m32 = 32 * m; t.Lm = n - 64 * m; t.nB = n - 32 * m;
+    const int nA = t.m32 + t.Lm, bwm = bw < t.Lm - 1 ? bw : t.Lm - 1;
+    if (!sb_band3_fits(nA, bw) || !sb_band3_fits(t.Lm, bwm)) return SB_ERR_ARG;
+    char* w = (char*)workspace;
+    void* wsA = w; w += align256(ws_bytes3(nA, bw));
+    void* wsB = w; w += align256(ws_bytes3(nA, bw));
+    void* wsM = w; w += align256(ws_bytes3(t.Lm, bwm));
+    double* AB2 = (double*)w; w += align256((long long)nA * ldab * 8);
+    double* g2 = (double*)w; w += align256((long long)nA * 8);
+    double* ABm = (double*)w; w += align256((long long)t.Lm * ldab * 8);
+    double* gm = (double*)w; w += align256((long long)t.Lm * 8);
+    double* dinvB = (double*)w; w += align256((long long)n * 8);
+    double* dinvM = (double*)w;
+    const int cA = n_ctas / 2, cB = n_ctas - cA;
+    Args3 aA, aB, aM;
+    fill_args3(aA, AB, ldab, nA, bw, g, u, dinv, info, wsA, m, 0, cA);
+    fill_args3(aB, AB2, ldab, t.nB, bw, g2, u, dinvB, info, wsB, m, cA, cB);
+    const int cM = n_ctas < 96 ? n_ctas : 96;
+    fill_args3(aM, ABm, ldab, t.Lm, bwm, gm, u, dinvM, info, wsM, -1, 0, cM);
+    size_t smem = smem_bytes3(nA);
+    if (smem_bytes3(t.Lm) > smem) smem = smem_bytes3(t.Lm);
+    static size_t conf_dual = 0, conf_single = 0, conf_back = 0;
+    if (smem > conf_dual) {
+        if (cudaFuncSetAttribute(band_chol3_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SB_ERR_CUDA;
+        conf_dual = smem;
+    }
+    if (smem > conf_single) {
+        if (cudaFuncSetAttribute(band_chol3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SB_ERR_CUDA;
+        conf_single = smem;
+    }
+    const size_t smem_back = (size_t)aA.NP * NB * sizeof(double);
+    if (smem_back > conf_back && smem_back > 48 * 1024) {
+        if (cudaFuncSetAttribute(band_backsub2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_back) != cudaSuccess) return SB_ERR_CUDA;
+        conf_back = smem_back;
+    }
+    // 1. reversed copy of the bottom part
+    band_reverse_kernel<<<(t.nB * ldab + 255) / 256, 256, 0, st>>>(AB, g, AB2, g2, t);
+    SB_CHECK_LAUNCH();
+    // 2. both ends at once
+    if (cudaMemsetAsync(aA.flags, 0, 4 * (size_t)aA.NP * sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    if (cudaMemsetAsync(aB.flags, 0, 4 * (size_t)aB.NP * sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    {
+        void* kargs[] = {(void*)&aA, (void*)&aB};
+        if (cudaLaunchCooperativeKernel((const void*)band_chol3_dual_kernel, dim3(n_ctas), dim3(THREADS), kargs, smem, st) != cudaSuccess)
+            return SB_ERR_CUDA;
+    }
+    // 3. middle system
+    band_combine_kernel<<<(t.Lm * ldab + 255) / 256, 256, 0, st>>>(AB, g, AB2, g2, ABm, gm, t);
+    SB_CHECK_LAUNCH();
+    if (cudaMemsetAsync(aM.flags, 0, 4 * (size_t)aM.NP * sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    {
+        void* kargs[] = {(void*)&aM};
+        if (cudaLaunchCooperativeKernel((const void*)band_chol3_kernel, dim3(cM), dim3(THREADS), kargs, smem, st) != cudaSuccess)
+            return SB_ERR_CUDA;
+    }
+    // 4. both back substitutions outwards from the middle
+    band_backsub2_kernel<<<2, THREADS, smem_back, st>>>(aA, aB, gm, g, t);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

@@ -183,7 +183,13 @@ def band_solve(band, u_ptr=None, cluster_size=16, variant=None):
     if variant is None:
         variant = int(os.environ.get("SB_BAND_VARIANT", "3"))
     l = lib.load()
-    if variant == 3 and cluster_size >= 3 and l.sb_band3_fits(band.n, band.bw):
+    if variant == 4 and cluster_size >= 8 and l.sb_band3_fits(band.n, band.bw):
+        if getattr(band, "ws4", None) is None:
+            band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8,
+                                   device=band.AB.device)
+        call("sb_band_solve4", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
+             ptr(band.info), ptr(band.ws4), band.ws4.numel(), int(cluster_size), stream())
+    elif variant in (3, 4) and cluster_size >= 3 and l.sb_band3_fits(band.n, band.bw):
         if getattr(band, "ws3", None) is None:
             band.ws3 = torch.zeros(int(l.sb_band3_workspace_bytes(band.n, band.bw)), dtype=torch.uint8,
                                    device=band.AB.device)

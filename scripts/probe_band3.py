@@ -26,6 +26,7 @@ for bw in [int(x) for x in os.environ.get("BW", "300,370").split(",")]:
         return round(tot / n_it * 1e3, 1)
     for cs in (148,):
         res[f"v3 bw{bw}/c{cs}"] = timeit(cs, 3)
+        res[f"v4 two-sided bw{bw}/c{cs}"] = timeit(cs, 4)
     if lib.load().sb_band2_fits(n, bw):
         res[f"v2 bw{bw}/c64"] = timeit(64, 2)
 print(json.dumps(res, indent=1))

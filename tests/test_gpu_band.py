@@ -85,6 +85,27 @@ def test_band_solve_v3_tile_owner_update_path(n, bw, ctas):
     assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
 
 
+@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (1862, 300, 64), (1000, 150, 32), (4000, 500, 148), (2000, 64, 16), (700, 100, 8)])
+def test_band_solve_v4_two_sided(n, bw, ctas):
+    """Two-sided solve (both ends eliminated concurrently, middle block last) against a dense solve."""
+    from super_b200 import ops
+    A, b = _random_band_system(n, bw, seed=n + bw + 2)
+    band = ops.Band(n, bw, None, "cuda")
+    AB = torch.zeros((n, bw + 1), dtype=torch.float64)
+    for d in range(bw + 1):
+        off = bw - d
+        if off < n:
+            AB[off:, d] = A.diagonal(-off)
+    band.AB.copy_(AB.cuda())
+    band.g.copy_(b.cuda())
+    u = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+    ops.band_solve(band, u.data_ptr(), ctas, variant=4)
+    x = band.g.cpu()
+    x_ref = torch.linalg.solve(A + 0.5 * torch.eye(n, dtype=torch.float64), b)
+    assert int(band.info.item()) == 0
+    assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
+
+
 def test_band_solve_flags_indefinite_matrix():
     from super_b200 import ops
     n, bw = 64, 4
