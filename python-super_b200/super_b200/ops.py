@@ -177,11 +177,12 @@ def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=N
 
 def band_solve(band, u_ptr=None, cluster_size=16, variant=None):
     """(A + u I) x = g in place: band.g <- x (solver node order).  u_ptr: device address of u.
-    variant 3 (default): sb_band_solve3 (DMMA products with explicit block inverses, push-style back substitution);
+    variant 4 (default): sb_band_solve4 (two-sided: variant 3's factorisation from both ends at once, middle block last);
+    variant 3: sb_band_solve3 (DMMA products with explicit block inverses, push-style back substitution);
     variant 2: sb_band_solve2 (first pipelined kernel); variant 1: barrier-per-panel cluster kernel sb_band_solve."""
     import os
     if variant is None:
-        variant = int(os.environ.get("SB_BAND_VARIANT", "3"))
+        variant = int(os.environ.get("SB_BAND_VARIANT", "4"))
     l = lib.load()
     if variant == 4 and cluster_size >= 8 and l.sb_band3_fits(band.n, band.bw):
         if getattr(band, "ws4", None) is None:
