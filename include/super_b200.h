@@ -196,6 +196,7 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
  * reversed copy), the middle block (>= bw rows) solved last, two concurrent back substitutions outwards: the pivot chain --
  * the solve's critical path -- is n/2 + bw/2 long instead of n.  Falls back to v3 for systems too small to split. */
 long long sb_band4_workspace_bytes(int n, int bw, int ldab);
+int sb_band4_stage_ms(float* out5); /* timing experiments (sb_band3_debug flag 256): ms of the 5 stages of the last sb_band_solve4 */
 int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                    void* workspace, long long ws_bytes, int n_ctas, void* stream);
 int sb_band_max_bw(void);
@@ -206,6 +207,11 @@ int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* 
 /* loss < minimal_loss ? accept : reject with u /= v | u *= v: /root/reference/super/LM.py:107-117 */
 int sb_lm_decide(void* state, const double* partials, int n_partials, double* loss_arap_rot, double* beta,
                  double* best, int n, void* stream);
+/* the same with the ARAP / Rot losses of the stepped beta (loss.py:433-437,487-497) evaluated inside the launch instead of
+ * by a loss-only sb_reg_terms in front of it: one launch less per LM iteration */
+int sb_lm_decide_reg(void* state, const double* partials, int n_partials, const double* ed_points, const int* ed_knn,
+                     int J, double lam_arap, double lam_rot, int use_arap, int use_rot, double* beta, double* best,
+                     int n, void* stream);
 
 
 /* ---- autograd optimiser (GraphFit) as fused loss + analytic-gradient kernels ------------------------------

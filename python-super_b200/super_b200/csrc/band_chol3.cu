@@ -1065,6 +1065,7 @@ __device__ __forceinline__ void run_roles(const Args3& a, double* smem) {
 // substitutions run outwards from it, again concurrently.
 struct TwoSided {
     int n, bw, ldab, m32, Lm, nB;       // rows: total, half bandwidth, band row length, 32*m, middle, bottom instance (= n - 32 m)
+    int* flags; int nflags;             // the three instances' counters (one block), zeroed by band_reverse_kernel
 };
 
 // AB2 = the rows >= 32 m of the matrix with both index directions reversed (lower band storage again), its middle block
@@ -1073,6 +1074,7 @@ __global__ void band_reverse_kernel(const double* __restrict__ AB, const double*
                                     double* __restrict__ g2, TwoSided t) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = t.nB * t.ldab;
+    if (e < t.nflags) t.flags[e] = 0;
     if (e < t.nB) {
         const int gi = t.n - 1 - e;                                   // original row
         g2[e] = (gi >= t.m32 + t.Lm) ? g[gi] : 0.0;
@@ -1128,6 +1130,129 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub2_kernel(Args3 a0, Arg
     }
 }
 
+// ---- bulk-copy (TMA) back substitution of the two-sided solve ---------------------------------------------------
+// The register-prefetched push loop above is bound by how fast ONE CTA pulls L out of L2: a panel's 11 tiles are
+// 88 KB and only one panel's loads are ever in flight (profiles/r1_microbench.md: 15-107 B/cycle depending only on
+// the bytes in flight) -> 3.4 k cycles per panel, 61 us for the two concurrent halves at n = 1862.  Here row k's tiles
+// (contiguous in the workspace) and L(k,k)^-1 arrive by cp.async.bulk into a two-stage shared-memory ring, each stage
+// with its own mbarrier, issued two panels ahead by one thread: up to 176 KB in flight, nothing of the copy on an
+// issue slot, and only the tiles whose targets are eliminated rows are fetched at all.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    long long it = 0;
+    while (true) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) break;
+        if (++it > (1LL << 26)) __trap();
+    }
+}
+
+// out[lane] = sum_r T[r][lane] * v[r]   (T row-major 32x32 in shared memory, v in shared memory: broadcast reads)
+__device__ __forceinline__ double tile_tmatvec(const double* __restrict__ T, const double* __restrict__ v, int lane) {
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+    for (int r = 0; r < NB; r += 4) {
+        c0 = fma(T[r * NB + lane], v[r], c0);
+        c1 = fma(T[(r + 1) * NB + lane], v[r + 1], c1);
+        c2 = fma(T[(r + 2) * NB + lane], v[r + 2], c2);
+        c3 = fma(T[(r + 3) * NB + lane], v[r + 3], c3);
+    }
+    return (c0 + c1) + (c2 + c3);
+}
+
+constexpr int BS3_STAGES = 2;
+size_t smem_backsub3(int NP, int WB) {      // s | ring of BS3_STAGES x (WB + 1) tiles | mbarriers
+    return (((size_t)NP * NB * sizeof(double) + 127) & ~(size_t)127) + (size_t)BS3_STAGES * (WB + 1) * T32 * sizeof(double) + 64;
+}
+
+// CTA 0: top instance, CTA 1: bottom instance (reversed).  Same contract as band_backsub2_kernel.
+__global__ void __launch_bounds__(THREADS, 1) band_backsub3_kernel(Args3 a0, Args3 a1, const double* __restrict__ xm,
+                                                                   double* __restrict__ gout, TwoSided t) {
+    extern __shared__ __align__(128) double smem_bs3[];
+    double* smem = smem_bs3;
+    const bool top = blockIdx.x == 0;
+    const Args3& a = top ? a0 : a1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = a.NP, WB = a.WB, ke = a.ke, ke32 = NB * ke;
+    double* s = smem;
+    double* ring = smem + ((((size_t)NP * NB * sizeof(double) + 127) & ~(size_t)127) / sizeof(double));
+    const size_t stage_elems = (size_t)(WB + 1) * T32;
+    unsigned long long* bars = (unsigned long long*)(ring + BS3_STAGES * stage_elems);
+    if (tid == 0) {
+        for (int q = 0; q < BS3_STAGES; ++q) mbar_init(smem_u32(bars + q), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // source panels, descending: k in [0, kmax]; panel k needs L(k,k)^-1 if it is solved here (k < ke) and the tiles
+    // d in [dlo, dhi] whose targets k - d are eliminated rows
+    const int kmax = min(NP - 1, ke - 1 + WB);
+    auto issue = [&](int k) {                    // thread 0 only
+        const int stage = (kmax - k) % BS3_STAGES;
+        double* slot = ring + (size_t)stage * stage_elems;
+        const unsigned bar = smem_u32(bars + stage);
+        const int dlo = max(1, k - ke + 1), dhi = min(WB, k);
+        const int nt = max(0, dhi - dlo + 1) + (k < ke ? 1 : 0);
+        mbar_expect_tx(bar, (unsigned)(nt * T32 * sizeof(double)));
+        if (k < ke) bulk_g2s(smem_u32(slot), a.LI + (size_t)k * T32, T32 * sizeof(double), bar);
+        for (int d = dlo; d <= dhi; ++d)
+            bulk_g2s(smem_u32(slot + (size_t)d * T32), lb_tile(a, k, d), T32 * sizeof(double), bar);
+    };
+    __syncthreads();
+    if (tid == 0)
+        for (int q = 0; q < BS3_STAGES && kmax - q >= 0; ++q) issue(kmax - q);
+    for (int i = tid; i < NP * NB; i += THREADS) {
+        double v = 0.0;
+        if (i < ke32) v = __ldcg(a.g + i);
+        else if (i < a.n) v = top ? xm[i - ke32] : xm[t.Lm - 1 - (i - ke32)];
+        s[i] = v;
+    }
+    __syncthreads();
+    for (int k = kmax; k >= 0; --k) {
+        const int idx = kmax - k, stage = idx % BS3_STAGES;
+        const double* slot = ring + (size_t)stage * stage_elems;
+        mbar_wait(smem_u32(bars + stage), (unsigned)((idx / BS3_STAGES) & 1));
+        double* sk = s + NB * k;
+        if (k < ke) {
+            if (warp == 0) {                     // x_k = L(k,k)^-T s_k
+                const double x = tile_tmatvec(slot, sk, lane);
+                __syncwarp();
+                sk[lane] = x;
+            }
+            __syncthreads();
+        }
+        const int dlo = max(1, k - ke + 1), dhi = min(WB, k);
+        // s_{k-d} -= L(k,k-d)^T x_k; the nearest target (next on the chain) alone on warp 0
+        for (int i = warp == 0 ? 0 : warp; dlo + i <= dhi; i += (warp == 0 ? 1 << 20 : 7)) {
+            const int d = dlo + i;
+            s[NB * (k - d) + lane] -= tile_tmatvec(slot + (size_t)d * T32, sk, lane);
+        }
+        __syncthreads();
+        if (tid == 0 && k - BS3_STAGES >= 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(k - BS3_STAGES);
+        }
+    }
+    if (top) {
+        for (int i = tid; i < a.n; i += THREADS) gout[i] = s[i];                 // rows [0, 32 m + Lm)
+    } else {
+        for (int i = tid; i < ke32; i += THREADS) gout[t.n - 1 - i] = s[i];       // rows [32 m + Lm, n), un-reversed
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) band_chol3_dual_kernel(Args3 a0, Args3 a1) {
     extern __shared__ double smem[];
     run_roles((int)blockIdx.x < a1.rank0 ? a0 : a1, smem);
@@ -1157,6 +1282,12 @@ long long ws_bytes3(int n, int bw) {
 }
 
 int g_debug3 = 0;
+cudaEvent_t g_ev4[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage stamps of sb_band_solve4 (debug & 256)
+inline void stamp4(int i, cudaStream_t st) {
+    if (!(g_debug3 & 256)) return;
+    if (!g_ev4[i]) cudaEventCreate(&g_ev4[i]);
+    cudaEventRecord(g_ev4[i], st);
+}
 
 }  // namespace
 
@@ -1251,7 +1382,7 @@ long long sb_band4_workspace_bytes(int n, int bw, int ldab) {
     const int Lm = n - 64 * m, nA = 32 * m + Lm;
     return 2 * align256(ws_bytes3(nA, bw)) + align256(ws_bytes3(Lm, bw < Lm - 1 ? bw : Lm - 1)) +
            align256((long long)nA * ldab * 8) + align256((long long)nA * 8) + align256((long long)Lm * ldab * 8) +
-           align256((long long)Lm * 8) + 2 * align256((long long)n * 8) + 1024;
+           align256((long long)Lm * 8) + 2 * align256((long long)n * 8) + align256(12LL * ((n + NB - 1) / NB + 2) * 4) + 1024;
 }
 
 int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
@@ -1283,13 +1414,16 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
     double* ABm = (double*)w; w += align256((long long)t.Lm * ldab * 8);
     double* gm = (double*)w; w += align256((long long)t.Lm * 8);
     double* dinvB = (double*)w; w += align256((long long)n * 8);
-    double* dinvM = (double*)w;
+    double* dinvM = (double*)w; w += align256((long long)n * 8);
+    int* flags4 = (int*)w;
     const int cA = n_ctas / 2, cB = n_ctas - cA;
     Args3 aA, aB, aM;
     fill_args3(aA, AB, ldab, nA, bw, g, u, dinv, info, wsA, m, 0, cA);
     fill_args3(aB, AB2, ldab, t.nB, bw, g2, u, dinvB, info, wsB, m, cA, cB);
     const int cM = n_ctas < 96 ? n_ctas : 96;
     fill_args3(aM, ABm, ldab, t.Lm, bwm, gm, u, dinvM, info, wsM, -1, 0, cM);
+    aA.flags = flags4; aB.flags = aA.flags + 4 * aA.NP; aM.flags = aB.flags + 4 * aB.NP;
+    t.flags = flags4; t.nflags = 4 * (aA.NP + aB.NP + aM.NP);
     size_t smem = smem_bytes3(nA);
     if (smem_bytes3(t.Lm) > smem) smem = smem_bytes3(t.Lm);
     static size_t conf_dual = 0, conf_single = 0, conf_back = 0;
@@ -1307,28 +1441,51 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
         conf_back = smem_back;
     }
     // 1. reversed copy of the bottom part
+    stamp4(0, st);
     band_reverse_kernel<<<(t.nB * ldab + 255) / 256, 256, 0, st>>>(AB, g, AB2, g2, t);
     SB_CHECK_LAUNCH();
     // 2. both ends at once
-    if (cudaMemsetAsync(aA.flags, 0, 4 * (size_t)aA.NP * sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
-    if (cudaMemsetAsync(aB.flags, 0, 4 * (size_t)aB.NP * sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    stamp4(1, st);
     {
         void* kargs[] = {(void*)&aA, (void*)&aB};
         if (cudaLaunchCooperativeKernel((const void*)band_chol3_dual_kernel, dim3(n_ctas), dim3(THREADS), kargs, smem, st) != cudaSuccess)
             return SB_ERR_CUDA;
     }
     // 3. middle system
+    stamp4(2, st);
     band_combine_kernel<<<(t.Lm * ldab + 255) / 256, 256, 0, st>>>(AB, g, AB2, g2, ABm, gm, t);
     SB_CHECK_LAUNCH();
-    if (cudaMemsetAsync(aM.flags, 0, 4 * (size_t)aM.NP * sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    stamp4(3, st);
     {
         void* kargs[] = {(void*)&aM};
         if (cudaLaunchCooperativeKernel((const void*)band_chol3_kernel, dim3(cM), dim3(THREADS), kargs, smem, st) != cudaSuccess)
             return SB_ERR_CUDA;
     }
     // 4. both back substitutions outwards from the middle
-    band_backsub2_kernel<<<2, THREADS, smem_back, st>>>(aA, aB, gm, g, t);
+    stamp4(4, st);
+    const size_t smem_b3 = smem_backsub3(aA.NP, aA.WB);
+    if (smem_b3 <= 227 * 1024 && !(g_debug3 & 128)) {
+        static size_t conf_b3 = 0;
+        if (smem_b3 > conf_b3) {
+            if (cudaFuncSetAttribute(band_backsub3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b3) != cudaSuccess) return SB_ERR_CUDA;
+            conf_b3 = smem_b3;
+        }
+        band_backsub3_kernel<<<2, THREADS, smem_b3, st>>>(aA, aB, gm, g, t);
+    } else {
+        band_backsub2_kernel<<<2, THREADS, smem_back, st>>>(aA, aB, gm, g, t);
+    }
     SB_CHECK_LAUNCH();
+    stamp4(5, st);
+    return SB_OK;
+}
+
+/* timing experiments (sb_band3_debug flag 256): milliseconds of the five stages of the last sb_band_solve4 --
+   reverse | both ends | combine + flag memset | middle | back substitution.  Synchronises. */
+int sb_band4_stage_ms(float* out5) {
+    if (!out5 || !g_ev4[5]) return SB_ERR_ARG;
+    if (cudaEventSynchronize(g_ev4[5]) != cudaSuccess) return SB_ERR_CUDA;
+    for (int i = 0; i < 5; ++i)
+        if (cudaEventElapsedTime(out5 + i, g_ev4[i], g_ev4[i + 1]) != cudaSuccess) return SB_ERR_CUDA;
     return SB_OK;
 }
 

@@ -84,7 +84,9 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
                                ws.partials, n_dev=n_dev)
         else:
             ws.partials.zero_()
-        if use_arap or use_rot:
-            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, loss2=ws.loss2)
-        ops.lm_decide(ws.state, ws.partials, ws.loss2, ws.beta, ws.best)
+        if use_arap or use_rot:      # regularisers' losses inside the decide launch
+            ops.lm_decide_reg(ws.state, ws.partials, ed.points, ed.knn_indices, lam_a, lam_r, use_arap, use_rot,
+                              ws.beta, ws.best)
+        else:
+            ops.lm_decide(ws.state, ws.partials, ws.loss2, ws.beta, ws.best)
     return ws.beta, ws

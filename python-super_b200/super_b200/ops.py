@@ -254,3 +254,10 @@ def lm_step(state, info, beta, delta, node_pos=None):
 def lm_decide(state, partials, loss2, beta, best):
     call("sb_lm_decide", ptr(state.buf), ptr(partials), partials.numel(), ptr(loss2), ptr(beta), ptr(best),
          beta.numel(), stream())
+
+
+def lm_decide_reg(state, partials, ed_points, ed_knn, lam_arap, lam_rot, use_arap, use_rot, beta, best):
+    """lm_decide with the regularisers' losses evaluated inside the same launch."""
+    call("sb_lm_decide_reg", ptr(state.buf), ptr(partials), partials.numel(), ptr(ed_points), ptr(ed_knn),
+         ed_points.shape[0], float(lam_arap), float(lam_rot), int(use_arap), int(use_rot), ptr(beta), ptr(best),
+         beta.numel(), stream())

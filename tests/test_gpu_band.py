@@ -85,7 +85,7 @@ def test_band_solve_v3_tile_owner_update_path(n, bw, ctas):
     assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
 
 
-@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (1862, 300, 64), (1000, 150, 32), (4000, 500, 148), (2000, 64, 16), (700, 100, 8)])
+@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (1862, 320, 148), (1862, 300, 64), (1094, 33, 148), (3000, 352, 148), (1000, 150, 32), (4000, 500, 148), (2000, 64, 16), (700, 100, 8)])
 def test_band_solve_v4_two_sided(n, bw, ctas):
     """Two-sided solve (both ends eliminated concurrently, middle block last) against a dense solve."""
     from super_b200 import ops
