@@ -20,8 +20,12 @@
 // Synchronisation: release/acquire counters in global memory (diag_done | rows_done | upd_done per panel),
 // zeroed by a memset node in front of the launch.  The grid is launched cooperatively only for the
 // co-residency guarantee (spinning CTAs); there is no grid-wide barrier.  Every spin is bounded and traps.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "super_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -1253,6 +1257,261 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub3_kernel(Args3 a0, Arg
     }
 }
 
+// ---- cluster back substitution of the two-sided solve --------------------------------------------------------------
+// One CTA pulls L out of L2 at ~45 B/cycle here whatever the mechanism (register prefetch or bulk copies: 2.1 k cycles
+// per 88 KB panel, profiles/r1f_band4_stages.md), so the panel's tiles are spread over a 4-CTA cluster and only what is
+// on the chain stays on the leader:
+//   leader  warp 0: s_k = y_k - sum_d mail[k][d];  x_k = L(k,k)^-T s_k -> xbuf of all four CTAs (DSMEM stores);
+//                   mail[k-1][1] = L(k,k-1)^T x_k  (the next panel's last input)
+//           warp 1: mail[k-2][2] = L(k,k-2)^T x_k
+//   helper h = 1..3, warp w = 0..2: tile d = 3 + (h-1) + 3 w:  mail[k-d][d] = L(k,k-d)^T x_k, stored into the LEADER's
+//                   shared memory; a contribution with distance d has d-1 panels of slack before the leader reads it.
+// Every hand-over is by value: xbuf and mail are NaN-armed and a word is its own ready flag (no barrier, no fence on
+// the chain).  Each CTA's tiles arrive through its own bulk-copy ring (one producer lane, full/empty mbarriers).
+constexpr int BS4_C = 4, BS4_TILES = 3, BS4_MAXWB = 2 + 3 * (BS4_C - 1);
+struct Bs4Layout { size_t xbuf, ybuf, pg, mail, xs, ring, bars, total; int stages; };
+Bs4Layout bs4_layout(int NP, int WB, int ke) {
+    Bs4Layout L;
+    size_t o = 0;
+    L.xbuf = o; o += (size_t)NP * NB * 8;
+    L.ybuf = o; o += (size_t)ke * NB * 8;
+    L.pg = o; o += (size_t)ke * NB * 8;
+    L.mail = o; o += (size_t)ke * WB * NB * 8;
+    L.xs = o; o += 8 * NB * 8;
+    o = (o + 127) & ~(size_t)127;
+    L.ring = o;
+    const size_t stage = (size_t)BS4_TILES * T32 * 8, avail = 227 * 1024 - 256;
+    int stages = o + 2 * stage <= avail ? (int)((avail - o) / stage) : 0;
+    if (stages > 8) stages = 8;
+    L.stages = stages;
+    o += (size_t)stages * stage;
+    L.bars = o; o += 2 * 8 * 8;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// spin until the word is not NaN; after one timeout the caller stops waiting (a NaN that is a VALUE -- a failed
+// factorisation upstream -- must flow through, not hang or trap)
+__device__ __forceinline__ double poll_value(const double* p, bool& poisoned) {
+    double v = *(const volatile double*)p;
+    if (v == v || poisoned) return v;
+    for (long long it = 0; it < (1LL << 19); ++it) {
+        const long long t0 = clock64();                  // back off between polls: a tight LDS loop on one warp slows the
+        while (clock64() - t0 < 48) {}                   // shared-memory products of the others (measured)
+        v = *(const volatile double*)p;
+        if (v == v) return v;
+    }
+    poisoned = true;
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Args3 a1, const double* __restrict__ xm,
+                                                                   double* __restrict__ gout, TwoSided t, Bs4Layout L) {
+    extern __shared__ __align__(128) unsigned char smem_bs4[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const bool top = (int)blockIdx.x < BS4_C;
+    const Args3& a = top ? a0 : a1;
+    if (*(const volatile int*)a.info != 0) return;          // failed factorisation: the caller ignores the step (LM.py:99-103)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool prof = (a.debug & 1024) && top && rank == 0 && tid == 0;
+    if (prof) { a.prof[56] = clock64(); for (int d = 0; d < BS4_MAXWB; ++d) a.prof[70 + d] = 0; }
+    const int NP = a.NP, WB = a.WB, ke = a.ke, ke32 = NB * ke;
+    double* xbuf = (double*)(smem_bs4 + L.xbuf);
+    double* ybuf = (double*)(smem_bs4 + L.ybuf);
+    double* pg = (double*)(smem_bs4 + L.pg);                 // y_j - sum_{d>=2} mail[j][d], NaN-armed
+    double* mail = (double*)(smem_bs4 + L.mail);             // [target j < ke][d - 1][lane]
+    double* xs = (double*)(smem_bs4 + L.xs) + warp * NB;
+    double* ring = (double*)(smem_bs4 + L.ring);
+    unsigned long long* full = (unsigned long long*)(smem_bs4 + L.bars);
+    unsigned long long* empty = full + 8;
+    const int S = L.stages;
+    const int n_cons = 3;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const int kmax = min(NP - 1, ke - 1 + WB);
+    // this CTA's tile in ring slot q of source panel k: leader 0 = L(k,k)^-1, 1 = d 1, 2 = d 2; helper q -> d = 2 + rank + 3 q
+    auto slot_d = [&](int q) { return rank == 0 ? q : 2 + rank + 3 * q; };
+    auto wanted = [&](int k, int q) {
+        const int d = slot_d(q);
+        if (d == 0) return k < ke;
+        return d >= max(1, k - ke + 1) && d <= min(WB, k);
+    };
+    // the producer lane owns the barriers (starting its copies under the buffers' initialisation was tried: the lane
+    // then reaches the cluster barrier 4 k cycles late, which costs more than the first tiles' latency it hides)
+    auto produce = [&](int k) {
+        const int idx = kmax - k, stage = idx % S;
+        mbar_wait(smem_u32(empty + stage), (unsigned)(((idx / S) & 1) ^ 1));
+        double* slot = ring + (size_t)stage * BS4_TILES * T32;
+        const unsigned bar = smem_u32(full + stage);
+        int nt = 0;
+        for (int q = 0; q < BS4_TILES; ++q) nt += wanted(k, q) ? 1 : 0;
+        if (nt == 0) { mbar_arrive(bar); return; }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)(nt * T32 * sizeof(double)));
+        for (int q = 0; q < BS4_TILES; ++q)
+            if (wanted(k, q)) {
+                const int d = slot_d(q);
+                const double* src = d == 0 ? a.LI + (size_t)k * T32 : lb_tile(a, k, d);
+                bulk_g2s(smem_u32(slot + (size_t)q * T32), src, T32 * sizeof(double), bar);
+            }
+    };
+    const bool producer = warp == 7 && lane == 0;
+    if (producer) {
+        for (int q = 0; q < S; ++q) { mbar_init(smem_u32(full + q), 1); mbar_init(smem_u32(empty + q), n_cons); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < NP * NB; i += THREADS) {
+        double v = qnan;
+        if (i >= a.n) v = 0.0;
+        else if (i >= ke32) v = top ? xm[i - ke32] : xm[t.Lm - 1 - (i - ke32)];
+        xbuf[i] = v;
+    }
+    if (rank == 0) {
+        for (int i = tid; i < ke32; i += THREADS) { ybuf[i] = __ldcg(a.g + i); pg[i] = qnan; }
+        for (int i = tid; i < ke * WB * NB; i += THREADS) mail[i] = qnan;
+    }
+    cluster.sync();                                          // everybody armed before the first remote store
+    if (prof) a.prof[57] = clock64();
+    if (warp == 7) {
+        if (producer)
+            for (int k = kmax; k >= 0; --k) produce(k);
+    } else if (rank == 0 && warp < 2) {
+        // ---- the chain, on two warps that alternate panels: while one is on the chain the other loads its next
+        // operands into registers.  Target k: x_k = L(k,k)^-T (pg_k - L(k+1,k)^T x_{k+1}), pg_k from warp 3.
+        bool poisoned = false;
+        double tq[NB], ti[NB];
+        long long tacc[3] = {0, 0, 0}, c0 = 0, c1;
+#define BS4PROF(slot_) do { if (prof) { c1 = clock64(); tacc[slot_] += c1 - c0; c0 = c1; } } while (0)
+        for (int k = kmax; k >= 0; --k) {
+            const int idx = kmax - k, stage = idx % S;
+            mbar_wait(smem_u32(full + stage), (unsigned)((idx / S) & 1));
+            const double* slot = ring + (size_t)stage * BS4_TILES * T32;
+            const bool mine = k < ke && (k & 1) == warp;                       // I solve panel k
+            const bool feeds_mine = k >= 1 && k - 1 < ke && ((k - 1) & 1) == warp && wanted(k, 1);   // tile (k, d=1) feeds my next target
+            if (mine) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) ti[r] = slot[r * NB + lane];
+            }
+            if (mine) {
+                if (prof) c0 = clock64();
+                double c = 0.0;
+                if (k + 1 <= kmax && wanted(k + 1, 1)) {                      // tq holds L(k+1,k), loaded one iteration ago
+                    const double* xk1 = xbuf + NB * (k + 1);
+                    (void)poll_value(xk1 + lane, poisoned);
+                    __syncwarp();
+                    BS4PROF(0);
+                    double c0_ = 0.0, c1_ = 0.0, c2_ = 0.0, c3_ = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NB; r += 4) {
+                        c0_ = fma(tq[r], xk1[r], c0_);
+                        c1_ = fma(tq[r + 1], xk1[r + 1], c1_);
+                        c2_ = fma(tq[r + 2], xk1[r + 2], c2_);
+                        c3_ = fma(tq[r + 3], xk1[r + 3], c3_);
+                    }
+                    c = (c0_ + c1_) + (c2_ + c3_);
+                }
+                const double sv = poll_value(pg + NB * k + lane, poisoned) - c;
+                xs[lane] = sv;
+                __syncwarp();
+                if (prof && sv == 1.2345e300) c0 = 0;
+                BS4PROF(1);
+                double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+                for (int r = 0; r < NB; r += 4) {
+                    x0 = fma(ti[r], xs[r], x0);
+                    x1 = fma(ti[r + 1], xs[r + 1], x1);
+                    x2 = fma(ti[r + 2], xs[r + 2], x2);
+                    x3 = fma(ti[r + 3], xs[r + 3], x3);
+                }
+                const double x = (x0 + x1) + (x2 + x3);
+                double* xk = xbuf + NB * k;
+                *(volatile double*)(xk + lane) = x;
+#pragma unroll
+                for (int h = 1; h < BS4_C; ++h) *(volatile double*)(cluster.map_shared_rank(xk + lane, h)) = x;
+                __syncwarp();
+                if (prof && x == 1.2345e300) c0 = 0;
+                BS4PROF(2);
+            }
+            if (feeds_mine) {                       // after my own step: tq of the step above is dead now
+#pragma unroll
+                for (int r = 0; r < NB; ++r) tq[r] = slot[T32 + r * NB + lane];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+            if (prof && k == ke) a.prof[60] = clock64();
+        }
+        if (prof) { a.prof[58] = clock64(); for (int q5 = 0; q5 < 3; ++q5) a.prof[64 + q5] = tacc[q5]; }
+#undef BS4PROF
+    } else if (rank == 0 && warp == 3) {
+        // ---- everything of s_k that has slack: pg_k = y_k - sum_{d>=2} mail[k][d]
+        bool poisoned = false;
+        for (int k = ke - 1; k >= 0; --k) {
+            const int nd = min(WB, NP - 1 - k);
+            const double* mk = mail + (size_t)k * WB * NB + lane;
+            double mv[BS4_MAXWB];
+            long long spins = 0;
+            while (true) {
+                bool ok = true;
+#pragma unroll
+                for (int d = 1; d < BS4_MAXWB; ++d) {
+                    mv[d] = d < nd ? *(const volatile double*)(mk + d * NB) : 0.0;
+                    ok = ok && (mv[d] == mv[d]);
+                }
+                if (ok || poisoned) break;
+                if (++spins > (1LL << 18)) poisoned = true;
+            }
+            double sv = ybuf[NB * k + lane];
+#pragma unroll
+            for (int d = 1; d < BS4_MAXWB; ++d) sv -= mv[d];
+            *(volatile double*)(pg + NB * k + lane) = sv;
+        }
+    } else if (warp < n_cons) {
+        // ---- one tile per warp and panel: leader warp 2 -> d = 2 (local mail), helper warps 0..2 -> their d (leader's mail)
+        double* lead_mail = rank == 0 ? mail : cluster.map_shared_rank(mail, 0);
+        bool poisoned = false;
+        const int q = rank == 0 ? 2 : warp;
+        for (int k = kmax; k >= 0; --k) {
+            const int idx = kmax - k, stage = idx % S;
+            mbar_wait(smem_u32(full + stage), (unsigned)((idx / S) & 1));
+            const double* slot = ring + (size_t)stage * BS4_TILES * T32;
+            const double* xk = xbuf + NB * k;
+            if (wanted(k, q)) {
+                double tq[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) tq[r] = slot[(size_t)q * T32 + r * NB + lane];
+                (void)poll_value(xk + lane, poisoned);
+                __syncwarp();
+                const int d = slot_d(q);
+                double c0_ = 0.0, c1_ = 0.0, c2_ = 0.0, c3_ = 0.0;
+#pragma unroll
+                for (int r = 0; r < NB; r += 4) {
+                    c0_ = fma(tq[r], xk[r], c0_);
+                    c1_ = fma(tq[r + 1], xk[r + 1], c1_);
+                    c2_ = fma(tq[r + 2], xk[r + 2], c2_);
+                    c3_ = fma(tq[r + 3], xk[r + 3], c3_);
+                }
+                *(volatile double*)(lead_mail + ((size_t)(k - d) * WB + (d - 1)) * NB + lane) = (c0_ + c1_) + (c2_ + c3_);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+        }
+    }
+    __syncthreads();
+    if (prof) a.prof[59] = clock64();
+    if (rank == 0) {
+        if (top) {
+            for (int i = tid; i < a.n; i += THREADS) gout[i] = xbuf[i];                  // rows [0, 32 m + Lm)
+        } else {
+            for (int i = tid; i < ke32; i += THREADS) gout[t.n - 1 - i] = xbuf[i];        // rows [32 m + Lm, n), un-reversed
+        }
+    }
+    cluster.sync();                                          // nobody leaves while its shared memory may still be written
+    if (prof) a.prof[61] = clock64();
+}
+
 __global__ void __launch_bounds__(THREADS, 1) band_chol3_dual_kernel(Args3 a0, Args3 a1) {
     extern __shared__ double smem[];
     run_roles((int)blockIdx.x < a1.rank0 ? a0 : a1, smem);
@@ -1464,7 +1723,27 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
     // 4. both back substitutions outwards from the middle
     stamp4(4, st);
     const size_t smem_b3 = smem_backsub3(aA.NP, aA.WB);
-    if (smem_b3 <= 227 * 1024 && !(g_debug3 & 128)) {
+    const Bs4Layout L4 = bs4_layout(aA.NP, aA.WB, aA.ke);
+    if (aA.WB <= BS4_MAXWB && aA.WB >= 1 && L4.stages >= 2 && !(g_debug3 & (128 | 512))) {
+        static size_t conf_b4 = 0;
+        if (L4.total > conf_b4) {
+            if (cudaFuncSetAttribute(band_backsub4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L4.total) != cudaSuccess) return SB_ERR_CUDA;
+            conf_b4 = L4.total;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * BS4_C);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = L4.total;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = BS4_C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, band_backsub4_kernel, aA, aB, (const double*)gm, g, t, L4) != cudaSuccess) return SB_ERR_CUDA;
+    } else if (smem_b3 <= 227 * 1024 && !(g_debug3 & 128)) {
         static size_t conf_b3 = 0;
         if (smem_b3 > conf_b3) {
             if (cudaFuncSetAttribute(band_backsub3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b3) != cudaSuccess) return SB_ERR_CUDA;

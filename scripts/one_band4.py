@@ -22,7 +22,7 @@ if variant == 4 and os.environ.get("STAGES", "1") == "1":
     import ctypes, numpy as np
     from super_b200 import lib
     l = lib.load()
-    for flags, label in ((256, "bulk-copy back substitution"), (256 | 128, "register-prefetch back substitution")):
+    for flags, label in ((256, "cluster back substitution"), (256 | 512, "bulk-copy back substitution"), (256 | 128, "register-prefetch back substitution"), (256, "cluster back substitution")):
         l.sb_band3_debug(flags)
         acc = np.zeros(5)
         for _ in range(reps):
@@ -32,4 +32,21 @@ if variant == 4 and os.environ.get("STAGES", "1") == "1":
             l.sb_band4_stage_ms(out)
             acc += np.array(out[:]) * 1e3
         print(f"  stages us [reverse, both ends, combine+memset, middle, back substitution] ({label}): {np.round(acc / reps, 1).tolist()}")
+    l.sb_band3_debug(0)
+if variant == 4 and os.environ.get("PROF4", "0") == "1":
+    from super_b200 import lib
+    l = lib.load()
+    need = max(bw, 64); m = (n - need) // 64
+    while m > 0 and n - 64 * m < need: m -= 1
+    nA = 32 * m + (n - 64 * m)
+    off = int(l.sb_band3_prof_offset(nA, bw))
+    l.sb_band3_debug(1024)
+    for _ in range(3):
+        band.AB.copy_(ABd); band.g.copy_(rd); ops.band_solve(band, None, 148, variant=4)
+    torch.cuda.synchronize()
+    pr = band.ws4[off: off + 1024].view(torch.int64).cpu().numpy()
+    t0 = pr[56]
+    print("  cluster back substitution, leader cycles since entry: after init+cluster.sync", pr[57] - t0, "| given panels done", pr[60] - t0,
+          "| chain done", pr[58] - t0, "| cta sync", pr[59] - t0, "| exit", pr[61] - t0)
+    print("  leader warp 0 totals over its panels: wait for x_{k+1}", pr[64], "| L(k+1,k)^T x + wait pg", pr[65], "| inverse product + x stores", pr[66])
     l.sb_band3_debug(0)
