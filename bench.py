@@ -102,7 +102,7 @@ def solver_report(trk, solve_ms):
     n, bw = trk.band.n, trk.band.bw
     ms = float(np.mean(solve_ms))
     variant = os.environ.get("SB_BAND_VARIANT", "4")
-    kern = ("band_reverse + band_chol3_dual + band_combine + band_chol3 + band_backsub2 kernels (sb_band_solve4, two-sided)"
+    kern = ("band_reverse + band_chol3_dual + band_combine + band_chol3 + band_backsub4 kernels (sb_band_solve4_step: two-sided solve, LM step folded into the last kernel)"
             if variant == "4" else "band_chol3_kernel (sb_band_solve3)")
     return {"kernel": kern, "n": n, "half_bandwidth": bw, "ms_per_solve": ms,
             "solves_timed": len(solve_ms), "band_flops": float(n) * bw * bw, "dense_flops": float(n) ** 3 / 3.0,
@@ -162,7 +162,7 @@ def run_cuda(args, rank, world, local_rank):
     lib.LAUNCHES = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kev, sev = [], []     # (start, end) events around every data-term J^T J launch / every banded solve
-    lib.KERNEL_EVENTS = {"sb_data_term_jtj": kev, "sb_band_solve3": sev, "sb_band_solve4": sev}
+    lib.KERNEL_EVENTS = {"sb_data_term_jtj": kev, "sb_band_solve3": sev, "sb_band_solve4": sev, "sb_band_solve4_step": sev}
     t_wall = time.perf_counter()
     for k in range(K):
         i = 1 + Wm + k

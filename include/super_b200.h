@@ -199,6 +199,12 @@ long long sb_band4_workspace_bytes(int n, int bw, int ldab);
 int sb_band4_stage_ms(float* out5); /* timing experiments (sb_band3_debug flag 256): ms of the 5 stages of the last sb_band_solve4 */
 int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                    void* workspace, long long ws_bytes, int n_ctas, void* stream);
+/* the same solve with the LM step (sb_lm_step's contract, /root/reference/super/LM.py:99-105) folded into its last kernel:
+ * beta[7 pos_node[p] + c] += x[7 p + c] (pos_node: solver position -> node id, NULL = identity) unless *info != 0 or
+ * *lm_failed != 0; a failed factorisation sets *lm_failed.  g still receives x. */
+int sb_band_solve4_step(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                        void* workspace, long long ws_bytes, int n_ctas, int* lm_failed, double* beta,
+                        const int* pos_node, void* stream);
 int sb_band_max_bw(void);
 int sb_band_debug(int flags); /* timing experiments only: 1 skip trailing update, 2 skip back-substitution, 4 skip panel math */
 int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,

@@ -1269,6 +1269,9 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub3_kernel(Args3 a0, Arg
 // Every hand-over is by value: xbuf and mail are NaN-armed and a word is its own ready flag (no barrier, no fence on
 // the chain).  Each CTA's tiles arrive through its own bulk-copy ring (one producer lane, full/empty mbarriers).
 constexpr int BS4_C = 4, BS4_TILES = 3, BS4_MAXWB = 2 + 3 * (BS4_C - 1);
+// optional LM step folded into the solve's last kernel (lm_step_kernel's contract, lm.cu): beta[7 pos_node[p] + c] += x[7 p + c]
+// unless the factorisation failed (*info != 0) or an earlier iteration did (*failed != 0); a failure sets *failed.
+struct StepArgs { int* failed; double* beta; const int* pos_node; };
 struct Bs4Layout { size_t xbuf, ybuf, pg, mail, xs, ring, bars, total; int stages; };
 Bs4Layout bs4_layout(int NP, int WB, int ke) {
     Bs4Layout L;
@@ -1309,13 +1312,17 @@ __device__ __forceinline__ double poll_value(const double* p, bool& poisoned) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Args3 a1, const double* __restrict__ xm,
-                                                                   double* __restrict__ gout, TwoSided t, Bs4Layout L) {
+                                                                   double* __restrict__ gout, TwoSided t, Bs4Layout L,
+                                                                   StepArgs step) {
     extern __shared__ __align__(128) unsigned char smem_bs4[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const bool top = (int)blockIdx.x < BS4_C;
     const Args3& a = top ? a0 : a1;
-    if (*(const volatile int*)a.info != 0) return;          // failed factorisation: the caller ignores the step (LM.py:99-103)
+    if (*(const volatile int*)a.info != 0) {                // failed factorisation: the caller ignores the step (LM.py:99-103)
+        if (step.failed && blockIdx.x == 0 && threadIdx.x == 0) *step.failed = 1;
+        return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool prof = (a.debug & 1024) && top && rank == 0 && tid == 0;
     if (prof) { a.prof[56] = clock64(); for (int d = 0; d < BS4_MAXWB; ++d) a.prof[70 + d] = 0; }
@@ -1502,14 +1509,31 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Arg
     __syncthreads();
     if (prof) a.prof[59] = clock64();
     if (rank == 0) {
-        if (top) {
-            for (int i = tid; i < a.n; i += THREADS) gout[i] = xbuf[i];                  // rows [0, 32 m + Lm)
-        } else {
-            for (int i = tid; i < ke32; i += THREADS) gout[t.n - 1 - i] = xbuf[i];        // rows [32 m + Lm, n), un-reversed
+        const bool do_step = step.beta && !(step.failed && *(const volatile int*)step.failed != 0);
+        const int rows = top ? a.n : ke32;                   // top: rows [0, 32 m + Lm); bottom: rows [32 m + Lm, n), un-reversed
+        for (int i = tid; i < rows; i += THREADS) {
+            const int gi = top ? i : t.n - 1 - i;
+            const double x = xbuf[i];
+            gout[gi] = x;
+            if (do_step) {
+                const int p = gi / 7, c = gi - 7 * p;
+                step.beta[7 * (step.pos_node ? step.pos_node[p] : p) + c] += x;
+            }
         }
     }
     cluster.sync();                                          // nobody leaves while its shared memory may still be written
     if (prof) a.prof[61] = clock64();
+}
+
+// the step as its own launch, behind the solvers that do not fold it in
+__global__ void band_step_kernel(const int* __restrict__ info, const double* __restrict__ x, int n, StepArgs step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = (step.failed && *step.failed != 0) || *info != 0;
+    if (i < n && !bad) {
+        const int p = i / 7, c = i - 7 * p;
+        step.beta[7 * (step.pos_node ? step.pos_node[p] : p) + c] += x[i];
+    }
+    if (i == 0 && bad && step.failed) *step.failed = 1;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) band_chol3_dual_kernel(Args3 a0, Args3 a1) {
@@ -1644,12 +1668,21 @@ long long sb_band4_workspace_bytes(int n, int bw, int ldab) {
            align256((long long)Lm * 8) + 2 * align256((long long)n * 8) + align256(12LL * ((n + NB - 1) / NB + 2) * 4) + 1024;
 }
 
-int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
-                   void* workspace, long long ws_bytes, int n_ctas, void* stream) {
+static int launch_step(const int* info, const double* x, int n, const StepArgs& step, cudaStream_t st) {
+    if (!step.beta) return SB_OK;
+    band_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(info, x, n, step);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                       void* workspace, long long ws_bytes, int n_ctas, void* stream, StepArgs step) {
     if (!AB || !g || !dinv || !info || !workspace || n <= 0 || bw < 0 || ldab < bw + 1) return SB_ERR_ARG;
     const int m = two_sided_m(n, bw);
-    if (m == 0 || n_ctas < 8)
-        return sb_band_solve3(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream);
+    if (m == 0 || n_ctas < 8) {
+        const int rc = sb_band_solve3(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream);
+        return rc != SB_OK ? rc : launch_step(info, g, n, step, (cudaStream_t)stream);
+    }
     if (ws_bytes < sb_band4_workspace_bytes(n, bw, ldab)) return SB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     static int max_ctas = 0;
@@ -1742,7 +1775,8 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, band_backsub4_kernel, aA, aB, (const double*)gm, g, t, L4) != cudaSuccess) return SB_ERR_CUDA;
+        if (cudaLaunchKernelEx(&cfg, band_backsub4_kernel, aA, aB, (const double*)gm, g, t, L4, step) != cudaSuccess) return SB_ERR_CUDA;
+        step.beta = nullptr;     // folded in
     } else if (smem_b3 <= 227 * 1024 && !(g_debug3 & 128)) {
         static size_t conf_b3 = 0;
         if (smem_b3 > conf_b3) {
@@ -1754,8 +1788,21 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
         band_backsub2_kernel<<<2, THREADS, smem_back, st>>>(aA, aB, gm, g, t);
     }
     SB_CHECK_LAUNCH();
+    if (launch_step(info, g, n, step, st) != SB_OK) return SB_ERR_CUDA;
     stamp4(5, st);
     return SB_OK;
+}
+
+int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                   void* workspace, long long ws_bytes, int n_ctas, void* stream) {
+    return solve4_impl(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream, StepArgs{nullptr, nullptr, nullptr});
+}
+
+int sb_band_solve4_step(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
+                        void* workspace, long long ws_bytes, int n_ctas, int* lm_failed, double* beta,
+                        const int* pos_node, void* stream) {
+    if (!beta || !lm_failed) return SB_ERR_ARG;
+    return solve4_impl(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream, StepArgs{lm_failed, beta, pos_node});
 }
 
 /* timing experiments (sb_band3_debug flag 256): milliseconds of the five stages of the last sb_band_solve4 --

@@ -27,6 +27,9 @@ class LMWorkspace:
         self.loss2 = torch.zeros(2, dtype=F64, device=device)
         self.state = ops.LMState(device)
         self.partials = None
+        # the regularisers' normal-equation terms (6 CTAs, ~7 us) run on a side stream under the data term's pass
+        self.side = torch.cuda.Stream(device=device)
+        self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
 
 
 def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
@@ -60,18 +63,29 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
         else:
             ws.A.zero_()
             ws.g.zero_()
+        overlap = use_data and (use_arap or use_rot) and on_iter is None
+        if overlap:      # fork: both kernels only add into the zeroed A, g
+            main = torch.cuda.current_stream()
+            ws.fork.record(main)
+            ws.side.wait_event(ws.fork)
+            with torch.cuda.stream(ws.side):
+                ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g, band=band)
+                ws.join.record(ws.side)
         if use_data:
             ops.data_term_jtj(sf.points, sf.knn_indices, sf.knn_w, order, ed.points, ws.beta, vmap, nmap, cam,
                               lam_d, ws.A, ws.g, n_dev=n_dev, band=band)
-        if use_arap or use_rot:
+        if overlap:
+            main.wait_event(ws.join)
+        elif use_arap or use_rot:
             ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g, band=band)
         if on_iter is not None:
             on_iter(it, "normal_equations", ws)
         if band is not None:
             # own banded Cholesky on one thread-block cluster; damping u is read from the device state
-            ops.band_solve(band, ws.state.buf.data_ptr(), cluster_size)
             delta = band.g
-            ops.lm_step(ws.state, band.info, ws.beta, delta, band.node_pos)
+            if not ops.band_solve_step(band, ws.state, ws.beta, cluster_size):       # step folded into the solve
+                ops.band_solve(band, ws.state.buf.data_ptr(), cluster_size)
+                ops.lm_step(ws.state, band.info, ws.beta, delta, band.node_pos)
         else:
             ops.lm_damp(ws.state, ws.A)
             L, info = torch.linalg.cholesky_ex(ws.A, check_errors=False)      # reads the lower triangle

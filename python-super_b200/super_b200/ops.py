@@ -113,6 +113,8 @@ class Band:
         self.AB = self.store[: self.n * self.ldab].view(self.n, self.ldab)
         self.g = self.store[self.n * self.ldab:]
         self.node_pos = node_pos
+        # solver position -> node id (the step folded into the solve scatters x back to beta's node order)
+        self.pos_node = None if node_pos is None else torch.argsort(node_pos.long()).to(I32).contiguous()
         self.overflow = torch.zeros(1, dtype=I32, device=device)
         self.dinv = torch.zeros(self.n, dtype=F64, device=device)
         self.info = torch.zeros(1, dtype=I32, device=device)
@@ -208,6 +210,22 @@ def band_solve(band, u_ptr=None, cluster_size=16, variant=None):
              ptr(band.info), cs, stream())
 
 
+def band_solve_step(band, state, beta, cluster_size=148):
+    """band_solve (two-sided variant) + lm_step in one call: beta += x unless the factorisation failed; the step rides in
+    the solve's last kernel.  Returns False if this system/variant has no folded path (caller runs the two calls)."""
+    import os
+    l = lib.load()
+    if int(os.environ.get("SB_BAND_VARIANT", "4")) != 4 or cluster_size < 8 or not l.sb_band3_fits(band.n, band.bw):
+        return False
+    if getattr(band, "ws4", None) is None:
+        band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8,
+                               device=band.AB.device)
+    call("sb_band_solve4_step", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), state.buf.data_ptr(),
+         ptr(band.dinv), ptr(band.info), ptr(band.ws4), band.ws4.numel(), int(cluster_size),
+         state.buf.data_ptr() + state.failed_offset, ptr(beta), ptr(band.pos_node), stream())
+    return True
+
+
 class LMState:
     """Device-resident controller (u, minimal_loss, trace) -- decoded on demand, never during the loop."""
 
@@ -218,6 +236,7 @@ class LMState:
         off = (ctypes.c_int * 8)()
         l.sb_lm_state_offsets(off)
         self.off = list(off)
+        self.failed_offset = self.off[3]
 
     def read(self):
         """D2H copy + decode (synchronises): dict(u, minimal_loss, iter, failed, loss, loss_terms, accept, u_trace)."""

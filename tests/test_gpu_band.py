@@ -106,6 +106,45 @@ def test_band_solve_v4_two_sided(n, bw, ctas):
     assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
 
 
+@pytest.mark.parametrize("n,bw", [(1862, 320), (700, 100), (140, 20)])
+def test_band_solve4_step_folds_the_lm_step(n, bw):
+    """sb_band_solve4_step = sb_band_solve4 + sb_lm_step: beta (node order) += x (solver order); a failed factorisation
+    leaves beta alone and raises the LM state's failed flag (LM.py:99-103)."""
+    from super_b200 import ops
+    J = n // 7
+    n = 7 * J
+    A, b = _random_band_system(n, bw, seed=n + bw + 5)
+    g = torch.Generator().manual_seed(3)
+    node_pos = torch.randperm(J, generator=g).to(torch.int32).cuda()
+    AB = torch.zeros((n, bw + 1), dtype=torch.float64)
+    for d in range(bw + 1):
+        off = bw - d
+        if off < n:
+            AB[off:, d] = A.diagonal(-off)
+    state = ops.LMState("cuda")
+    beta0 = torch.randn((J, 7), generator=g, dtype=torch.float64)
+    for fail in (False, True):
+        band = ops.Band(n, bw, node_pos, "cuda")
+        band.AB.copy_(AB.cuda())
+        if fail:
+            band.AB[:, bw] = -1.0
+        band.g.copy_(b.cuda())
+        beta, best = beta0.clone().cuda(), beta0.clone().cuda()
+        ops.lm_begin(state, beta, best, u=0.5)
+        beta.copy_(beta0.cuda())
+        assert ops.band_solve_step(band, state, beta, 148)
+        st = state.read()
+        if fail:
+            assert int(band.info.item()) == 1 and st["failed"] == 1
+            assert torch.equal(beta.cpu(), beta0)
+        else:
+            x_ref = torch.linalg.solve(A + 0.5 * torch.eye(n, dtype=torch.float64), b)
+            want = beta0 + x_ref.view(J, 7)[node_pos.cpu().long()]
+            assert int(band.info.item()) == 0 and st["failed"] == 0
+            assert (band.g.cpu() - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
+            assert (beta.cpu() - want).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
+
+
 def test_band_solve_flags_indefinite_matrix():
     from super_b200 import ops
     n, bw = 64, 4
