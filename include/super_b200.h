@@ -137,6 +137,13 @@ int sb_data_term_loss(const double* points, const int* knn_idx, const double* kn
                       const float* nmap, int H, int W, const double* intr, double lambda, double* partials,
                       int n_partials, void* stream);
 
+/* loss-only pass + the accept/reject step of the iteration in ONE launch (sb_data_term_loss followed by sb_lm_decide_reg):
+ * the last block to deliver its partial sums them in their fixed order and decides.  beta_in == beta (the trial beta). */
+int sb_data_term_loss_decide(const double* points, const int* knn_idx, const double* knn_w, int n_cap,
+                             const int* n_dev, const double* ed_points, const double* beta_in, int J, const float* vmap,
+                             const float* nmap, int H, int W, const double* intr, double lambda, double* partials,
+                             int n_partials, void* state, const int* ed_knn, double lam_arap, double lam_rot,
+                             int use_arap, int use_rot, double* beta, double* best, void* stream);
 /* Per-surfel rows of the same computation (parity tests, drop-in DataLoss face): matched (n,) u8,
  * corners (n,4) i32 [floor v, ceil v, floor u, ceil u], r (n,) f64, jrow (n,28) f64; any of the last
  * three may be NULL. */

@@ -14,6 +14,7 @@
 // one f64 atomic per entry only when the node tuple changes.  No 3 400-op ATen chain, no COO
 // Jacobian, no SpGEMM.
 #include "common.cuh"
+#include "lm_state.cuh"
 #include "super_b200.h"
 
 namespace {
@@ -314,6 +315,33 @@ __global__ void __launch_bounds__(LOSS_BLOCK) data_loss_kernel(DataArgs a, doubl
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// The same pass with the LM accept/reject step behind it IN the launch: every block delivers its partial and takes a
+// ticket; the block that draws the last one sums all partials in their fixed order, evaluates the regularisers' losses
+// and runs lm_decide_body (lm_state.cuh) -- what sb_lm_decide_reg does as a launch of its own.
+struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; };
+__global__ void __launch_bounds__(LOSS_BLOCK) data_loss_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d) {
+    __shared__ double red[LOSS_BLOCK / 32];
+    __shared__ bool s_last;
+    const int n = n_active(a.n_cap, a.n_dev);
+    double s = 0.0;
+    for (int i = blockIdx.x * LOSS_BLOCK + threadIdx.x; i < n; i += gridDim.x * LOSS_BLOCK) {
+        Eval ev;
+        if (eval_surfel<false>(a, i, ev, nullptr, 1)) s += ev.r * ev.r;
+    }
+    s = block_sum<LOSS_BLOCK>(s, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&d.st->ticket, 1u);
+        s_last = ticket == gridDim.x - 1;
+        if (s_last) d.st->ticket = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    lm_decide_body<LOSS_BLOCK>(d.st, partials, (int)gridDim.x, nullptr, d.beta, d.best, d.n, d.rg);
+}
+
 // Per-surfel rows for parity tests and for the drop-in DataLoss.forward face.
 __global__ void data_rows_kernel(DataArgs a, unsigned char* __restrict__ matched, int* __restrict__ corners,
                                  double* __restrict__ r, double* __restrict__ jrow_out) {
@@ -440,6 +468,24 @@ int sb_data_term_loss(const double* points, const int* knn_idx, const double* kn
     DataArgs a = make_args(points, knn_idx, knn_w, nullptr, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
                            intr, lambda);
     data_loss_kernel<<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_data_term_loss_decide(const double* points, const int* knn_idx, const double* knn_w, int n_cap,
+                             const int* n_dev, const double* ed_points, const double* beta_in, int J, const float* vmap,
+                             const float* nmap, int H, int W, const double* intr, double lambda, double* partials,
+                             int n_partials, void* state, const int* ed_knn, double lam_arap, double lam_rot,
+                             int use_arap, int use_rot, double* beta, double* best, void* stream) {
+    if (!points || !knn_idx || !knn_w || !ed_points || !beta_in || !vmap || !nmap || !partials) return SB_ERR_ARG;
+    if (!state || !ed_knn || !beta || !best || beta_in != beta) return SB_ERR_ARG;
+    if (n_partials != sb_data_loss_blocks(n_cap)) return SB_ERR_WORKSPACE;
+    DataArgs a = make_args(points, knn_idx, knn_w, nullptr, n_cap, n_dev, ed_points, beta_in, J, vmap, nmap, H, W,
+                           intr, lambda);
+    DecideArgs d;
+    d.st = (LMState*)state; d.beta = beta; d.best = best; d.n = 7 * J;
+    d.rg = RegLossArgs{ed_points, ed_knn, J, lam_arap, lam_rot, use_arap, use_rot};
+    data_loss_decide_kernel<<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials, d);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

@@ -4,22 +4,10 @@
 // /root/reference/super/LM.py:81-122 without any host synchronisation: u, minimal_loss, the
 // failure flag and the per-iteration trace live in a small device struct.
 #include "common.cuh"
+#include "lm_state.cuh"
 #include "super_b200.h"
 
 namespace {
-
-// Device-resident controller state (mirrors LM_Solver.LM's locals u, minimal_loss, best_beta).
-struct LMState {
-    double u;             // additive damping (reset to 10 every frame)
-    double v;             // 7.5
-    double minimal_loss;  // 1e10 at frame start
-    int iter;             // iterations completed
-    int failed;           // Cholesky failed -> the reference breaks out of the loop, beta unchanged
-    double loss[64];      // trace: loss at the trial beta of iteration i
-    double loss_terms[64][3];
-    int accept[64];
-    double u_trace[64];
-};
 
 __device__ __forceinline__ void add_lower(const MatView& M, int r, int c, double v) {
     if (r >= c) M.add(r, c, v);
@@ -124,7 +112,7 @@ __global__ void lm_begin_kernel(LMState* st, double* beta, double* best, int J, 
                                 double minimal_loss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
-        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0;
+        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0; st->ticket = 0;
     }
     if (i < 7 * J) {
         const double val = (i % 7 == 0) ? 1.0 : 0.0;
@@ -148,87 +136,10 @@ __global__ void lm_step_kernel(LMState* st, const int* info, double* beta, const
     if (i == 0 && bad) st->failed = 1;
 }
 
-// squared ARAP residual of (node j, neighbour slot k) = item tid, and squared Rot residual of node j: the loss-only
-// halves of reg_terms_kernel (same expressions, same float32 Rot term)
-__device__ __forceinline__ double arap_loss_item(const double* __restrict__ ed_points, const int* __restrict__ ed_knn,
-                                                 const double* __restrict__ beta, int tid, double lam_arap) {
-    const int j = tid / SB_KNN;
-    const int n = ed_knn[tid];
-    const V3 gj = v3(ed_points[3 * j], ed_points[3 * j + 1], ed_points[3 * j + 2]);
-    const V3 gn = v3(ed_points[3 * n], ed_points[3 * n + 1], ed_points[3 * n + 2]);
-    const V3 d = v3(gj.x - gn.x, gj.y - gn.y, gj.z - gn.z);
-    const double* bn = beta + 7 * n;
-    const double* bj = beta + 7 * j;
-    const V3 qv = v3(bn[1], bn[2], bn[3]);
-    V3 cp;
-    V3 tv = quat_rot_ref(d, bn[0], qv, cp);
-    const double r[3] = {lam_arap * ((tv.x + bn[4]) - (d.x + bj[4])), lam_arap * ((tv.y + bn[5]) - (d.y + bj[5])),
-                         lam_arap * ((tv.z + bn[6]) - (d.z + bj[6]))};
-    return r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-}
-__device__ __forceinline__ double rot_loss_item(const double* __restrict__ beta, int j, double lam_rot) {
-    const float lam = (float)lam_rot;
-    float q[4];
-    for (int a = 0; a < 4; ++a) q[a] = (float)beta[7 * j + a];
-    const float s = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3];
-    const float r = lam * (1.f - s);
-    return (double)(r * r);
-}
-
-struct RegLossArgs {     // ed_points == nullptr: the ARAP / Rot losses come in through loss_arap_rot (separate launch)
-    const double* ed_points; const int* ed_knn; int J; double lam_arap, lam_rot; int use_arap, use_rot;
-};
-
-// loss = sum(data partials) + arap + rot; accept iff loss < minimal_loss   (LM.py:107-117)
+// loss = sum(data partials) + arap + rot; accept iff loss < minimal_loss   (LM.py:107-117): lm_decide_body, lm_state.cuh
 __global__ void lm_decide_kernel(LMState* st, const double* partials, int n_partials, double* loss_arap_rot,
                                  double* beta, double* best, int n, RegLossArgs rg) {
-    __shared__ double red[8];
-    __shared__ int s_accept;
-    __shared__ double s_reg[2];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += 256) s += partials[i];
-    s = block_sum<256>(s, red);
-    if (rg.ed_points) {                      // the regularisers' losses of the stepped beta, in this launch
-        double la = 0.0, lr = 0.0;
-        if (rg.use_arap)
-            for (int i = threadIdx.x; i < rg.J * SB_KNN; i += 256) la += arap_loss_item(rg.ed_points, rg.ed_knn, beta, i, rg.lam_arap);
-        if (rg.use_rot)
-            for (int j = threadIdx.x; j < rg.J; j += 256) lr += rot_loss_item(beta, j, rg.lam_rot);
-        la = block_sum<256>(la, red);
-        lr = block_sum<256>(lr, red);
-        if (threadIdx.x == 0) { s_reg[0] = la; s_reg[1] = lr; }
-    }
-    if (threadIdx.x == 0) {
-        const int it = st->iter;
-        if (st->failed) {
-            s_accept = -1;
-        } else {
-            const double la = rg.ed_points ? s_reg[0] : loss_arap_rot[0], lr = rg.ed_points ? s_reg[1] : loss_arap_rot[1];
-            const double loss = s + la + lr;
-            const bool acc = loss < st->minimal_loss;
-            if (it < 64) {
-                st->loss[it] = loss;
-                st->loss_terms[it][0] = s; st->loss_terms[it][1] = la; st->loss_terms[it][2] = lr;
-                st->accept[it] = acc ? 1 : 0;
-                st->u_trace[it] = st->u;
-            }
-            if (acc) { st->minimal_loss = loss; st->u /= st->v; }
-            else st->u *= st->v;
-            st->iter = it + 1;
-            s_accept = acc ? 1 : 0;
-        }
-        if (loss_arap_rot) {
-            loss_arap_rot[0] = 0.0;
-            loss_arap_rot[1] = 0.0;
-        }
-    }
-    __syncthreads();
-    const int acc = s_accept;
-    if (acc < 0) return;
-    for (int i = threadIdx.x; i < n; i += 256) {
-        if (acc) best[i] = beta[i];
-        else beta[i] = best[i];
-    }
+    lm_decide_body<256>(st, partials, n_partials, loss_arap_rot, beta, best, n, rg);
 }
 
 }  // namespace

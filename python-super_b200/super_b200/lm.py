@@ -29,7 +29,7 @@ class LMWorkspace:
         self.partials = None
         # the regularisers' normal-equation terms (6 CTAs, ~7 us) run on a side stream under the data term's pass
         self.side = torch.cuda.Stream(device=device)
-        self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+        self.fork, self.join, self.cleared = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
 
 def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
@@ -57,13 +57,18 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
     ws.loss2.zero_()
     if band is not None:
         band.info.zero_()
+    overlap = use_data and (use_arap or use_rot) and on_iter is None
+    cleared_ahead = False
     for it in range(opt.num_optimize_iterations):
         if band is not None:
-            band.store.zero_()                                             # AB and g in one memset
+            if cleared_ahead:                # the side stream cleared the other store during the previous iteration
+                band.flip()
+                torch.cuda.current_stream().wait_event(ws.cleared)
+            else:
+                band.store.zero_()           # AB and g in one memset
         else:
             ws.A.zero_()
             ws.g.zero_()
-        overlap = use_data and (use_arap or use_rot) and on_iter is None
         if overlap:      # fork: both kernels only add into the zeroed A, g
             main = torch.cuda.current_stream()
             ws.fork.record(main)
@@ -71,6 +76,10 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
             with torch.cuda.stream(ws.side):
                 ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g, band=band)
                 ws.join.record(ws.side)
+                if band is not None:         # last read by the previous iteration's solve, which the fork is behind
+                    band.other_store.zero_()
+                    ws.cleared.record(ws.side)
+                    cleared_ahead = True
         if use_data:
             ops.data_term_jtj(sf.points, sf.knn_indices, sf.knn_w, order, ed.points, ws.beta, vmap, nmap, cam,
                               lam_d, ws.A, ws.g, n_dev=n_dev, band=band)
@@ -93,11 +102,12 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
             ops.lm_step(ws.state, info, ws.beta, delta)
         if on_iter is not None:
             on_iter(it, "step", ws, delta)
-        if use_data:
-            ops.data_term_loss(sf.points, sf.knn_indices, sf.knn_w, ed.points, ws.beta, vmap, nmap, cam, lam_d,
-                               ws.partials, n_dev=n_dev)
-        else:
-            ws.partials.zero_()
+        if use_data:     # loss-only pass; its last block runs the accept/reject step (one launch)
+            ops.data_term_loss_decide(sf.points, sf.knn_indices, sf.knn_w, ed.points, ed.knn_indices, ws.beta, ws.best,
+                                      vmap, nmap, cam, lam_d, lam_a, lam_r, use_arap, use_rot, ws.partials, ws.state,
+                                      n_dev=n_dev)
+            continue
+        ws.partials.zero_()
         if use_arap or use_rot:      # regularisers' losses inside the decide launch
             ops.lm_decide_reg(ws.state, ws.partials, ed.points, ed.knn_indices, lam_a, lam_r, use_arap, use_rot,
                               ws.beta, ws.best)

@@ -108,16 +108,27 @@ class Band:
     def __init__(self, n, bw, node_pos, device):
         self.n, self.bw = int(n), int(bw)
         self.ldab = self.bw + 1
-        # AB and g share one allocation so that one memset clears both
-        self.store = torch.zeros(self.n * self.ldab + self.n, dtype=F64, device=device)
-        self.AB = self.store[: self.n * self.ldab].view(self.n, self.ldab)
-        self.g = self.store[self.n * self.ldab:]
+        # AB and g share one allocation so that one memset clears both; two of them, so that the LM loop can clear the
+        # next iteration's on a side stream while this iteration's is being solved (flip())
+        self._stores = [torch.zeros(self.n * self.ldab + self.n, dtype=F64, device=device) for _ in range(2)]
+        self._cur = 0
+        self._bind()
         self.node_pos = node_pos
         # solver position -> node id (the step folded into the solve scatters x back to beta's node order)
         self.pos_node = None if node_pos is None else torch.argsort(node_pos.long()).to(I32).contiguous()
         self.overflow = torch.zeros(1, dtype=I32, device=device)
         self.dinv = torch.zeros(self.n, dtype=F64, device=device)
         self.info = torch.zeros(1, dtype=I32, device=device)
+
+    def _bind(self):
+        self.store = self._stores[self._cur]
+        self.other_store = self._stores[self._cur ^ 1]
+        self.AB = self.store[: self.n * self.ldab].view(self.n, self.ldab)
+        self.g = self.store[self.n * self.ldab:]
+
+    def flip(self):
+        self._cur ^= 1
+        self._bind()
 
     def to_dense(self):
         """Symmetric dense matrix in the ORIGINAL node order (tests)."""
@@ -155,6 +166,15 @@ def data_term_loss(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam
     call("sb_data_term_loss", ptr(points), ptr(knn_idx), ptr(knn_w), points.shape[0], ptr(n_dev), ptr(ed_points),
          ptr(beta), ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam), ptr(partials),
          partials.numel(), stream())
+
+
+def data_term_loss_decide(points, knn_idx, knn_w, ed_points, ed_knn, beta, best, vmap, nmap, cam, lam, lam_arap, lam_rot,
+                          use_arap, use_rot, partials, state, n_dev=None):
+    """Loss-only pass + accept/reject (regularisers' losses included) in one launch."""
+    call("sb_data_term_loss_decide", ptr(points), ptr(knn_idx), ptr(knn_w), points.shape[0], ptr(n_dev), ptr(ed_points),
+         ptr(beta), ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam), ptr(partials),
+         partials.numel(), ptr(state.buf), ptr(ed_knn), float(lam_arap), float(lam_rot), int(use_arap), int(use_rot),
+         ptr(beta), ptr(best), stream())
 
 
 def tuple_order(knn_idx, n_dev=None, node_pos=None, block_bw=None):
