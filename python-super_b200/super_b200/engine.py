@@ -2,9 +2,9 @@
 
 This is the B200-native equivalent of SuPer.forward / SuPer.fusion
 (/root/reference/super/super.py:23-83): preprocess -> [init | LM -> update -> fuse -> compact],
-with every stage a handful of CUDA kernels from libsuper_b200.so and NO host synchronisation in
-the tracked-frame path (row counts live on the device; the host only keeps an upper bound that it
-refreshes asynchronously through pinned memory).
+with every stage a handful of CUDA kernels from libsuper_b200.so.  Row counts live on the device; the
+host waits ONCE per tracked frame, for the pinned-memory copy of the row count and of the band width the
+next normal equations need (Tracker._publish_count / _refresh_bound).
 
 Layouts are the reference's in capacity-sized buffers; the drop-in classes in
 super_b200/super/ expose exact-size views of them.

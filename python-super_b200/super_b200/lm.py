@@ -1,9 +1,12 @@
 """Levenberg-Marquardt loop over beta in R^{J x 7} on the device: the B200 restatement of
 LM_Solver.LM (/root/reference/super/LM.py:81-122).
 
-Per iteration: zero A,g -> data-term J^T J kernel (tensor-core Gram panels) -> ARAP/Rot kernel ->
-damping -> dense Cholesky solve -> step -> loss-only pass -> accept/reject.  u, minimal_loss, the
-failure flag and the loss trace stay on the device (ops.LMState): the loop issues no host sync.
+Per iteration, band path (the default): data-term J^T J kernel (tensor-core Gram panels), with the ARAP/Rot kernel
+and the memset of the next iteration's band buffer on a side stream under it -> two-sided banded Cholesky with the
+damping read from the device state and the step beta += delta in its last kernel -> loss-only pass whose last block
+runs the accept/reject step.  Dense path (cross-check): zero A,g -> J^T J -> ARAP/Rot -> damping -> library Cholesky ->
+step -> loss-only pass -> accept/reject.  u, minimal_loss, the failure flag and the loss trace stay on the device
+(ops.LMState): the loop issues no host sync.
 """
 from __future__ import annotations
 
