@@ -156,6 +156,7 @@ def run_cuda(args, rank, world, local_rank):
     trk.step(dd[0], dc, Kt, iKt, host[0]["time"])
     for i in range(1, 1 + Wm):
         trk.step(dd[i], dc, Kt, iKt, host[i]["time"])
+    n_surf_first = trk.num_surfels()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -240,7 +241,7 @@ def run_cuda(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "ms_per_lm_iteration": (total_ms / K) / LM_ITERS,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "configs_index": 1, "frames_timed": K, "surfels": N, "ed_nodes": int(trk.ED.num),
+        "config": {"workload": WORKLOAD, "configs_index": 1, "frames_timed": K, "surfels": N, "surfels_first_timed_frame": n_surf_first, "ed_nodes": int(trk.ED.num),
                    "parallelism": f"{world} independent sequence replica(s), no data-path collective",
                    "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
@@ -257,7 +258,7 @@ def run_cuda(args, rank, world, local_rank):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
         "solver": solver_report(trk, solve_ms),
         "lm_trace_last_frame": {"loss": [float(x) for x in st["loss"]], "accept": [int(x) for x in st["accept"]]},
-        "wall_s_timed_region": wall, "capacity_overflow": overflow,
+        "wall_s_timed_region": wall, "capacity_overflow": overflow, "tuple_order_redone": int(trk._order_redone),
     }
     if gathered:
         out["per_rank"] = gathered

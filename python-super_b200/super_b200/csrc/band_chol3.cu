@@ -1646,7 +1646,7 @@ static void fill_args3(Args3& a, double* AB, int ldab, int n, int bw, double* g,
     a.two_phase = (a.WB * (a.WB + 1) / 2 - 1 > ncta - 2 || (g_debug3 & 64)) ? 1 : 0;
     a.ke = ke < 0 ? a.NP : ke; a.rank0 = rank0; a.ncta = ncta;
     a.prof = (long long*)((char*)ws + ws_bytes3(n, bw) - 1024);
-    a.debug = g_debug3 & ~4;
+    a.debug = ((g_debug3 & 2048) && rank0 == 0 && ke >= 0) ? g_debug3 : (g_debug3 & ~4);   // 2048: role counters of the top instance
 }
 
 /* split: m panels eliminated from the top, m from the bottom, the middle Lm = n - 64 m >= bw rows; 0 = do not split */

@@ -235,6 +235,10 @@ class Tracker:
         self._n_event = None
         self._order = None           # visiting order of the next frame's J^T J pass (computed after compaction)
         self._bands = {}             # half bandwidth -> ops.Band
+        self._order_rows = 0         # rows the precomputed order covers
+        self._n_exact = None         # exact row count at the last hand-over, growth since the one before
+        self._last_growth = 0
+        self._order_redone = 0
         self.n_tmp = torch.zeros(1, dtype=I32, device=self.dev)
         self.overflow = torch.zeros(1, dtype=I32, device=self.dev)
         self.track_id = None
@@ -260,8 +264,14 @@ class Tracker:
     def _publish_count(self):
         self._order = None
         if self.ED is not None and self.ED.node_pos is not None and getattr(self.opt, "use_derived_gradient", True):
-            self._order = ops.tuple_order(self.cur.knn_idx[: self.n_bound], self.cur.n_dev, self.ED.node_pos,
-                                          self.block_bw)
+            # The host's bound at this point is (rows at frame start + H W); the frame really adds a few thousand rows.
+            # Sort the rows that can be expected (last exact count + a margin that follows the last growth); if the
+            # exact count turns out larger, _refresh_bound redoes the order (slow path, counted in _order_redone).
+            rows = self.n_bound
+            if self._n_exact is not None:
+                rows = min(rows, self._n_exact + max(16384, 4 * max(0, self._last_growth)))
+            self._order_rows = rows
+            self._order = ops.tuple_order(self.cur.knn_idx[:rows], self.cur.n_dev, self.ED.node_pos, self.block_bw)
         self._n_pinned.copy_(self.cur.n_dev, non_blocking=True)
         self._bw_pinned[0:1].copy_(self.block_bw, non_blocking=True)
         if self.band is not None:
@@ -274,11 +284,19 @@ class Tracker:
             return
         self._n_event.synchronize()
         self._n_event = None
-        self.n_bound = min(self.cap, int(self._n_pinned[0]))
+        n = min(self.cap, int(self._n_pinned[0]))
+        self._last_growth = 0 if self._n_exact is None else n - self._n_exact
+        self._n_exact = self.n_bound = n
         if self.band is not None and int(self._bw_pinned[1]) != 0:
             raise lib.SuperB200Error("normal-equation entries fell outside the planned band")
         if self._order is not None:
-            self._plan_band(max(int(self._bw_pinned[0]), self.ED.block_bw_ed))
+            bwb = int(self._bw_pinned[0])
+            if n > self._order_rows:             # more rows than the order covers: redo it (synchronises; rare)
+                self._order = ops.tuple_order(self.cur.knn_idx[:n], self.cur.n_dev, self.ED.node_pos, self.block_bw)
+                self._order_rows = n
+                self._order_redone += 1
+                bwb = int(self.block_bw.item())
+            self._plan_band(max(bwb, self.ED.block_bw_ed))
 
     def _plan_band(self, block_bw_needed):
         """Band storage exactly as wide as the pattern (rounded up to the solver's 32-column tile, which costs the

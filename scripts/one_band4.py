@@ -50,3 +50,25 @@ if variant == 4 and os.environ.get("PROF4", "0") == "1":
           "| chain done", pr[58] - t0, "| cta sync", pr[59] - t0, "| exit", pr[61] - t0)
     print("  leader warp 0 totals over its panels: wait for x_{k+1}", pr[64], "| L(k+1,k)^T x + wait pg", pr[65], "| inverse product + x stores", pr[66])
     l.sb_band3_debug(0)
+
+if variant == 4 and os.environ.get("PROFP", "0") == "1":
+    # role counters (debug 4) of the TOP instance of the two-sided solve (debug 2048), per eliminated panel
+    import numpy as np
+    from super_b200 import lib
+    l = lib.load()
+    need = max(bw, 64); m = (n - need) // 64
+    while m > 0 and n - 64 * m < need: m -= 1
+    nA = 32 * m + (n - 64 * m)
+    off = int(l.sb_band3_prof_offset(nA, bw))
+    l.sb_band3_debug(4 | 2048)
+    for _ in range(3):
+        band.AB.copy_(ABd); band.g.copy_(rd); ops.band_solve(band, None, 148, variant=4)
+    torch.cuda.synchronize()
+    prof = band.ws4[off: off + 512].view(torch.int64).cpu().numpy()
+    names = ["potrf-end->top", "wait BAR_A", "trsm", "syrk", "potrf", "io wait upd"]
+    print("  top instance, P role, cycles per eliminated panel (m = %d):" % m, {nm: int(v) // m for nm, v in zip(names, prof[:6])},
+          "| P total", int(prof[9] - prof[8]), "=", int(prof[9] - prof[8]) // m, "per panel",
+          "\n   io warps [release diag, arm+wait Lx, store Lx, release rows, spin upd, stage]:", [[int(v) // m for v in prof[12 + 6 * w:18 + 6 * w]] for w in range(3)],
+          "\n   potrf parts [load, chain+T, dmma update]", [int(v) // m for v in prof[48:51]],
+          "\n   U (rank 3) per panel [wait upd(p-1), operand loads, wait diag(p), Linv load + products + stores, signal, idle]:", [int(v) // m for v in prof[52:58]])
+    l.sb_band3_debug(0)

@@ -89,6 +89,35 @@ def test_free_running_tracker_follows_reference():
     assert np.abs(trk.ED.points.cpu().numpy() - G[f"f{t}.state.ED_points"]).max() < 1e-6
 
 
+def test_hand_over_slow_paths_give_the_same_frames():
+    """The per-frame hand-over (engine.Tracker._publish_count / _refresh_bound): a precomputed tuple order that turns
+    out too short is redone, and a band of another width is planned and cached -- same losses and beta as the plain run."""
+    from super_b200 import engine
+    runs = []
+    for sabotage in (False, True):
+        trk = engine.Tracker(G.opt)
+        out = []
+        for t in G.frames:
+            f = G.frame(t)
+            if sabotage and trk.cur is not None:
+                # pretend the order computed after the last compaction covered only a few rows, and that the planned band
+                # was another one: the first forces the redo path, the second a (cached) re-plan
+                trk._order_rows = 64
+                trk._order = trk._order[:64].contiguous()
+                trk.band = None
+            beta = trk.step(torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["color"]).cuda(),
+                            torch.from_numpy(f["K"]), torch.from_numpy(f["inv_K"]), f["time"])
+            if beta is not None:
+                out.append((trk.ws.state.read()["loss"].copy(), beta.cpu().numpy().copy(), trk.num_surfels()))
+        if sabotage:
+            assert trk._order_redone == len(G.frames) - 1 and trk.band is not None
+        runs.append(out)
+    for (la, ba, na), (lb, bb, nb) in zip(*runs):
+        assert na == nb
+        assert np.abs(la - lb).max() <= 1e-9 * np.abs(la).max()      # atomics: summation order differs run to run
+        assert np.abs(ba - bb).max() < 1e-9
+
+
 def test_init_state_matches_reference():
     from super_b200 import engine
     trk = engine.Tracker(G.opt)
