@@ -185,8 +185,24 @@ constexpr int FL_DOUBLES = 436;          // flush scratch: packed upper triangle
 // common.cuh MatView), g (= -J^T r) and the optional sum r^2.  The tiles go through a shared 32x32 scratch and
 // a run-time loop over the 29x29 upper triangle: the fully unrolled version was 2 x 2.4 k instructions and made
 // the kernel miss the instruction cache (ncu r1c: "no instruction" stalls 3.0 per issue, as much as memory).
+// table of the 435 packed upper-triangle entries e -> (node slot, component) of its row m and column n:
+// km | cm << 3 | kn << 6 | cn << 9 with m = 7 km + cm, n = 7 kn + cn  (km = 4: the residual row/column 28).
+// Built once per CTA (ncu r1e: decoding m, n by sqrt + correction loops in every flush iteration was 115 instructions per
+// iteration and the flush 30 % of the kernel's issue slots and 32 % of its stall samples).
+__device__ __forceinline__ void build_flush_table(unsigned short* tab, int tid, int nthreads) {
+    for (int e = tid; e < 435; e += nthreads) {
+        int m = (int)((59.f - sqrtf(3481.f - 8.f * (float)e)) * 0.5f);
+        while ((m + 1) * 29 - (m + 1) * m / 2 <= e) ++m;
+        while (m * 29 - m * (m - 1) / 2 > e) --m;
+        const int n = m + (e - (m * 29 - m * (m - 1) / 2));
+        const int km = m / 7, cm = m - 7 * km, kn = n / 7, cn = n - 7 * kn;
+        tab[e] = (unsigned short)(km | (cm << 3) | (kn << 6) | (cn << 9));
+    }
+}
+
 __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, const MatView& M,
-                                          double* g, double* loss_cur, double* __restrict__ St) {
+                                          double* g, double* loss_cur, double* __restrict__ St,
+                                          const unsigned short* __restrict__ tab) {
     int t = 0;
 #pragma unroll
     for (int ti = 0; ti < 4; ++ti)
@@ -201,27 +217,23 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
             }
         }
     __syncwarp();
-    // the 435 entries (m <= n <= 28) of the upper triangle are dealt round-robin to the lanes (14 each);
-    // row m belongs to node m/7, component m%7; row/column 28 is the residual column.  Lane k < 4 looks up the
-    // solver position of node k once; the others fetch it by shuffle.
+    // the 435 entries (m <= n <= 28) of the upper triangle are dealt round-robin to the lanes (14 each).  Lane k < 4 looks
+    // up the solver position of node k once; everybody fetches the four of them by shuffle before the loop.
     const int my_pos = (lane < 4) ? M.pos((int)(key >> (48 - 16 * lane)) & 0xffff) : 0;
-    for (int e0 = 0; e0 < 448; e0 += 32) {
-        const int e = e0 + lane;
-        int m = (int)((59.f - sqrtf(3481.f - 8.f * (float)min(e, 434))) * 0.5f);
-        while ((m + 1) * 29 - (m + 1) * m / 2 <= min(e, 434)) ++m;
-        while (m * 29 - m * (m - 1) / 2 > min(e, 434)) --m;
-        const int n = m + (min(e, 434) - (m * 29 - m * (m - 1) / 2));
-        const int km = (m * 37) >> 8, cm = m - 7 * km;                     // m/7, m%7 for m < 29  (km = 4 for m = 28)
-        const int kn = (n * 37) >> 8, cn = n - 7 * kn;
-        const int pm = __shfl_sync(0xffffffffu, my_pos, km & 3), pn = __shfl_sync(0xffffffffu, my_pos, kn & 3);
-        if (e >= 435) continue;
+    const int p0 = __shfl_sync(0xffffffffu, my_pos, 0), p1 = __shfl_sync(0xffffffffu, my_pos, 1);
+    const int p2 = __shfl_sync(0xffffffffu, my_pos, 2), p3 = __shfl_sync(0xffffffffu, my_pos, 3);
+    for (int e = lane; e < 435; e += 32) {
         const double val = St[e];
         if (val == 0.0) continue;
-        if (n == 28) {
-            if (m == 28) { if (loss_cur) atomicAdd(loss_cur, val); }
+        const unsigned tb = tab[e];
+        const int km = tb & 7, cm = (tb >> 3) & 7, kn = (tb >> 6) & 7, cn = (tb >> 9) & 7;
+        const int pm = km == 0 ? p0 : km == 1 ? p1 : km == 2 ? p2 : p3;
+        if (kn == 4) {                       // column 28: -J^T r, and r^T r in the corner
+            if (km == 4) { if (loss_cur) atomicAdd(loss_cur, val); }
             else atomicAdd(g + 7 * pm + cm, -val);
             continue;
         }
+        const int pn = kn == 0 ? p0 : kn == 1 ? p1 : kn == 2 ? p2 : p3;
         const int gm = 7 * pm + cm, gn = 7 * pn + cn;
         M.add(max(gm, gn), min(gm, gn), val);
     }
@@ -231,10 +243,13 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
 __global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
 data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur) {
     extern __shared__ double smem[];
+    __shared__ unsigned short fl_tab[448];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
     double* St = Jt + JT_DOUBLES;
     for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
+    build_flush_table(fl_tab, threadIdx.x, JTJ_WARPS * 32);
+    __syncthreads();
 
     const int n = n_active(a.n_cap, a.n_dev);
     const int n_chunks = (n + 31) >> 5;
@@ -274,7 +289,7 @@ data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur)
             const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
             const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
             if (!have || k != acc_key) {
-                if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur, St);
+                if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur, St, fl_tab);
                 acc_key = k;
                 have = !tail;
             }
