@@ -15,7 +15,7 @@ ts = []
 for _ in range(reps):
     band.AB.copy_(ABd); band.g.copy_(rd)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); ops.band_solve(band, None, 148, variant=variant); e1.record(); torch.cuda.synchronize()
+    e0.record(); ops.band_solve(band, None, int(os.environ.get("CS", 148)), variant=variant); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 print(f"n={n} bw={bw} variant={variant}: us per solve {[round(t, 1) for t in ts]}")
 if variant == 4 and os.environ.get("STAGES", "1") == "1":
