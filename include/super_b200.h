@@ -138,7 +138,9 @@ int sb_data_term_loss(const double* points, const int* knn_idx, const double* kn
                       int n_partials, void* stream);
 
 /* loss-only pass + the accept/reject step of the iteration in ONE launch (sb_data_term_loss followed by sb_lm_decide_reg):
- * the last block to deliver its partial sums them in their fixed order and decides.  beta_in == beta (the trial beta). */
+ * /root/reference/super/loss.py:212-246,290 (DataLoss.forward, grad=False), loss.py:433-437,487-497 (ARAP / Rot losses) and
+ * /root/reference/super/LM.py:107-117 (accept iff loss < minimal_loss; u /= v or u *= v, revert beta).  The last block to
+ * deliver its partial sums them in their fixed order and decides.  beta_in == beta (the trial beta). */
 int sb_data_term_loss_decide(const double* points, const int* knn_idx, const double* knn_w, int n_cap,
                              const int* n_dev, const double* ed_points, const double* beta_in, int J, const float* vmap,
                              const float* nmap, int H, int W, const double* intr, double lambda, double* partials,
