@@ -129,9 +129,56 @@ def dilate(x, kernel):
     return F.conv2d(x, k, padding="same") > 0
 
 
-def normals_8(points, colors):
+def fma32(a, b, c):
+    """Correctly rounded float32 fma(a, b, c) on float32 tensors, machine-independent: the product is exact in
+    float64, the sum is rounded to ODD in float64 (TwoSum error term), and the cast to float32 then rounds once."""
+    p = a.double() * b.double()
+    c = c.double().expand_as(p)
+    s = p + c
+    bb = s - p
+    e = (p - (s - bb)) + (c - bb)
+    even = (s.view(torch.int64) & 1) == 0
+    fix = even & (e != 0) & torch.isfinite(s)
+    toward = torch.where(e > 0, torch.full_like(s, math.inf), torch.full_like(s, -math.inf))
+    s = torch.where(fix, torch.nextafter(s, toward), s)
+    return s.float()
+
+
+EXP_LOG2E = 1.4426950408889634        # the literals below are part of the DEFINITION (csrc/preprocess.cu holds the same)
+EXP_LN2_HI = 0.693147180369123816490  # ln 2 with the low 21 mantissa bits cleared: n * LN2_HI is exact for |n| < 2^21
+EXP_LN2_LO = 1.90821492927058770002e-10
+EXP_COEF = [1.0 / math.factorial(k) for k in range(14)]
+
+
+def exp32_def(x):
+    """exp of a float32 tensor, returned as float32.  DEFINED here (and restated instruction for instruction in
+    csrc/preprocess.cu exp32_def) because the reference's torch.exp on CPU float32 is MKL VML's vsExp, which is neither
+    correctly rounded nor available as source: n = rint(x log2 e), r = (x - n LN2_HI) - n LN2_LO, degree-13 Taylor
+    polynomial by Horner in float64 with separate multiplies and adds (no FMA), 2^n p rounded once to float32.  Agrees
+    with the correctly rounded exp except where exp(x) lies within ~1e-16 relative of a float32 rounding boundary;
+    differs from the reference's vsExp in the last float32 bit on ~1.2 % of arguments (oracle/validate_port.py)."""
+    xd = x.double()
+    n = torch.round(xd * EXP_LOG2E)
+    r = (xd - n * EXP_LN2_HI) - n * EXP_LN2_LO
+    p = torch.full_like(r, EXP_COEF[13])
+    for k in range(12, -1, -1):
+        p = p * r + EXP_COEF[k]
+    return torch.ldexp(p, n.to(torch.int32)).float()
+
+
+def normals_8(points, colors, exp=None):
     """getN with colours (/root/reference/utils/data_loader.py:546-583): ring neighbours in order
-    L, LU, U, RU, R, RD, D, DL; h_a = (p_a - p_c) * exp(-mean|c_a - c_c|); N = sum_{a<b} h_a x h_b."""
+    L, LU, U, RU, R, RD, D, DL; h_a = (p_a - p_c) * exp(-mean|c_a - c_c|); N = sum_{a<b} h_a x h_b, normalised.
+    float32 throughout.  Every step whose rounding depends on how torch's CPU kernels happen to be compiled is spelt
+    out, so that the result is the same on any machine (measured bit-identical to the reference's own ops on the
+    build container except for exp, see exp32_def):
+      mean over 3 channels   ((a0 + a1) + a2) / 3
+      cross product          fma(a1, b2, -(a2 b1)) per component (torch.linalg.cross, CPU float32)
+      sum of the 7 terms     torch's 4-accumulator row sum: (((((t0 + t4) + t5) + t6) + t1) + t2) + t3
+      F.normalize            n = sqrt(fma(z, z, fma(y, y, x x))) with the correctly rounded sqrt, N / max(n, 1e-12)
+    exp: the float32 exponential; None = exp32_def (the definition the CUDA path is held to), torch.exp = the
+    reference's own (used by the tests that pin this port against the reference's golden vectors)."""
+    exp = exp or exp32_def
     b, h, w, _ = points.shape
     col = F.pad(colors.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1), value=float("nan"))
     pts = F.pad(points, (0, 0, 1, 1, 1, 1), value=float("nan"))
@@ -142,16 +189,24 @@ def normals_8(points, colors):
     for dy, dx in offs:
         ca = col[:, 1 + dy:h + 1 + dy, 1 + dx:w + 1 + dx, :].reshape(-1, 3)
         pa = pts[:, 1 + dy:h + 1 + dy, 1 + dx:w + 1 + dx, :].reshape(-1, 3)
-        wgt = torch.exp(-torch.mean(torch.abs(ca - cc), dim=1, keepdim=True))
-        hs.append((pa - pc) * wgt)
-    terms = []
+        ad = torch.abs(ca - cc)
+        m = ((ad[:, 0:1] + ad[:, 1:2]) + ad[:, 2:3]) / 3.0
+        hs.append((pa - pc) * exp(-m))
+
+    def cross(a, bb):
+        return torch.stack([fma32(a[:, 1], bb[:, 2], -(a[:, 2] * bb[:, 1])),
+                            fma32(a[:, 2], bb[:, 0], -(a[:, 0] * bb[:, 2])),
+                            fma32(a[:, 0], bb[:, 1], -(a[:, 1] * bb[:, 0]))], dim=1)
+    t = []
     for a in range(7):
         rest = hs[a + 1]
         for bb in range(a + 2, 8):
             rest = rest + hs[bb]
-        terms.append(torch.linalg.cross(hs[a], rest))
-    N = torch.stack(terms, dim=2).sum(2)
-    N = F.normalize(N, dim=-1).reshape(b, h, w, 3)
+        t.append(cross(hs[a], rest))
+    N = (((((t[0] + t[4]) + t[5]) + t[6]) + t[1]) + t[2]) + t[3]
+    n2 = fma32(N[:, 2], N[:, 2], fma32(N[:, 1], N[:, 1], N[:, 0] * N[:, 0]))
+    nn = torch.from_numpy(np.sqrt(n2.numpy())).clamp_min(1e-12)     # IEEE sqrt (torch.sqrt on CPU float32 is not)
+    N = (N / nn[:, None]).reshape(b, h, w, 3)
     return N, ~torch.any(torch.isnan(N), -1)
 
 
@@ -169,11 +224,14 @@ def find_edge_region(seg, num_classes, class_id, kernel, ignore_img_edge=True):
     return edge
 
 
-def preprocess(opt, frame):
+def preprocess(opt, frame, ref_exp=False):
     """depth_preprocessing (/root/reference/utils/data_loader.py:333-523) for --load_depth inputs.
     `frame`: dict from super_b200.synth.frame_inputs (numpy).  Returns new_data namespace:
     points,norms (Nv,3) f64; colors (Nv,3) f32; radii (Nv,) f64; confs (Nv,) f32; valid (P,) bool;
-    index_map (H,W) i64; time; [seg, seg_conf, dist2edge]."""
+    index_map (H,W) i64; time; [seg, seg_conf, dist2edge].
+    ref_exp: evaluate the two float32 exponentials (normal weights, confidences) with torch.exp like the reference
+    instead of exp32_def -- for the golden-vector pin tests only."""
+    exp = torch.exp if ref_exp else exp32_def
     H, W = opt.height, opt.width
     depth = torch.from_numpy(frame["depth"]).clone()[None]          # (1,1,H,W) f32
     color = torch.from_numpy(frame["color"])[None]                  # (1,3,H,W) f32
@@ -191,12 +249,12 @@ def preprocess(opt, frame):
     # The reference does torch.matmul(inv_K[:, :3, :3], pix) in float32.  Its CPU BLAS evaluates each
     # entry as the FMA chain  t = a*x; t = fma(b, y, t); t = fma(c, 1, t)  (measured here, bit for bit:
     # oracle/validate_port.py); the restatement spells that chain out so that it does not depend on the
-    # BLAS build of the machine it runs on.  fma is emulated in float64 (f32 products are exact there).
-    ik = inv_K[0, :3, :3].double()
-    px, py, p1 = pix[0, 0:1].double(), pix[0, 1:2].double(), pix[0, 2:3].double()
-    t = (ik[:, 0:1] * px).float()
-    t = (ik[:, 1:2] * py + t.double()).float()
-    cam = (ik[:, 2:3] * p1 + t.double()).float()[None]
+    # BLAS build of the machine it runs on (fma32: exact float32 fma).
+    ik = inv_K[0, :3, :3]
+    px, py, p1 = pix[0, 0:1], pix[0, 1:2], pix[0, 2:3]
+    t = ik[:, 0:1] * px
+    t = fma32(ik[:, 1:2].expand(3, H * W), py.expand(3, H * W), t)
+    cam = fma32(ik[:, 2:3].expand(3, H * W), p1.expand(3, H * W), t)[None]
     cam = depth.view(1, 1, -1) * cam
     pcd = cam.reshape(1, 3, H, W).permute(0, 2, 3, 1).clone()
 
@@ -220,7 +278,7 @@ def preprocess(opt, frame):
         depth[inval] = float("nan")
         pcd[inval[0]] = float("nan")
 
-    norms, valid = normals_8(pcd, color)                             # :437-441
+    norms, valid = normals_8(pcd, color, exp)                           # :437-441
     valid &= ~torch.any(torch.isnan(pcd), dim=3)
     Z = -depth
     points = pcd[0].type(F64)
@@ -233,7 +291,7 @@ def preprocess(opt, frame):
     radii = Z[0, 0][valid] / (np.sqrt(2) * K[0, 0, 0] * torch.clamp(torch.abs(norms[..., 2]), 0.26, 1.0))
     U, V = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
     dc2 = (2. * (U / W) - 1.) ** 2 + (2. * (V / H) - 1.) ** 2
-    confs = torch.exp(-dc2 * frame["divterm"])
+    confs = exp(-dc2 * frame["divterm"])
     colors = color[0].permute(1, 2, 0)[valid]
     nd = NS(points=points, norms=norms, colors=colors, radii=radii, confs=confs[valid],
             valid=valid.view(-1), index_map=index_map, valid_map=valid, time=int(frame["filename"]))

@@ -91,9 +91,19 @@ def main():
         t = fr["t"]
         print(f"== frame {t}")
         frame = synth.frame_inputs(t, a.height, a.width, tex=tex, speed=a.speed)
-        nd = so.preprocess(opt, frame)
+        nd = so.preprocess(opt, frame, ref_exp=True)     # with the reference's own float32 exp: everything bit-exact
         for k in ("points", "norms", "colors", "radii", "confs", "valid", "index_map"):
             cmp(f"new_data.{k}", getattr(nd, k), fr["new_data"][k], report=report)
+        # with the oracle's DEFINED exponential (exp32_def, what the CUDA path is held to): same validity and points,
+        # normals / confidences / radii within float32 rounding of the reference's
+        nd_def = so.preprocess(opt, frame)
+        for k in ("points", "valid", "index_map"):
+            cmp(f"new_data[exp32_def].{k}", getattr(nd_def, k), fr["new_data"][k], report=report)
+        cmp("new_data[exp32_def].norms", nd_def.norms, fr["new_data"]["norms"], tol=2.5e-7, report=report)
+        cmp("new_data[exp32_def].confs", nd_def.confs.double(), fr["new_data"]["confs"].astype(np.float64), tol=1e-7, report=report)
+        cmp("new_data[exp32_def].radii", nd_def.radii, fr["new_data"]["radii"], tol=1e-9, report=report)
+        nb = int((nd_def.norms != nd.norms).any(1).sum())
+        print(f"  exp32_def vs the reference's exp: {nb} of {len(nd.norms)} normals differ in the last float32 bit")
         nd_ref = newdata_from_snapshot(fr["new_data"], fr["K"])
         if prev_state is None:
             graph = so.build_graph(opt, nd_ref)

@@ -5,9 +5,10 @@
 // in two stencil passes instead of ~150 ATen launches, and keeps everything on the device (the
 // reference leaves index_map on the CPU, data_loader.py:464).
 //
-// float32 arithmetic follows the reference's op order where it decides VALUES that the tracker
-// treats as exact (back-projected points are f32 and compared bit-exactly in tests); normals go
-// through expf/sqrtf and are tolerance-checked (1e-6).
+// float32 arithmetic follows the reference's op order and roundings instruction for instruction (points, normals,
+// radii and confidences are compared BIT-EXACTLY against oracle/super_oracle.py preprocess in the tests): torch's CPU
+// kernels' summation order and FMA placement as measured (oracle normals_8 docstring), the IEEE sqrt / divide, and the
+// exponential DEFINED in the oracle (exp32_def: the reference's is MKL's vsExp, not reproducible from source).
 #include "common.cuh"
 #include "super_b200.h"
 
@@ -51,6 +52,21 @@ __global__ void backproject_kernel(PreArgs a, float4* __restrict__ pcd) {
     pcd[p] = o;
 }
 
+// exp32_def of oracle/super_oracle.py, same operations in the same order: float64, no FMA contraction
+__device__ __forceinline__ float exp32_def(float xf) {
+    const double x = (double)xf;
+    const double n = rint(__dmul_rn(x, 0x1.71547652b82fep+0));
+    const double r = __dsub_rn(__dsub_rn(x, __dmul_rn(n, 0x1.62e42fee00000p-1)), __dmul_rn(n, 0x1.a39ef35793c76p-33));
+    const double c[14] = {0x1.0000000000000p+0,  0x1.0000000000000p+0,  0x1.0000000000000p-1,  0x1.5555555555555p-3,
+                          0x1.5555555555555p-5,  0x1.1111111111111p-7,  0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13,
+                          0x1.a01a01a01a01ap-16, 0x1.71de3a556c734p-19, 0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26,
+                          0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33};
+    double p = c[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = __dadd_rn(__dmul_rn(p, r), c[k]);
+    return __double2float_rn(ldexp(p, (int)n));
+}
+
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ F3 add3(F3 a, F3 b) { return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
@@ -81,20 +97,22 @@ __global__ void normals_kernel(PreArgs a, const float4* __restrict__ pcd, float4
         const float4 pa = pcd[q];
         const float m = __fdiv_rn(__fadd_rn(__fadd_rn(fabsf(__fsub_rn(a.color[q], c0)), fabsf(__fsub_rn(a.color[P + q], c1))),
                                             fabsf(__fsub_rn(a.color[2 * P + q], c2))), 3.f);
-        const float wgt = expf(-m);
+        const float wgt = exp32_def(-m);
         h[k] = f3(__fmul_rn(__fsub_rn(pa.x, pc.x), wgt), __fmul_rn(__fsub_rn(pa.y, pc.y), wgt),
                   __fmul_rn(__fsub_rn(pa.z, pc.z), wgt));
     }
-    F3 N = f3(0.f, 0.f, 0.f);
+    F3 t[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
         F3 rest = h[i + 1];
 #pragma unroll
         for (int j = i + 2; j < 8; ++j) rest = add3(rest, h[j]);
-        const F3 c = crossf(h[i], rest);
-        N = (i == 0) ? c : add3(N, c);
+        t[i] = crossf(h[i], rest);
     }
-    const float nn = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(N.x, N.x), __fmul_rn(N.y, N.y)), __fmul_rn(N.z, N.z))), 1e-12f);
+    // torch's row sum over 7 contiguous floats (4 accumulators): (((((t0+t4)+t5)+t6)+t1)+t2)+t3
+    F3 N = add3(add3(add3(add3(add3(add3(t[0], t[4]), t[5]), t[6]), t[1]), t[2]), t[3]);
+    // F.normalize: vector_norm accumulates by FMA, z*z + (y*y + x*x); IEEE sqrt and divide
+    const float nn = fmaxf(__fsqrt_rn(__fmaf_rn(N.z, N.z, __fmaf_rn(N.y, N.y, __fmul_rn(N.x, N.x)))), 1e-12f);
     N = f3(__fdiv_rn(N.x, nn), __fdiv_rn(N.y, nn), __fdiv_rn(N.z, nn));
     const bool valid = !(isnan(N.x) || isnan(N.y) || isnan(N.z) || isnan(pc.x) || isnan(pc.y) || isnan(pc.z));
     float4 v, n;
@@ -115,7 +133,7 @@ __global__ void normals_kernel(PreArgs a, const float4* __restrict__ pcd, float4
     const float su = __fsub_rn(__fmul_rn(2.f, __fdiv_rn((float)x, (float)W)), 1.f);
     const float sv = __fsub_rn(__fmul_rn(2.f, __fdiv_rn((float)y, (float)H)), 1.f);
     const float dc2 = __fadd_rn(__fmul_rn(su, su), __fmul_rn(sv, sv));
-    confs[p] = expf(__fmul_rn(-dc2, a.divterm));
+    confs[p] = exp32_def(__fmul_rn(-dc2, a.divterm));
     if (valid_i32) valid_i32[p] = valid ? 1 : 0;
 }
 

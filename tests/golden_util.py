@@ -53,7 +53,8 @@ class Golden:
         sf.track_id = None
         return sf
 
-    def new_data(self, t):
+    def new_data(self, t, ref_exp=True):
         """new_data of frame t: recomputed by the port's producer (checked against the golden copies
-        in test_oracle_golden.py)."""
-        return so.preprocess(self.opt, self.frame(t))
+        in test_oracle_golden.py).  ref_exp: with the reference's float32 exp (torch.exp), so that everything downstream
+        compares against the reference's golden vectors at rounding level; False = the oracle's defined exp32_def."""
+        return so.preprocess(self.opt, self.frame(t), ref_exp=ref_exp)

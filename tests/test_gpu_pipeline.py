@@ -20,18 +20,32 @@ def _gpu_frame(t):
                              torch.from_numpy(f["K"]), torch.from_numpy(f["inv_K"]), f["time"])
 
 
-@pytest.mark.parametrize("t", G.frames[:2])
-def test_producer_matches_oracle(t):
-    nd = G.new_data(t)
-    fr = _gpu_frame(t)
+def _check_producer_bit_exact(fr, nd):
     valid = fr.valid.cpu()
     assert torch.equal(valid, nd.valid), "validity map differs"
-    # float32 back-projection: same FMA chain as the reference's CPU BLAS (oracle.preprocess) -> bit-exact
+    # float32 arithmetic restated instruction for instruction (oracle normals_8 / exp32_def): everything is bit-exact
     assert torch.equal(fr.vmap.cpu()[valid, :3].double(), nd.points), "back-projected points must be bit-exact (f32)"
-    assert (fr.nmap.cpu()[valid, :3].double() - nd.norms).abs().max() < 2e-6
-    assert ((fr.radii.cpu()[valid] - nd.radii).abs() <= 2e-6 * nd.radii.abs()).all()
-    assert (fr.confs.cpu()[valid] - nd.confs).abs().max() < 1e-6
+    assert torch.equal(fr.nmap.cpu()[valid, :3].double(), nd.norms), "normals must be bit-exact (f32)"
+    assert torch.equal(fr.confs.cpu()[valid], nd.confs), "confidences must be bit-exact (f32)"
+    assert ((fr.radii.cpu()[valid] - nd.radii).abs() <= 4e-16 * nd.radii.abs()).all()     # one f64 divide
     assert float(fr.vmap.cpu()[~valid].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("t", G.frames[:2])
+def test_producer_matches_oracle(t):
+    _check_producer_bit_exact(_gpu_frame(t), G.new_data(t, ref_exp=False))
+
+
+@pytest.mark.parametrize("data", ["superv1", "superv2"])
+def test_producer_bit_exact_fullsize(data):
+    """640x480, both datasets' validity rules: the producer's float32 outputs equal the oracle's to the bit."""
+    from super_b200 import engine, synth
+    H, W = 480, 640
+    opt = so.default_opt(height=H, width=W, data=data)
+    f = synth.frame_inputs(7, H, W, data=data)
+    fr = engine.preprocess(opt, torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["color"]).cuda(),
+                           torch.from_numpy(f["K"]), torch.from_numpy(f["inv_K"]), f["time"])
+    _check_producer_bit_exact(fr, so.preprocess(opt, f))
 
 
 @pytest.mark.parametrize("t", TRACKED)
