@@ -13,6 +13,7 @@ pinned HOST buffers (H2D of depth+colour and a D2H read of beta inside the timed
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -120,7 +121,7 @@ def solver_report(trk, solve_ms):
     n, bw = trk.band.n, trk.band.bw
     ms = float(np.mean(solve_ms))
     variant = os.environ.get("SB_BAND_VARIANT", "4")
-    kern = ("band_reverse + band_chol3_dual + band_combine + band_chol3 + band_backsub4 kernels (sb_band_solve4_step: two-sided solve, LM step folded into the last kernel)"
+    kern = ("band_from_fixed + band_reverse + band_chol3_dual + band_combine + band_chol3 + band_backsub4 kernels (fixed-point store -> f64 band, then sb_band_solve4_step: two-sided solve, LM step folded into the last kernel)"
             if variant == "4" else "band_chol3_kernel (sb_band_solve3)")
     return {"kernel": kern, "n": n, "half_bandwidth": bw, "ms_per_solve": ms,
             "solves_timed": len(solve_ms), "band_flops": float(n) * bw * bw, "dense_flops": float(n) ** 3 / 3.0,
@@ -181,8 +182,9 @@ def run_cuda(args, rank, world, local_rank):
     sampler.mark_begin()
     lib.LAUNCHES = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev, sev = [], []     # (start, end) events around every data-term J^T J launch / every banded solve
-    lib.KERNEL_EVENTS = {"sb_data_term_jtj": kev, "sb_band_solve3": sev, "sb_band_solve4": sev, "sb_band_solve4_step": sev}
+    # (begin, end) CUDA events on the launch stream around the first 3 J^T J passes and the first 2 linear solves of
+    # every timed frame, recorded inside sb_lm_frame (SbLMFrame.jtj_events / solve_events)
+    trk.event_sink = {"jtj": [], "solve": []}
     t_wall = time.perf_counter()
     for k in range(K):
         i = 1 + Wm + k
@@ -192,13 +194,23 @@ def run_cuda(args, rank, world, local_rank):
         ev[k][1].record()
     barrier()
     wall = time.perf_counter() - t_wall
-    lib.KERNEL_EVENTS = None
     launches = lib.LAUNCHES
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
-    jt_ms = [a.elapsed_time(b) for a, b in kev]
-    solve_ms = [a.elapsed_time(b) for a, b in sev]
+
+    def ev_ms(pairs):
+        out = []
+        for a, b in pairs:
+            ms = ctypes.c_float()
+            lib.call("sb_event_elapsed_ms", a, b, ctypes.byref(ms))
+            out.append(ms.value)
+        return out
+    jt_ms, solve_ms = ev_ms(trk.event_sink["jtj"]), ev_ms(trk.event_sink["solve"])
+    for a, b in trk.event_sink["jtj"] + trk.event_sink["solve"]:
+        lib.call("sb_event_destroy", a)
+        lib.call("sb_event_destroy", b)
+    trk.event_sink = None
     n_surf = trk.num_surfels()
     st = trk.ws.state.read()
     overflow = int(trk.overflow.item())
@@ -271,7 +283,7 @@ def run_cuda(args, rank, world, local_rank):
         "gpu_launches": launches,
         "gpu_launches_per_lm_iteration": launches / (K * LM_ITERS),
         "clocks": clocks,
-        "roofline": {"kernel": "data_jtj_kernel (fused warp+project+bilinear+Jacobian+J^T J, one LM iteration)",
+        "roofline": {"kernel": "data_jtj_kernel<fused> (warp+project+bilinear+Jacobian+J^T J of one LM iteration; ARAP/Rot blocks and the LM decision ride in the same launch)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
                      "algorithmic_bytes": b_pass, "launch_ms": jt_avg_ms,
@@ -383,6 +395,7 @@ def run_reference(args, rank):
            "steps": steps_done, "warmup": args.warmup, "ms_per_step": 1e3 * frame_s,
            "ms_per_lm_iteration": 1e3 * t_it, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "configs_index": 1},
+           "extrapolated": True,     # frame time = producer + 10 x (timed LM iteration) + update/fuse/compact, not a timed frame
            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)

@@ -71,6 +71,59 @@ typedef struct SbFuseParams {
     const int* ed_seg;          /* (J,) i32 node classes: new surfels search their nodes inside their own class (--hard_seg, nodes.py:494-497) or NULL */
 } SbFuseParams;
 
+/* Everything one tracked frame's LM solve reads and writes (sb_lm_frame).  Device pointers unless marked host. */
+typedef struct SbLMFrame {
+    /* surfel model: Surfels.points / knn_indices / knn_w (/root/reference/super/nodes.py:36-91) */
+    const double* points;       /* (n_cap,3) f64 */
+    const int* knn_idx;         /* (n_cap,4) i32 */
+    const double* knn_w;        /* (n_cap,4) f64 */
+    const int* order;           /* (n_cap,) i32 visiting order (sb_tuple_keys, sorted) or NULL */
+    int n_cap;
+    const int* n_dev;
+    /* ED graph */
+    const double* ed_points;    /* (J,3) */
+    const int* ed_knn;          /* (J,4) i32 */
+    int J;
+    /* new frame */
+    const float* vmap;          /* (P,4) f32 */
+    const float* nmap;          /* (P,4) f32 */
+    int H, W;
+    double intr[4];             /* fx, fy, cx, cy */
+    /* terms: sqrt-free weights as LM_Solver passes them (/root/reference/super/LM.py:18-26) */
+    double lam_data, lam_arap, lam_rot;
+    int use_arap, use_rot;
+    /* controller: LM(u=10, v=7.5, minimal_loss=1e10), num_optimize_iterations (/root/reference/super/LM.py:81-92) */
+    int iterations;
+    double u, v, minimal_loss;
+    void* state;                /* sb_lm_state_bytes() */
+    double* beta;               /* (J,7) out: the frame's result */
+    double* best;               /* (J,7) scratch */
+    double* partials_jtj;       /* n_partials_jtj >= sb_lm_frame_partials(n_cap) doubles */
+    int n_partials_jtj;
+    double* partials_loss;      /* n_partials_loss == sb_data_loss_blocks(n_cap) doubles */
+    int n_partials_loss;
+    /* normal equations, band storage in the solver's node order */
+    int n, bw, ldab;            /* n = 7J, half bandwidth, row stride (>= bw+1) */
+    const int* node_pos;        /* node id -> solver position, or NULL */
+    const int* pos_node;        /* solver position -> node id, or NULL */
+    long long* fx_store[2];     /* two fixed-point stores of n*ldab + n int64 each (AB | g) */
+    int fx_shift, fx_gshift;    /* entries are multiples of 2^-fx_shift (AB), 2^-fx_gshift (g) */
+    double* AB;                 /* (n,ldab) f64 work band the solver factors */
+    double* g;                  /* (n,) f64 work right-hand side / solution */
+    int* band_overflow;         /* bit 0: entry outside the band, bit 1: addend outside the fixed-point range */
+    double* dinv;               /* (n,) scratch */
+    int* info;                  /* factorisation status */
+    void* solver_ws;            /* sb_band4_workspace_bytes(n, bw, ldab) */
+    long long solver_ws_bytes;
+    int n_ctas;
+    /* measurement (optional, HOST array of cudaEvent_t from sb_event_create): events [2k], [2k+1] are recorded on `stream`
+     * right before / after the k-th J^T J pass of the frame, for as many passes as the array covers */
+    void* const* jtj_events;
+    int n_jtj_events;
+    void* const* solve_events;  /* the same around the k-th linear solve (from_fixed + the five solver kernels) */
+    int n_solve_events;
+} SbLMFrame;
+
 int sb_version(void);
 
 /* ---- kNN / weights / warp -------------------------------------------------------------------- */
@@ -124,11 +177,15 @@ int sb_data_loss_blocks(int n_cap);
  * both must be zeroed (or hold the other terms) by the caller.  `order` (n,) optional kNN-tuple-sorted
  * surfel ids.  intr = host double[4] {fx,fy,cx,cy}.  loss_cur (optional) accumulates sum r^2 at beta.
  * Matrix target: bw < 0 -> dense A[row*lda + col]; bw >= 0 -> lower band A[row*lda + col - row + bw] in the
- * node order node_pos (node id -> position, may be NULL); entries outside the band set *band_overflow. */
+ * node order node_pos (node id -> position, may be NULL); entries outside the band set bit 0 of *band_overflow.
+ * fx_shift >= 0: A and g are int64 FIXED-POINT arrays (multiples of 2^-fx_shift, 2^-fx_gshift) added with integer atomics:
+ * the sums are independent of the order of arrival (bitwise reproducible); sb_band_from_fixed converts; an addend outside
+ * +-2^(62-shift) sets bit 1 of *band_overflow.  fx_shift < 0: f64 atomics (results vary ~1e-9 from run to run). */
 int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
                      const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
                      const float* nmap, int H, int W, const double* intr, double lambda, double* A, int lda,
-                     int bw, const int* node_pos, int* band_overflow, double* g, double* loss_cur, void* stream);
+                     int bw, const int* node_pos, int* band_overflow, double* g, double* loss_cur, int fx_shift,
+                     int fx_gshift, void* stream);
 
 /* DataLoss.forward(grad=False): /root/reference/super/loss.py:222-248,289-290.  partials[b] = sum of r^2
  * over the surfels of block b (n_partials == sb_data_loss_blocks(n_cap)); deterministic. */
@@ -169,7 +226,24 @@ int sb_lm_begin(void* state, double* beta, double* best, int J, double u, double
  * With A != NULL adds J^T J (lower) and -J^T r; always adds sum r^2 to loss_arap_rot[0..1] if non-NULL. */
 int sb_reg_terms(const double* ed_points, const int* ed_knn, const double* beta, int J, double lam_arap,
                  double lam_rot, int use_arap, int use_rot, double* A, int lda, int bw, const int* node_pos,
-                 int* band_overflow, double* g, double* loss_arap_rot, void* stream);
+                 int* band_overflow, double* g, double* loss_arap_rot, int fx_shift, int fx_gshift, void* stream);
+
+/* int64 fixed-point store (AB | g, as sb_data_term_jtj / sb_reg_terms fill it with fx_shift >= 0) -> the f64 band AB (n,ldab)
+ * and right-hand side g (n) the solver takes. */
+int sb_band_from_fixed(const long long* store, int n, int ldab, int fx_shift, int fx_gshift, double* AB, double* g,
+                       void* stream);
+
+/* LM_Solver.LM, the whole loop of one frame: /root/reference/super/LM.py:81-122 (prepareCostTerm :53-79, Solver :38-51)
+ * over DataLoss / ARAPLoss / RotLoss (/root/reference/super/loss.py:207-499), band path.  Enqueues
+ * 1 + 7*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
+ * result and the controller state the per-iteration trace (sb_lm_state_offsets).  A failed factorisation stops the
+ * updates and leaves the last accepted beta (LM.py:99-103).  Bitwise reproducible. */
+int sb_lm_frame_partials(int n_cap);
+/* CUDA events for timing launches inside sb_lm_frame on the stream they run on (bench.py's roofline) */
+int sb_event_create(void** ev);
+int sb_event_destroy(void* ev);
+int sb_event_elapsed_ms(void* ev_begin, void* ev_end, float* ms);   /* synchronises on ev_end */
+int sb_lm_frame(const SbLMFrame* f, void* stream);
 
 /* jtj[diag] += u: /root/reference/super/LM.py:97 */
 int sb_lm_damp(const void* state, double* A, int lda, int n, void* stream);
@@ -179,33 +253,23 @@ int sb_lm_step(void* state, const int* info, double* beta, const double* delta, 
                void* stream);
 
 /* Banded Cholesky solve of (A + u I) x = g replacing torch.linalg.cholesky + cholesky_solve:
- * /root/reference/super/LM.py:38-51,97-100.  AB (n, ldab) lower band row-major (overwritten by L), g (n) rhs in /
- * solution out, u device scalar (NULL = 0), dinv (n) scratch, *info set to 1 on a non-positive pivot.
- * One launch on one thread-block cluster of `cluster_size` CTAs (1,2,4,8 or 16). */
-/* v2: same contract, pipelined (one CTA runs the pivot chain, one the forward substitution, the others the
- * panel rows and trailing updates, synchronised by release/acquire flags).  The factor L is written OUT OF PLACE
- * into the workspace (AB keeps the updated, unfactored tiles); workspace >= sb_band2_workspace_bytes2(n, ldab);
- * cluster_size 3..16. */
-long long sb_band2_workspace_bytes2(int n, int ldab);
-int sb_band_solve2(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
-                   void* workspace, long long ws_bytes, int cluster_size, void* stream);
-int sb_band2_debug(int flags);
-int sb_band2_fits(int n, int bw);
-/* v3: same contract as v2 (pivot-chain CTA + substitution CTA + update CTAs, release/acquire counters), with every
- * 32x32 triangular solve replaced by an FP64 tensor-core product with the explicit inverse of the diagonal factor
- * and a push-style back substitution.  AB keeps the updated, unfactored tiles; L and the inverses live in the
- * workspace (>= sb_band3_workspace_bytes(n, bw)); n_ctas >= 3 CTAs of one cooperative grid (clamped to the SM count). */
+ * /root/reference/super/LM.py:38-51,97-100.  AB (n, ldab) lower band row-major (overwritten with updated, unfactored tiles),
+ * g (n) rhs in / solution out, u device scalar (NULL = 0), dinv (n) scratch, *info set to 1 on a non-positive pivot.
+ *
+ * sb_band_solve3: one cooperative grid of n_ctas >= 3 CTAs (clamped to the SM count) -- a pivot-chain CTA, a substitution
+ * CTA and update CTAs synchronised by release/acquire counters; every 32x32 triangular solve is an FP64 tensor-core
+ * product with the explicit inverse of the diagonal factor; push-style back substitution.  L and the inverses live in the
+ * workspace (>= sb_band3_workspace_bytes(n, bw)).  sb_band3_update_role: 1 = one trailing tile per CTA and panel,
+ * 2 = fixed tile owners (bands too wide for role 1 on n_ctas CTAs). */
 long long sb_band3_workspace_bytes(int n, int bw);
 int sb_band3_fits(int n, int bw);
-int sb_band3_debug(int flags); /* timing experiments only: 1 no trailing update, 2 no back substitution, 4 cycle counters */
-long long sb_band3_prof_offset(int n, int bw);
+int sb_band3_update_role(int n, int bw, int n_ctas);
 int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                    void* workspace, long long ws_bytes, int n_ctas, void* stream);
 /* v4 = v3's pipeline run from BOTH ends of the band at once (two partial factorisations: top-down on the matrix, bottom-up on a
  * reversed copy), the middle block (>= bw rows) solved last, two concurrent back substitutions outwards: the pivot chain --
  * the solve's critical path -- is n/2 + bw/2 long instead of n.  Falls back to v3 for systems too small to split. */
 long long sb_band4_workspace_bytes(int n, int bw, int ldab);
-int sb_band4_stage_ms(float* out5); /* timing experiments (sb_band3_debug flag 256): ms of the 5 stages of the last sb_band_solve4 */
 int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                    void* workspace, long long ws_bytes, int n_ctas, void* stream);
 /* the same solve with the LM step (sb_lm_step's contract, /root/reference/super/LM.py:99-105) folded into its last kernel:
@@ -214,10 +278,16 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
 int sb_band_solve4_step(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                         void* workspace, long long ws_bytes, int n_ctas, int* lm_failed, double* beta,
                         const int* pos_node, void* stream);
-int sb_band_max_bw(void);
-int sb_band_debug(int flags); /* timing experiments only: 1 skip trailing update, 2 skip back-substitution, 4 skip panel math */
-int sb_band_solve(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
-                  int cluster_size, void* stream);
+int sb_band_max_bw(void);     /* widest half bandwidth the band solver takes */
+
+#ifdef SB_DEBUG_EXPORTS
+/* Timing experiments only (scripts/one_band4.py, scripts/probe_band3.py): built with SB_DEBUG_EXPORTS=1 python -m
+ * super_b200.build; NOT part of the product library.  Process-global flags: 1 no trailing update, 2 no back substitution,
+ * 4 cycle counters, 64 force update role 2, 256 stage events. */
+int sb_band3_debug(int flags);
+long long sb_band3_prof_offset(int n, int bw);
+int sb_band4_stage_ms(float* out5); /* ms of the 5 stages of the last sb_band_solve4 (flag 256) */
+#endif
 
 /* loss < minimal_loss ? accept : reject with u /= v | u *= v: /root/reference/super/LM.py:107-117 */
 int sb_lm_decide(void* state, const double* partials, int n_partials, double* loss_arap_rot, double* beta,

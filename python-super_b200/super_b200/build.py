@@ -38,13 +38,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("SB_DEBUG_EXPORTS") == "1":       # timing experiments (scripts/one_band4.py ...): not the product build
+        flags.append("-DSB_DEBUG_EXPORTS")
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc, *flags, "-I", CSRC, "-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

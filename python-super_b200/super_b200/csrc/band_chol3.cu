@@ -1324,6 +1324,8 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Arg
         return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_poison;                                 // a poll of the chain timed out (time slicing, a debugger): report it
+    if (tid == 0) s_poison = 0;
     const bool prof = (a.debug & 1024) && top && rank == 0 && tid == 0;
     if (prof) { a.prof[56] = clock64(); for (int d = 0; d < BS4_MAXWB; ++d) a.prof[70 + d] = 0; }
     const int NP = a.NP, WB = a.WB, ke = a.ke, ke32 = NB * ke;
@@ -1450,6 +1452,7 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Arg
             if (lane == 0) mbar_arrive(smem_u32(empty + stage));
             if (prof && k == ke) a.prof[60] = clock64();
         }
+        if (poisoned) s_poison = 1;
         if (prof) { a.prof[58] = clock64(); for (int q5 = 0; q5 < 3; ++q5) a.prof[64 + q5] = tacc[q5]; }
 #undef BS4PROF
     } else if (rank == 0 && warp == 3) {
@@ -1509,7 +1512,13 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Arg
     __syncthreads();
     if (prof) a.prof[59] = clock64();
     if (rank == 0) {
-        const bool do_step = step.beta && !(step.failed && *(const volatile int*)step.failed != 0);
+        // a timed-out poll means x is garbage: no step, *info = 2 and the LM failure flag, so that the caller sees it
+        const bool timed_out = s_poison != 0;
+        if (timed_out && tid == 0) {
+            *a.info = 2;
+            if (step.failed) *step.failed = 1;
+        }
+        const bool do_step = step.beta && !timed_out && !(step.failed && *(const volatile int*)step.failed != 0);
         const int rows = top ? a.n : ke32;                   // top: rows [0, 32 m + Lm); bottom: rows [32 m + Lm, n), un-reversed
         for (int i = tid; i < rows; i += THREADS) {
             const int gi = top ? i : t.n - 1 - i;
@@ -1564,22 +1573,61 @@ long long ws_bytes3(int n, int bw) {
     return (NP * (WB > 0 ? WB : 1) + NP) * (long long)T32 * (long long)sizeof(double) + ((4 * NP * (long long)sizeof(int) + 255) & ~255LL) + 256 + 1024;
 }
 
-int g_debug3 = 0;
+#ifdef SB_DEBUG_EXPORTS
+int g_debug3 = 0;            // timing experiments only; the product build has no mutable globals
 cudaEvent_t g_ev4[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage stamps of sb_band_solve4 (debug & 256)
 inline void stamp4(int i, cudaStream_t st) {
     if (!(g_debug3 & 256)) return;
     if (!g_ev4[i]) cudaEventCreate(&g_ev4[i]);
     cudaEventRecord(g_ev4[i], st);
 }
+#else
+constexpr int g_debug3 = 0;
+inline void stamp4(int, cudaStream_t) {}
+#endif
+
+// Per-device launch configuration (SM count; largest dynamic shared memory opted in per kernel): cudaFuncSetAttribute and
+// the co-residency bound are properties of the DEVICE the call runs on, so they are cached per device ordinal.
+struct DevConf { int sms; size_t smem_single, smem_dual, smem_back2, smem_back3, smem_back4; };
+DevConf* dev_conf() {
+    static DevConf conf[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (conf[dev].sms == 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        conf[dev].sms = sms;
+    }
+    return &conf[dev];
+}
+template <typename K>
+bool opt_in_smem(K kernel, size_t smem, size_t& configured) {
+    if (smem <= configured) return true;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return false;
+    configured = smem;
+    return true;
+}
 
 }  // namespace
 
 extern "C" {
 
+#ifdef SB_DEBUG_EXPORTS
 int sb_band3_debug(int flags) { g_debug3 = flags; return SB_OK; }
 
 /* byte offset of the 32 cycle counters inside the workspace (debug flag 4) */
 long long sb_band3_prof_offset(int n, int bw) { return ws_bytes3(n, bw) - 1024; }
+#endif
+
+int sb_band_max_bw(void) { return MAX_WB3 * NB; }
+
+int sb_band3_update_role(int n, int bw, int n_ctas) {
+    const int NP = (n + NB - 1) / NB;
+    int WB = (bw + NB - 1) / NB;
+    if (WB > NP - 1) WB = NP - 1 > 0 ? NP - 1 : 0;
+    return (WB * (WB + 1) / 2 - 1 > n_ctas - 2 || (g_debug3 & 64)) ? 2 : 1;
+}
 
 int sb_band3_fits(int n, int bw) {
     return (n > 0 && bw >= 0 && (bw + NB - 1) / NB <= MAX_WB3 && smem_bytes3(n) <= 227 * 1024) ? 1 : 0;
@@ -1593,21 +1641,11 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
     if (n_ctas < 3) return SB_ERR_ARG;
     if (!sb_band3_fits(n, bw)) return SB_ERR_ARG;
     if (ws_bytes < ws_bytes3(n, bw)) return SB_ERR_WORKSPACE;
-    static int max_ctas = 0;
-    static size_t configured = 0;
+    DevConf* dc = dev_conf();
+    if (!dc) return SB_ERR_CUDA;
     const size_t smem = smem_bytes3(n);
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(band_chol3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return SB_ERR_CUDA;
-        configured = smem;
-    }
-    if (max_ctas == 0) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        max_ctas = sms;            // 1 CTA per SM (launch bounds): the cooperative launch checks co-residency
-    }
-    if (n_ctas > max_ctas) n_ctas = max_ctas;
+    if (!opt_in_smem(band_chol3_kernel, smem, dc->smem_single)) return SB_ERR_CUDA;
+    if (n_ctas > dc->sms) n_ctas = dc->sms;   // 1 CTA per SM (launch bounds): the cooperative launch checks co-residency
     Args3 a;
     a.AB = AB; a.ldab = ldab; a.n = n; a.bw = bw; a.g = g; a.u = u; a.dinv = dinv; a.info = info;
     a.NP = (n + NB - 1) / NB;
@@ -1685,14 +1723,9 @@ static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const dou
     }
     if (ws_bytes < sb_band4_workspace_bytes(n, bw, ldab)) return SB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    static int max_ctas = 0;
-    if (max_ctas == 0) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        max_ctas = sms;
-    }
-    if (n_ctas > max_ctas) n_ctas = max_ctas;
+    DevConf* dc = dev_conf();
+    if (!dc) return SB_ERR_CUDA;
+    if (n_ctas > dc->sms) n_ctas = dc->sms;
     TwoSided t;
     t.n = n; t.bw = bw; t.ldab = ldab; t.m32 = 32 * m; t.Lm = n - 64 * m; t.nB = n - 32 * m;
     const int nA = t.m32 + t.Lm, bwm = bw < t.Lm - 1 ? bw : t.Lm - 1;
@@ -1718,20 +1751,10 @@ static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const dou
     t.flags = flags4; t.nflags = 4 * (aA.NP + aB.NP + aM.NP);
     size_t smem = smem_bytes3(nA);
     if (smem_bytes3(t.Lm) > smem) smem = smem_bytes3(t.Lm);
-    static size_t conf_dual = 0, conf_single = 0, conf_back = 0;
-    if (smem > conf_dual) {
-        if (cudaFuncSetAttribute(band_chol3_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SB_ERR_CUDA;
-        conf_dual = smem;
-    }
-    if (smem > conf_single) {
-        if (cudaFuncSetAttribute(band_chol3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SB_ERR_CUDA;
-        conf_single = smem;
-    }
+    if (!opt_in_smem(band_chol3_dual_kernel, smem, dc->smem_dual)) return SB_ERR_CUDA;
+    if (!opt_in_smem(band_chol3_kernel, smem, dc->smem_single)) return SB_ERR_CUDA;
     const size_t smem_back = (size_t)aA.NP * NB * sizeof(double);
-    if (smem_back > conf_back && smem_back > 48 * 1024) {
-        if (cudaFuncSetAttribute(band_backsub2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_back) != cudaSuccess) return SB_ERR_CUDA;
-        conf_back = smem_back;
-    }
+    if (!opt_in_smem(band_backsub2_kernel, smem_back, dc->smem_back2)) return SB_ERR_CUDA;
     // 1. reversed copy of the bottom part
     stamp4(0, st);
     band_reverse_kernel<<<(t.nB * ldab + 255) / 256, 256, 0, st>>>(AB, g, AB2, g2, t);
@@ -1758,11 +1781,7 @@ static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const dou
     const size_t smem_b3 = smem_backsub3(aA.NP, aA.WB);
     const Bs4Layout L4 = bs4_layout(aA.NP, aA.WB, aA.ke);
     if (aA.WB <= BS4_MAXWB && aA.WB >= 1 && L4.stages >= 2 && !(g_debug3 & (128 | 512))) {
-        static size_t conf_b4 = 0;
-        if (L4.total > conf_b4) {
-            if (cudaFuncSetAttribute(band_backsub4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L4.total) != cudaSuccess) return SB_ERR_CUDA;
-            conf_b4 = L4.total;
-        }
+        if (!opt_in_smem(band_backsub4_kernel, (size_t)L4.total, dc->smem_back4)) return SB_ERR_CUDA;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * BS4_C);
         cfg.blockDim = dim3(THREADS);
@@ -1778,11 +1797,7 @@ static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const dou
         if (cudaLaunchKernelEx(&cfg, band_backsub4_kernel, aA, aB, (const double*)gm, g, t, L4, step) != cudaSuccess) return SB_ERR_CUDA;
         step.beta = nullptr;     // folded in
     } else if (smem_b3 <= 227 * 1024 && !(g_debug3 & 128)) {
-        static size_t conf_b3 = 0;
-        if (smem_b3 > conf_b3) {
-            if (cudaFuncSetAttribute(band_backsub3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b3) != cudaSuccess) return SB_ERR_CUDA;
-            conf_b3 = smem_b3;
-        }
+        if (!opt_in_smem(band_backsub3_kernel, smem_b3, dc->smem_back3)) return SB_ERR_CUDA;
         band_backsub3_kernel<<<2, THREADS, smem_b3, st>>>(aA, aB, gm, g, t);
     } else {
         band_backsub2_kernel<<<2, THREADS, smem_back, st>>>(aA, aB, gm, g, t);
@@ -1805,6 +1820,7 @@ int sb_band_solve4_step(double* AB, int ldab, int n, int bw, double* g, const do
     return solve4_impl(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream, StepArgs{lm_failed, beta, pos_node});
 }
 
+#ifdef SB_DEBUG_EXPORTS
 /* timing experiments (sb_band3_debug flag 256): milliseconds of the five stages of the last sb_band_solve4 --
    reverse | both ends | combine + flag memset | middle | back substitution.  Synchronises. */
 int sb_band4_stage_ms(float* out5) {
@@ -1814,5 +1830,6 @@ int sb_band4_stage_ms(float* out5) {
         if (cudaEventElapsedTime(out5 + i, g_ev4[i], g_ev4[i + 1]) != cudaSuccess) return SB_ERR_CUDA;
     return SB_OK;
 }
+#endif
 
 }  // extern "C"

@@ -83,22 +83,41 @@ __device__ __forceinline__ int n_active(int n_cap, const int* n_dev) {
 
 // Lower-triangular normal-equation matrix, dense (bw < 0: A[row*lda + col]) or band
 // (A[row*lda + col - row + bw], entries with row - col > bw raise *overflow), with an optional node
-// permutation (node id -> position in the solver's ordering).
+// permutation (node id -> position in the solver's ordering), and the right-hand side g beside it.
+//
+// Accumulation mode.  shift < 0: f64 atomics (order of arrival decides the last bits: run-to-run differences ~1e-9 on
+// J^T J -- kept for the dense cross-check path).  shift >= 0: FIXED POINT -- A and g are int64 arrays, every addend is
+// rounded once to a multiple of 2^-shift (2^-gshift for g) and added with an integer atomic.  Integer addition is
+// associative, so the sums do not depend on the order in which the warps arrive: the normal equations, hence the whole
+// tracker, are bitwise reproducible.  Resolution 2^-40 = 9.1e-13 absolute on entries of magnitude 1e2..1e4 (below the
+// f64 rounding of such an entry above 8192), range +-2^(62-shift); an addend beyond the range sets bit 1 of *overflow.
 struct MatView {
     double* A;
     int lda, bw;
     const int* node_pos;
     int* overflow;
+    double* g;
+    int shift, gshift;       // fixed-point exponents, or -1
     __device__ __forceinline__ int pos(int node) const { return node_pos ? node_pos[node] : node; }
-    __device__ __forceinline__ void add(int row, int col, double v) const {   // requires row >= col
-        if (bw < 0) {
-            atomicAdd(A + (size_t)row * lda + col, v);
-        } else if (row - col <= bw) {
-            atomicAdd(A + (size_t)row * lda + (col - row + bw), v);
+    __device__ __forceinline__ void put(double* p, double v, int sh) const {
+        if (sh < 0) {
+            atomicAdd(p, v);
         } else {
-            *overflow = 1;
+            const double sv = scalbn(v, sh);
+            if (!(fabs(sv) < 4.6e18)) { atomicOr(overflow, 2); return; }
+            atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double2ll_rn(sv));
         }
     }
+    __device__ __forceinline__ void add(int row, int col, double v) const {   // requires row >= col
+        if (bw < 0) {
+            put(A + (size_t)row * lda + col, v, shift);
+        } else if (row - col <= bw) {
+            put(A + (size_t)row * lda + (col - row + bw), v, shift);
+        } else {
+            atomicOr(overflow, 1);
+        }
+    }
+    __device__ __forceinline__ void add_g(int i, double v) const { put(g + i, v, gshift); }
 };
 
 // ---- block-wide deterministic sum (fixed tree), result valid in thread 0 -----------------------

@@ -15,6 +15,8 @@
 // Jacobian, no SpGEMM.
 #include "common.cuh"
 #include "lm_state.cuh"
+#include "reg_terms.cuh"
+#include "internal.h"
 #include "super_b200.h"
 
 namespace {
@@ -201,7 +203,7 @@ __device__ __forceinline__ void build_flush_table(unsigned short* tab, int tid, 
 }
 
 __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, const MatView& M,
-                                          double* g, double* loss_cur, double* __restrict__ St,
+                                          double* loss_cur, double& warp_loss, double* __restrict__ St,
                                           const unsigned short* __restrict__ tab) {
     int t = 0;
 #pragma unroll
@@ -229,8 +231,8 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
         const int km = tb & 7, cm = (tb >> 3) & 7, kn = (tb >> 6) & 7, cn = (tb >> 9) & 7;
         const int pm = km == 0 ? p0 : km == 1 ? p1 : km == 2 ? p2 : p3;
         if (kn == 4) {                       // column 28: -J^T r, and r^T r in the corner
-            if (km == 4) { if (loss_cur) atomicAdd(loss_cur, val); }
-            else atomicAdd(g + 7 * pm + cm, -val);
+            if (km == 4) { warp_loss += val; if (loss_cur) atomicAdd(loss_cur, val); }   // entry 434: always lane 18
+            else M.add_g(7 * pm + cm, -val);
             continue;
         }
         const int pn = kn == 0 ? p0 : kn == 1 ? p1 : kn == 2 ? p2 : p3;
@@ -240,78 +242,133 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
     __syncwarp();
 }
 
+// Extras of the frame loop (sb_lm_frame, lm_frame.cu): the pass assembles into the fixed-point store that is NOT the
+// current one, the trailing blocks of the grid assemble the ARAP / Rot terms into the same store, every J^T J warp
+// delivers its own sum of r^2, and the block that draws the last ticket sums them in index order, adds the regularisers'
+// losses and takes the LM decision for the beta this pass was evaluated at.
+struct FrameFuse {
+    double* store[2];     // (AB | g) as int64 fixed point; target = store[1 - st->sel]
+    long long g_off;      // elements from the start of a store to its g
+    LMState* st;
+    double* partials;     // >= JTJ_WARPS * (J^T J blocks) doubles
+    int n_reg_blocks;
+    RegArgs reg;
+    double* beta; double* best;
+    int adopt;            // prologue: adopt the system, no decision
+};
+
+// the two rarely-taken parts of the fused pass, kept out of line so that their registers and local arrays do not weigh on
+// the surfel loop (inlined they cost it 450 bytes of spills)
+__device__ __noinline__ void fused_reg_block(const FrameFuse& f, const MatView& M, int tid) {
+    double la, lr;
+    reg_terms_item(f.reg, tid, M, true, la, lr);
+}
+__device__ __noinline__ void fused_decide(const FrameFuse& f, int n_partials) {
+    const RegLossArgs rg{f.reg.ed_points, f.reg.ed_knn, f.reg.J, f.reg.lam_arap, f.reg.lam_rot, f.reg.use_arap,
+                         f.reg.use_rot};
+    lm_decide_body<JTJ_WARPS * 32>(f.st, f.partials, n_partials, nullptr, f.beta, f.best, 7 * f.reg.J, rg, true,
+                                   f.adopt != 0);
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
-data_jtj_kernel(DataArgs a, MatView M, double* __restrict__ g, double* loss_cur) {
+data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, FrameFuse f) {
     extern __shared__ double smem[];
     __shared__ unsigned short fl_tab[448];
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
-    double* St = Jt + JT_DOUBLES;
-    for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
-    build_flush_table(fl_tab, threadIdx.x, JTJ_WARPS * 32);
-    __syncthreads();
+    int jtj_blocks = gridDim.x;
+    if (FUSED) {
+        M.A = f.store[1 - f.st->sel];
+        M.g = M.A + f.g_off;
+        jtj_blocks -= f.n_reg_blocks;
+    }
+    if (!FUSED || (int)blockIdx.x < jtj_blocks) {
+        double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
+        double* St = Jt + JT_DOUBLES;
+        for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
+        build_flush_table(fl_tab, threadIdx.x, JTJ_WARPS * 32);
+        __syncthreads();
 
-    const int n = n_active(a.n_cap, a.n_dev);
-    const int n_chunks = (n + 31) >> 5;
-    const int total_warps = gridDim.x * JTJ_WARPS;
-    const int gw = blockIdx.x * JTJ_WARPS + warp;
-    const int per = (n_chunks + total_warps - 1) / total_warps;
-    const int c0 = gw * per, c1 = min(n_chunks, c0 + per);
+        const int n = n_active(a.n_cap, a.n_dev);
+        const int n_chunks = (n + 31) >> 5;
+        const int total_warps = jtj_blocks * JTJ_WARPS;
+        const int gw = blockIdx.x * JTJ_WARPS + warp;
+        const int per = (n_chunks + total_warps - 1) / total_warps;
+        const int c0 = gw * per, c1 = min(n_chunks, c0 + per);
 
-    double acc[10][2];
+        double acc[10][2];
 #pragma unroll
-    for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
-    unsigned long long acc_key = 0;
-    bool have = false;
+        for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
+        unsigned long long acc_key = 0;
+        bool have = false;
+        double warp_loss = 0.0;      // sum of r^2 over this warp's surfels, in flush order (held by lane 18)
 
-    // one extra "tail" pass with a sentinel key flushes the last accumulator through the same code as a tuple
-    // change inside the loop (a single inlined copy of the flush)
-    for (int c = c0; c <= c1; ++c) {
-        const bool tail = (c == c1);
-        const int slot = c * 32 + lane;
-        Eval ev;
-        bool matched = false;
-        if (!tail && slot < n) {
-            const int sid = a.order ? a.order[slot] : slot;
-            matched = eval_surfel<true, true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
-        }
-        if (matched) {
-            Jt[28 * JT_STRIDE + lane] = ev.r;
-        } else if (!tail) {
-#pragma unroll
-            for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
-        }
-        __syncwarp();
-        const unsigned long long key = matched ? pack_key(ev.idx) : ~0ull;
-        unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
-        while (remaining) {
-            const int leader = __ffs(remaining) - 1;
-            const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
-            const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
-            if (!have || k != acc_key) {
-                if (have) flush_acc(acc, acc_key, lane, M, g, loss_cur, St, fl_tab);
-                acc_key = k;
-                have = !tail;
+        // one extra "tail" pass with a sentinel key flushes the last accumulator through the same code as a tuple
+        // change inside the loop (a single inlined copy of the flush)
+        for (int c = c0; c <= c1; ++c) {
+            const bool tail = (c == c1);
+            const int slot = c * 32 + lane;
+            Eval ev;
+            bool matched = false;
+            if (!tail && slot < n) {
+                const int sid = a.order ? a.order[slot] : slot;
+                matched = eval_surfel<true, true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
             }
+            if (matched) {
+                Jt[28 * JT_STRIDE + lane] = ev.r;
+            } else if (!tail) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const unsigned m4 = (m >> (4 * ks)) & 0xfu;
-                if (m4 == 0u) continue;   // warp-uniform
-                // rows of other tuples in this k-step are masked out (1.0 / 0.0 factor)
-                const double keep = ((m4 >> (lane & 3)) & 1u) ? 1.0 : 0.0;
-                double x[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    x[t] = keep * Jt[(8 * t + (lane >> 2)) * JT_STRIDE + 4 * ks + (lane & 3)];
-                int t = 0;
-#pragma unroll
-                for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-                    for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], x[ti], x[tj]);
+                for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
             }
-            remaining = tail ? 0u : (remaining & ~m);
+            __syncwarp();
+            const unsigned long long key = matched ? pack_key(ev.idx) : ~0ull;
+            unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
+            while (remaining) {
+                const int leader = __ffs(remaining) - 1;
+                const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
+                const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
+                if (!have || k != acc_key) {
+                    if (have) flush_acc(acc, acc_key, lane, M, loss_cur, warp_loss, St, fl_tab);
+                    acc_key = k;
+                    have = !tail;
+                }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const unsigned m4 = (m >> (4 * ks)) & 0xfu;
+                    if (m4 == 0u) continue;   // warp-uniform
+                    // rows of other tuples in this k-step are masked out (1.0 / 0.0 factor)
+                    const double keep = ((m4 >> (lane & 3)) & 1u) ? 1.0 : 0.0;
+                    double x[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        x[t] = keep * Jt[(8 * t + (lane >> 2)) * JT_STRIDE + 4 * ks + (lane & 3)];
+                    int t = 0;
+#pragma unroll
+                    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                        for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], x[ti], x[tj]);
+                }
+                remaining = tail ? 0u : (remaining & ~m);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        if (FUSED && lane == 18) f.partials[gw] = warp_loss;
+    } else {
+        fused_reg_block(f, M, ((int)blockIdx.x - jtj_blocks) * (JTJ_WARPS * 32) + threadIdx.x);
+    }
+    if (FUSED) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int ticket = atomicAdd(&f.st->ticket, 1u);
+            s_last = ticket == gridDim.x - 1;
+            if (s_last) f.st->ticket = 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        fused_decide(f, jtj_blocks * JTJ_WARPS);
     }
 }
 
@@ -424,6 +481,24 @@ DataArgs make_args(const double* points, const int* knn_idx, const double* knn_w
 
 }  // namespace
 
+// One resident wave of the J^T J kernel on the current device (a partial second wave was a 40 % tail, ncu r1), and the
+// kernel's shared-memory opt-in: both are per DEVICE, so the cache is indexed by the device ordinal.
+template <bool FUSED>
+static int jtj_resident(size_t smem) {
+    static int resident[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (resident[dev] == 0) {
+        int per_sm = 0, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(data_jtj_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_jtj_kernel<FUSED>, JTJ_WARPS * 32, smem);
+        resident[dev] = (per_sm > 0 ? per_sm : 1) * sms;
+    }
+    return resident[dev];
+}
+
 extern "C" {
 
 int sb_data_loss_blocks(int n_cap) {
@@ -444,32 +519,27 @@ int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* ke
 int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
                      const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
                      const float* nmap, int H, int W, const double* intr, double lambda, double* A, int lda,
-                     int bw, const int* node_pos, int* band_overflow, double* g, double* loss_cur, void* stream) {
+                     int bw, const int* node_pos, int* band_overflow, double* g, double* loss_cur, int fx_shift,
+                     int fx_gshift, void* stream) {
     if (!points || !knn_idx || !knn_w || !ed_points || !beta || !vmap || !nmap || !A || !g) return SB_ERR_ARG;
     if (J <= 0 || J > 65535) return SB_ERR_ARG;
     if (bw < 0 ? lda < 7 * J : (lda < bw + 1 || !band_overflow)) return SB_ERR_ARG;
+    if (fx_shift >= 0 && (!band_overflow || fx_gshift < 0 || fx_shift > 60 || fx_gshift > 60)) return SB_ERR_ARG;
     MatView M;
-    M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow;
+    M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow; M.g = g;
+    M.shift = fx_shift >= 0 ? fx_shift : -1; M.gshift = fx_shift >= 0 ? fx_gshift : -1;
     if (n_cap <= 0) return SB_OK;
     DataArgs a = make_args(points, knn_idx, knn_w, order, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
                            intr, lambda);
     const int n_chunks = (n_cap + 31) / 32;
     const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
-    // exactly one wave: resident CTAs per SM x SM count (a partial second wave was a 40% tail, ncu r1)
-    static int resident = 0;
-    if (resident == 0) {
-        int per_sm = 0, dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(data_jtj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return SB_ERR_CUDA;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_jtj_kernel, JTJ_WARPS * 32, smem);
-        resident = (per_sm > 0 ? per_sm : 1) * sms;
-    }
+    const int resident = jtj_resident<false>(smem);
+    if (resident <= 0) return SB_ERR_CUDA;
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, g, loss_cur);
+    FrameFuse none{};
+    data_jtj_kernel<false><<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, loss_cur, none);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -519,3 +589,45 @@ int sb_data_term_rows(const double* points, const int* knn_idx, const double* kn
 }
 
 }  // extern "C"
+
+// ---- frame loop (lm_frame.cu) ---------------------------------------------------------------------------------
+namespace sbi {
+
+int jtj_fused_partials(int n_cap) {      // upper bound on the per-warp partials a fused pass writes (any device)
+    (void)n_cap;
+    return JTJ_WARPS * 4 * 256;          // <= 4 CTAs per SM (launch bounds), <= 256 SMs
+}
+
+int launch_jtj_fused(const SbLMFrame* f, int adopt, cudaStream_t st) {
+    MatView M;
+    M.A = nullptr; M.g = nullptr;        // chosen in the kernel from the device-resident selector
+    M.lda = f->ldab; M.bw = f->bw; M.node_pos = f->node_pos; M.overflow = f->band_overflow;
+    M.shift = f->fx_shift; M.gshift = f->fx_gshift;
+    DataArgs a = make_args(f->points, f->knn_idx, f->knn_w, f->order, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
+                           f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data);
+    FrameFuse ff;
+    ff.store[0] = reinterpret_cast<double*>(f->fx_store[0]);
+    ff.store[1] = reinterpret_cast<double*>(f->fx_store[1]);
+    ff.g_off = (long long)f->n * f->ldab;
+    ff.st = (LMState*)f->state;
+    ff.partials = f->partials_jtj;
+    ff.reg = RegArgs{f->ed_points, f->ed_knn, f->beta, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
+    ff.beta = f->beta; ff.best = f->best;
+    ff.adopt = adopt;
+    const int reg_threads = (f->use_arap ? f->J * SB_KNN : 0) + (f->use_rot ? f->J : 0);
+    ff.n_reg_blocks = (reg_threads + JTJ_WARPS * 32 - 1) / (JTJ_WARPS * 32);
+    const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
+    const int resident = jtj_resident<true>(smem);
+    if (resident <= 0) return SB_ERR_CUDA;
+    const int n_chunks = (f->n_cap + 31) / 32;
+    int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
+    if (blocks > resident - ff.n_reg_blocks) blocks = resident - ff.n_reg_blocks;   // J^T J + regulariser blocks: one wave
+    if (blocks < 1) blocks = 1;
+    if (JTJ_WARPS * blocks > f->n_partials_jtj) return SB_ERR_WORKSPACE;
+    data_jtj_kernel<true><<<blocks + ff.n_reg_blocks, JTJ_WARPS * 32, smem, st>>>(a, M, nullptr, ff);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+}  // namespace sbi
+

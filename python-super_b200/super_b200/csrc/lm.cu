@@ -5,100 +5,17 @@
 // failure flag and the per-iteration trace live in a small device struct.
 #include "common.cuh"
 #include "lm_state.cuh"
+#include "reg_terms.cuh"
 #include "super_b200.h"
 
 namespace {
 
-__device__ __forceinline__ void add_lower(const MatView& M, int r, int c, double v) {
-    if (r >= c) M.add(r, c, v);
-    else M.add(c, r, v);
-}
-
-// d[R(q)v]/dq as 3x4 (col 0 = d/dqw, cols 1..3 = d/dqv)   (/root/reference/super/utils.py:59-69)
-__device__ __forceinline__ void quat_jac(const V3& v, double qw, const V3& qv, const V3& cp, double (&Jq)[3][4]) {
-    const double qd = dot3(qv, v);
-    const double q[3] = {qv.x, qv.y, qv.z}, vv[3] = {v.x, v.y, v.z};
-    const double sk[3][3] = {{0, -v.z, v.y}, {v.z, 0, -v.x}, {-v.y, v.x, 0}};
-    Jq[0][0] = 2.0 * cp.x; Jq[1][0] = 2.0 * cp.y; Jq[2][0] = 2.0 * cp.z;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            Jq[i][1 + j] = 2.0 * ((i == j ? qd : 0.0) + q[i] * vv[j] - 2.0 * vv[i] * q[j] - qw * sk[i][j]);
-}
-
 // One thread per (node j, neighbour slot k) for ARAP; one thread per node for Rot (threads >= J*K).
 // With A == nullptr only the loss partials are produced.
-__global__ void reg_terms_kernel(const double* __restrict__ ed_points, const int* __restrict__ ed_knn,
-                                 const double* __restrict__ beta, int J, double lam_arap, double lam_rot,
-                                 int use_arap, int use_rot, MatView M,
-                                 double* __restrict__ g, double* __restrict__ loss_arap_rot /* [2] */) {
-    double* const A = M.A;
+__global__ void reg_terms_kernel(RegArgs a, MatView M, double* __restrict__ loss_arap_rot /* [2] */) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_arap = use_arap ? J * SB_KNN : 0;
-    double la = 0.0, lr = 0.0;
-    if (tid < n_arap) {
-        const int j = tid / SB_KNN;
-        const int n = ed_knn[tid];
-        const V3 gj = v3(ed_points[3 * j], ed_points[3 * j + 1], ed_points[3 * j + 2]);
-        const V3 gn = v3(ed_points[3 * n], ed_points[3 * n + 1], ed_points[3 * n + 2]);
-        const V3 d = v3(gj.x - gn.x, gj.y - gn.y, gj.z - gn.z);
-        const double* bn = beta + 7 * n;
-        const double* bj = beta + 7 * j;
-        const V3 qv = v3(bn[1], bn[2], bn[3]);
-        V3 cp;
-        V3 tv = quat_rot_ref(d, bn[0], qv, cp);
-        // r = lam [ (R(q_n) d + b_n) - (d + b_j) ]        (loss.py:433-437)
-        const double r[3] = {lam_arap * ((tv.x + bn[4]) - (d.x + bj[4])), lam_arap * ((tv.y + bn[5]) - (d.y + bj[5])),
-                             lam_arap * ((tv.z + bn[6]) - (d.z + bj[6]))};
-        la = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-        if (A) {
-            double Jq[3][4];
-            quat_jac(d, bn[0], qv, cp, Jq);
-            // residual row c: cols 7n+{0..3} = lam*Jq[c][.], 7n+4+c = lam, 7j+4+c = -lam   (loss.py:418-451)
-            const int bn0 = 7 * M.pos(n), bj0 = 7 * M.pos(j);
-            const double l = lam_arap, l2 = lam_arap * lam_arap;
-            for (int a = 0; a < 4; ++a) {
-                for (int b = 0; b <= a; ++b) {
-                    double s = 0.0;
-                    for (int c = 0; c < 3; ++c) s += Jq[c][a] * Jq[c][b];
-                    M.add(bn0 + a, bn0 + b, l2 * s);
-                }
-                double gq = 0.0;
-                for (int c = 0; c < 3; ++c) {
-                    add_lower(M, bn0 + 4 + c, bn0 + a, l2 * Jq[c][a]);     // q_n x b_n
-                    add_lower(M, bj0 + 4 + c, bn0 + a, -l2 * Jq[c][a]);    // q_n x b_j
-                    gq += l * Jq[c][a] * r[c];
-                }
-                atomicAdd(g + bn0 + a, -gq);
-            }
-            for (int c = 0; c < 3; ++c) {
-                M.add(bn0 + 4 + c, bn0 + 4 + c, l2);
-                M.add(bj0 + 4 + c, bj0 + 4 + c, l2);
-                add_lower(M, bj0 + 4 + c, bn0 + 4 + c, -l2);
-                atomicAdd(g + bn0 + 4 + c, -l * r[c]);
-                atomicAdd(g + bj0 + 4 + c, l * r[c]);
-            }
-        }
-    } else if (use_rot && tid < n_arap + J) {
-        // RotLoss in float32 like the reference (loss.py:487-497)
-        const int j = tid - n_arap;
-        const float lam = (float)lam_rot;
-        float q[4];
-        for (int a = 0; a < 4; ++a) q[a] = (float)beta[7 * j + a];
-        const float s = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3];
-        const float r = lam * (1.f - s);
-        lr = (double)(r * r);
-        if (A) {
-            float jv[4];
-            for (int a = 0; a < 4; ++a) jv[a] = -lam * 2.f * q[a];
-            const int pj = 7 * M.pos(j);
-            for (int a = 0; a < 4; ++a) {
-                for (int b = 0; b <= a; ++b) M.add(pj + a, pj + b, (double)(jv[a] * jv[b]));
-                atomicAdd(g + pj + a, -(double)(jv[a] * r));
-            }
-        }
-    }
+    double la, lr;
+    reg_terms_item(a, tid, M, M.A != nullptr, la, lr);
     if (loss_arap_rot) {
         __shared__ double red[8];
         double s = block_sum<256>(la, red);
@@ -112,7 +29,7 @@ __global__ void lm_begin_kernel(LMState* st, double* beta, double* best, int J, 
                                 double minimal_loss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
-        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0; st->ticket = 0;
+        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0; st->ticket = 0; st->sel = 0;
     }
     if (i < 7 * J) {
         const double val = (i % 7 == 0) ? 1.0 : 0.0;
@@ -169,15 +86,17 @@ int sb_lm_begin(void* state, double* beta, double* best, int J, double u, double
 
 int sb_reg_terms(const double* ed_points, const int* ed_knn, const double* beta, int J, double lam_arap,
                  double lam_rot, int use_arap, int use_rot, double* A, int lda, int bw, const int* node_pos,
-                 int* band_overflow, double* g, double* loss_arap_rot, void* stream) {
+                 int* band_overflow, double* g, double* loss_arap_rot, int fx_shift, int fx_gshift, void* stream) {
     if (!ed_points || !ed_knn || !beta || J <= 0) return SB_ERR_ARG;
     if (A && (!g || (bw < 0 ? lda < 7 * J : (lda < bw + 1 || !band_overflow)))) return SB_ERR_ARG;
+    if (A && fx_shift >= 0 && (!band_overflow || fx_gshift < 0 || fx_shift > 60 || fx_gshift > 60)) return SB_ERR_ARG;
     MatView M;
-    M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow;
+    M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow; M.g = g;
+    M.shift = fx_shift >= 0 ? fx_shift : -1; M.gshift = fx_shift >= 0 ? fx_gshift : -1;
     const int threads = (use_arap ? J * SB_KNN : 0) + (use_rot ? J : 0);
     if (threads == 0) return SB_OK;
-    reg_terms_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        ed_points, ed_knn, beta, J, lam_arap, lam_rot, use_arap, use_rot, M, g, loss_arap_rot);
+    RegArgs ra{ed_points, ed_knn, beta, J, lam_arap, lam_rot, use_arap, use_rot};
+    reg_terms_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ra, M, loss_arap_rot);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

@@ -1,0 +1,129 @@
+// The whole LM loop of one tracked frame behind ONE C call: LM_Solver.LM (/root/reference/super/LM.py:81-122) with its
+// prepareCostTerm / Solver steps (LM.py:38-79) and the three terms of /root/reference/super/loss.py, on the band path.
+//
+// What is restructured against the reference (results unchanged):
+//   * the loss of a trial beta falls out of the J^T J pass AT that beta (sum r^2 is entry (28,28) of the Gram panels), and
+//     if the step is accepted that pass already IS the next iteration's normal equations.  So the loop is
+//         assemble(beta_0) ; repeat { solve -> beta' = beta + delta ; assemble(beta') -> loss' ; accept / reject }
+//     with one J^T J pass per iteration and no separate loss-only pass, except after the last solve where only the loss
+//     is needed.  The reference evaluates J^T J at the current beta and the loss at the trial beta in two passes per
+//     iteration (LM.py:93-107); after a rejected step it rebuilds the same J^T J again, here the kept copy is reused.
+//   * the normal equations are accumulated in 64-bit FIXED POINT (common.cuh MatView): integer atomics commute, so the
+//     assembled system is bitwise independent of the order in which warps arrive.  Two stores alternate: the current
+//     system and the one being assembled at the trial beta; LMState.sel says which is which, on the device.
+//   * band_from_fixed_kernel turns the current store into the f64 band the solver factors (the solver overwrites its
+//     input, so a copy is needed anyway) and clears the other store for the next assembly: no memset nodes, no side stream.
+// One iteration = 7 launches: from_fixed, band_reverse, band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
+// data_jtj<fused> (+ ARAP/Rot blocks + decision).  No host synchronisation, no allocation.
+#include "common.cuh"
+#include "lm_state.cuh"
+#include "internal.h"
+#include "super_b200.h"
+
+namespace {
+
+__global__ void band_from_fixed_kernel(const long long* __restrict__ s0, const long long* __restrict__ s1,
+                                       const LMState* __restrict__ st, long long n_ab, long long n_tot, double inv_scale,
+                                       double inv_gscale, double* __restrict__ AB, double* __restrict__ g, int zero_other) {
+    const int sel = st ? st->sel : 0;
+    const long long* src = sel ? s1 : s0;
+    long long* oth = const_cast<long long*>(sel ? s0 : s1);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tot; i += stride) {
+        const long long v = src[i];
+        if (i < n_ab) AB[i] = (double)v * inv_scale;          // power-of-two scale: exact
+        else g[i - n_ab] = (double)v * inv_gscale;
+        if (zero_other) oth[i] = 0;
+    }
+}
+
+int from_fixed(const long long* s0, const long long* s1, const LMState* st, int n, int ldab, int shift, int gshift,
+               double* AB, double* g, int zero_other, cudaStream_t stream) {
+    const long long n_ab = (long long)n * ldab, n_tot = n_ab + n;
+    long long blocks = (n_tot + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    band_from_fixed_kernel<<<(int)blocks, 256, 0, stream>>>(s0, s1, st, n_ab, n_tot, ldexp(1.0, -shift), ldexp(1.0, -gshift),
+                                                          AB, g, zero_other);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_band_from_fixed(const long long* store, int n, int ldab, int fx_shift, int fx_gshift, double* AB, double* g,
+                       void* stream) {
+    if (!store || !AB || !g || n <= 0 || ldab <= 0 || fx_shift < 0 || fx_gshift < 0 || fx_shift > 60 || fx_gshift > 60)
+        return SB_ERR_ARG;
+    return from_fixed(store, store, nullptr, n, ldab, fx_shift, fx_gshift, AB, g, 0, (cudaStream_t)stream);
+}
+
+int sb_lm_frame_partials(int n_cap) { return sbi::jtj_fused_partials(n_cap); }
+
+int sb_event_create(void** ev) {
+    if (!ev) return SB_ERR_ARG;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return SB_ERR_CUDA;
+    *ev = (void*)e;
+    return SB_OK;
+}
+int sb_event_destroy(void* ev) { return (ev && cudaEventDestroy((cudaEvent_t)ev) == cudaSuccess) ? SB_OK : SB_ERR_ARG; }
+int sb_event_elapsed_ms(void* ev_begin, void* ev_end, float* ms) {
+    if (!ev_begin || !ev_end || !ms) return SB_ERR_ARG;
+    if (cudaEventSynchronize((cudaEvent_t)ev_end) != cudaSuccess) return SB_ERR_CUDA;
+    return cudaEventElapsedTime(ms, (cudaEvent_t)ev_begin, (cudaEvent_t)ev_end) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st) {
+    const bool timed = f->jtj_events && 2 * k + 1 < f->n_jtj_events;
+    if (timed && cudaEventRecord((cudaEvent_t)f->jtj_events[2 * k], st) != cudaSuccess) return SB_ERR_CUDA;
+    const int rc = sbi::launch_jtj_fused(f, adopt, st);
+    if (rc != SB_OK) return rc;
+    if (timed && cudaEventRecord((cudaEvent_t)f->jtj_events[2 * k + 1], st) != cudaSuccess) return SB_ERR_CUDA;
+    return SB_OK;
+}
+
+int sb_lm_frame(const SbLMFrame* f, void* stream) {
+    if (!f || !f->points || !f->knn_idx || !f->knn_w || !f->ed_points || !f->ed_knn || !f->vmap || !f->nmap) return SB_ERR_ARG;
+    if (!f->state || !f->beta || !f->best || !f->partials_jtj || !f->partials_loss) return SB_ERR_ARG;
+    if (!f->fx_store[0] || !f->fx_store[1] || !f->AB || !f->g || !f->band_overflow || !f->dinv || !f->info || !f->solver_ws)
+        return SB_ERR_ARG;
+    if (f->J <= 0 || f->J > 65535 || f->n != 7 * f->J || f->bw < 0 || f->ldab < f->bw + 1 || f->iterations < 1 ||
+        f->iterations > 64 || f->n_cap <= 0)
+        return SB_ERR_ARG;
+    if (f->fx_shift < 0 || f->fx_shift > 60 || f->fx_gshift < 0 || f->fx_gshift > 60) return SB_ERR_ARG;
+    if (f->n_partials_loss != sb_data_loss_blocks(f->n_cap)) return SB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    LMState* state = (LMState*)f->state;
+    const long long n_tot = (long long)f->n * f->ldab + f->n;
+    // prologue: controller state, the store the first assembly goes to, the normal equations at the initial beta
+    if (cudaMemsetAsync(f->fx_store[1], 0, (size_t)n_tot * sizeof(long long), st) != cudaSuccess) return SB_ERR_CUDA;
+    if (cudaMemsetAsync(f->info, 0, sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    int rc = sb_lm_begin(f->state, f->beta, f->best, f->J, f->u, f->v, f->minimal_loss, stream);
+    if (rc != SB_OK) return rc;
+    rc = jtj_pass(f, 1, 0, st);
+    if (rc != SB_OK) return rc;
+    for (int it = 0; it < f->iterations; ++it) {
+        const bool timed = f->solve_events && 2 * it + 1 < f->n_solve_events;
+        if (timed && cudaEventRecord((cudaEvent_t)f->solve_events[2 * it], st) != cudaSuccess) return SB_ERR_CUDA;
+        rc = from_fixed(f->fx_store[0], f->fx_store[1], state, f->n, f->ldab, f->fx_shift, f->fx_gshift, f->AB, f->g, 1, st);
+        if (rc != SB_OK) return rc;
+        rc = sb_band_solve4_step(f->AB, f->ldab, f->n, f->bw, f->g, &state->u, f->dinv, f->info, f->solver_ws,
+                                 f->solver_ws_bytes, f->n_ctas, &state->failed, f->beta, f->pos_node, stream);
+        if (rc != SB_OK) return rc;
+        if (timed && cudaEventRecord((cudaEvent_t)f->solve_events[2 * it + 1], st) != cudaSuccess) return SB_ERR_CUDA;
+        if (it + 1 < f->iterations) {
+            rc = jtj_pass(f, 0, it + 1, st);
+        } else {      // after the last solve only the loss of the trial beta is needed
+            rc = sb_data_term_loss_decide(f->points, f->knn_idx, f->knn_w, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
+                                          f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data, f->partials_loss,
+                                          f->n_partials_loss, f->state, f->ed_knn, f->lam_arap, f->lam_rot, f->use_arap,
+                                          f->use_rot, f->beta, f->best, stream);
+        }
+        if (rc != SB_OK) return rc;
+    }
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -17,6 +17,8 @@ struct LMState {
     int accept[64];
     double u_trace[64];
     unsigned int ticket;  // blocks of the fused loss pass that have delivered their partial (self-resetting)
+    int sel;              // frame loop (sb_lm_frame): which of the two fixed-point stores holds the normal equations of the
+                          // CURRENT beta; the J^T J pass at a trial beta assembles into the other one, an accepted step flips
 };
 
 // squared ARAP residual of (node j, neighbour slot k) = item tid, and squared Rot residual of node j: the loss-only
@@ -52,9 +54,16 @@ struct RegLossArgs {     // ed_points == nullptr: the ARAP / Rot losses come in 
 
 // loss = sum(data partials) + arap + rot; accept iff loss < minimal_loss   (LM.py:107-117)
 // Block-wide (BLOCK threads, every thread of the block must call it).
+// flip_sel: an accepted step makes the store assembled at the trial beta the current one (frame loop); adopt: the
+// prologue of the frame loop -- the system assembled at the initial beta becomes current, no LM decision is taken.
 template <int BLOCK>
 __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partials, int n_partials, double* loss_arap_rot,
-                                               double* beta, double* best, int n, RegLossArgs rg) {
+                                               double* beta, double* best, int n, RegLossArgs rg, bool flip_sel = false,
+                                               bool adopt = false) {
+    if (adopt) {
+        if (threadIdx.x == 0) st->sel ^= 1;
+        return;
+    }
     __shared__ double red[BLOCK / 32];
     __shared__ int s_accept;
     __shared__ double s_reg[2];
@@ -85,7 +94,7 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
                 st->accept[it] = acc ? 1 : 0;
                 st->u_trace[it] = st->u;
             }
-            if (acc) { st->minimal_loss = loss; st->u /= st->v; }
+            if (acc) { st->minimal_loss = loss; st->u /= st->v; if (flip_sel) st->sel ^= 1; }
             else st->u *= st->v;
             st->iter = it + 1;
             s_accept = acc ? 1 : 0;

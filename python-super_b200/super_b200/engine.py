@@ -252,7 +252,11 @@ class Tracker:
         self.cluster_size = int(getattr(opt, "solver_ctas", os.environ.get("SB_SOLVER_CTAS", "148")))
         self.band = None
         self.block_bw = torch.zeros(1, dtype=I32, device=self.dev)
-        self._bw_pinned = torch.zeros(2, dtype=I32).pin_memory() if torch.cuda.is_available() else None
+        # pinned hand-over words: block half-bandwidth needed, band.overflow (bit 0 outside the band, bit 1 outside the
+        # fixed-point range), sb_fuse's capacity-overflow flag
+        self._bw_pinned = torch.zeros(3, dtype=I32).pin_memory() if torch.cuda.is_available() else None
+        self.event_sink = None       # bench.py: {"jtj": [], "solve": []} receiving (begin, end) raw cudaEvent_t pairs
+        self.events_per_frame = (3, 2)
 
     # -- row-count / band-width hand-over: ONE host wait per tracked frame -----------------------------------
     # After compaction the surfels' node tuples are final, so the NEXT frame's visiting order and the block
@@ -276,6 +280,7 @@ class Tracker:
         self._bw_pinned[0:1].copy_(self.block_bw, non_blocking=True)
         if self.band is not None:
             self._bw_pinned[1:2].copy_(self.band.overflow, non_blocking=True)
+        self._bw_pinned[2:3].copy_(self.overflow, non_blocking=True)
         self._n_event = torch.cuda.Event()
         self._n_event.record()
 
@@ -287,8 +292,20 @@ class Tracker:
         n = min(self.cap, int(self._n_pinned[0]))
         self._last_growth = 0 if self._n_exact is None else n - self._n_exact
         self._n_exact = self.n_bound = n
+        # Both flags are raised by kernels of the frame that has just been handed over: its beta has been applied and fused
+        # by the time the host sees them (the price of running one frame ahead).  The tracker state is not trustworthy
+        # after either, so this is fatal rather than a warning.
+        if int(self._bw_pinned[2]) != 0:
+            raise lib.SuperB200Error(f"surfel capacity ({self.cap} rows) exceeded in the fusion of the previous frame: new "
+                                     "surfels were dropped; construct Tracker with a larger capacity_factor")
         if self.band is not None and int(self._bw_pinned[1]) != 0:
-            raise lib.SuperB200Error("normal-equation entries fell outside the planned band")
+            what = []
+            if int(self._bw_pinned[1]) & 1:
+                what.append("normal-equation entries fell outside the planned band")
+            if int(self._bw_pinned[1]) & 2:
+                what.append(f"a normal-equation addend exceeded the fixed-point range 2^{62 - self.band.fx_shift} "
+                            "(lower Band.FX_SHIFT for such term weights)")
+            raise lib.SuperB200Error("previous frame's LM solve: " + "; ".join(what))
         if self._order is not None:
             bwb = int(self._bw_pinned[0])
             if n > self._order_rows:             # more rows than the order covers: redo it (synchronises; rare)
@@ -304,13 +321,30 @@ class Tracker:
         J = self.ED.num
         bw = 7 * min(J - 1, block_bw_needed) + 6
         bw = min(7 * J - 1, (bw + 31) // 32 * 32)
-        if self.solver != "band" or bw > lib.load().sb_band_max_bw():
+        if self.solver != "band" or not lib.load().sb_band3_fits(7 * J, bw):
             self.band = None
             return
         if self.band is None or self.band.bw != bw:
             if bw not in self._bands:
-                self._bands[bw] = ops.Band(7 * J, bw, self.ED.node_pos, self.dev)
+                # fixed-point range follows the term weights: entries of J^T J scale with lambda^2 (defaults 1, 10, 1 ->
+                # the default exponent; 4x the weight -> 4 bits more range, 4 bits less resolution)
+                import math
+                o = self.opt
+                lam2 = max(float(o.sf_point_plane_weight) ** 2, float(o.mesh_arap_weight) ** 2 if o.mesh_arap else 0.0,
+                           float(o.mesh_rot_weight) ** 2 if o.mesh_rot else 0.0, 1e-30)
+                extra = max(0, math.ceil(math.log2(lam2 / 100.0)))
+                self._bands[bw] = ops.Band(7 * J, bw, self.ED.node_pos, self.dev, fx_shift=ops.Band.FX_SHIFT - extra,
+                                           fx_gshift=ops.Band.FX_GSHIFT - extra)
             self.band = self._bands[bw]
+
+    @staticmethod
+    def _new_events(n):
+        out = []
+        for _ in range(n):
+            e = ctypes.c_void_p()
+            call("sb_event_create", ctypes.byref(e))
+            out.append(e.value)
+        return out
 
     def num_surfels(self):
         """Exact row count (synchronises)."""
@@ -389,8 +423,14 @@ class Tracker:
             order = self._order
             if order is None:
                 order = ops.tuple_order(sfv.knn_indices, self.cur.n_dev, self.ED.node_pos, self.block_bw)
+            jev = sev = None
+            if self.event_sink is not None:
+                jev, sev = self._new_events(2 * self.events_per_frame[0]), self._new_events(2 * self.events_per_frame[1])
+                self.event_sink["jtj"] += list(zip(jev[0::2], jev[1::2]))
+                self.event_sink["solve"] += list(zip(sev[0::2], sev[1::2]))
             beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, n_dev=self.cur.n_dev,
-                                        order=order, band=self.band, cluster_size=self.cluster_size)
+                                        order=order, band=self.band, cluster_size=self.cluster_size, jtj_events=jev,
+                                        solve_events=sev)
             self.last_beta = beta
             ops.warp_update(sfv.points, sfv.norms, sfv.knn_indices, sfv.knn_w, self.ED.points, self.ED.norms, beta,
                             n_dev=self.cur.n_dev)

@@ -1,20 +1,44 @@
 """Levenberg-Marquardt loop over beta in R^{J x 7} on the device: the B200 restatement of
 LM_Solver.LM (/root/reference/super/LM.py:81-122).
 
-Per iteration, band path (the default): data-term J^T J kernel (tensor-core Gram panels), with the ARAP/Rot kernel
-and the memset of the next iteration's band buffer on a side stream under it -> two-sided banded Cholesky with the
-damping read from the device state and the step beta += delta in its last kernel -> loss-only pass whose last block
-runs the accept/reject step.  Dense path (cross-check): zero A,g -> J^T J -> ARAP/Rot -> damping -> library Cholesky ->
-step -> loss-only pass -> accept/reject.  u, minimal_loss, the failure flag and the loss trace stay on the device
-(ops.LMState): the loop issues no host sync.
+Band path (the default, `lm_frame`): ONE C call, sb_lm_frame (csrc/lm_frame.cu), enqueues the whole loop -- per iteration
+fixed-point store -> f64 band, two-sided banded Cholesky with the damping read from the device state and the step
+beta += delta in its last kernel, then the J^T J pass AT the trial beta (tensor-core Gram panels; ARAP/Rot in the same
+launch) whose last block takes the accept/reject decision: the trial loss falls out of that pass and, when the step is
+accepted, the pass already is the next iteration's normal equations.  Bitwise reproducible (integer atomics).
+Step-by-step path (`lm_solve` with on_iter hooks, the dense cross-check, systems the band solver does not take): zero
+-> J^T J -> ARAP/Rot -> [damping -> library Cholesky | band solve] -> step -> loss-only pass -> accept/reject, one C call
+per stage.  u, minimal_loss, the failure flag and the loss trace stay on the device (ops.LMState): no host sync.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
-from . import ops
+import os
+
+from . import lib, ops
+from .lib import call, ptr, stream
 
 F64 = torch.float64
+
+
+class SbLMFrame(ctypes.Structure):
+    """ctypes mirror of SbLMFrame (include/super_b200.h)."""
+    _P, _I, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    _fields_ = [("points", _P), ("knn_idx", _P), ("knn_w", _P), ("order", _P), ("n_cap", _I), ("n_dev", _P),
+                ("ed_points", _P), ("ed_knn", _P), ("J", _I),
+                ("vmap", _P), ("nmap", _P), ("H", _I), ("W", _I), ("intr", _D * 4),
+                ("lam_data", _D), ("lam_arap", _D), ("lam_rot", _D), ("use_arap", _I), ("use_rot", _I),
+                ("iterations", _I), ("u", _D), ("v", _D), ("minimal_loss", _D),
+                ("state", _P), ("beta", _P), ("best", _P),
+                ("partials_jtj", _P), ("n_partials_jtj", _I), ("partials_loss", _P), ("n_partials_loss", _I),
+                ("n", _I), ("bw", _I), ("ldab", _I), ("node_pos", _P), ("pos_node", _P),
+                ("fx_store", _P * 2), ("fx_shift", _I), ("fx_gshift", _I),
+                ("AB", _P), ("g", _P), ("band_overflow", _P), ("dinv", _P), ("info", _P),
+                ("solver_ws", _P), ("solver_ws_bytes", ctypes.c_longlong), ("n_ctas", _I),
+                ("jtj_events", _P), ("n_jtj_events", _I), ("solve_events", _P), ("n_solve_events", _I)]
 
 
 class LMWorkspace:
@@ -23,20 +47,85 @@ class LMWorkspace:
     def __init__(self, J, device):
         n = 7 * J
         self.J, self.n = J, n
-        self.A = torch.zeros((n, n), dtype=F64, device=device)
-        self.g = torch.zeros((n, 1), dtype=F64, device=device)
+        self.device = device
+        self._A = self._g = None       # dense (7J)^2 matrix: allocated only when the dense cross-check path runs
         self.beta = torch.zeros((J, 7), dtype=F64, device=device)
         self.best = torch.zeros((J, 7), dtype=F64, device=device)
         self.loss2 = torch.zeros(2, dtype=F64, device=device)
         self.state = ops.LMState(device)
         self.partials = None
-        # the regularisers' normal-equation terms (6 CTAs, ~7 us) run on a side stream under the data term's pass
-        self.side = torch.cuda.Stream(device=device)
-        self.fork, self.join, self.cleared = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.partials_jtj = None
+
+    @property
+    def A(self):
+        if self._A is None:
+            self._A = torch.zeros((self.n, self.n), dtype=F64, device=self.device)
+        return self._A
+
+    @property
+    def g(self):
+        if self._g is None:
+            self._g = torch.zeros((self.n, 1), dtype=F64, device=self.device)
+        return self._g
+
+
+def band_frame_ok(band, cluster_size):
+    """The one-call frame loop needs the two-sided / one-sided tensor-core band solver for this system."""
+    return band is not None and cluster_size >= 8 and bool(lib.load().sb_band3_fits(band.n, band.bw))
+
+
+def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None, cluster_size=148,
+             jtj_events=None, solve_events=None):
+    """The whole LM loop of one frame in one C call (sb_lm_frame).  Same arguments and result as lm_solve.
+    jtj_events: optional list of raw cudaEvent_t handles (2 per J^T J pass: begin, end) recorded around those launches."""
+    ed = sf.ED
+    J = ed.points.shape[0]
+    dev = sf.points.device
+    l = lib.load()
+    n_cap = sf.points.shape[0]
+    nb = ops.data_loss_blocks(n_cap)
+    if ws.partials is None or ws.partials.numel() != nb:
+        ws.partials = torch.zeros(nb, dtype=F64, device=dev)
+    if ws.partials_jtj is None:
+        ws.partials_jtj = torch.zeros(int(l.sb_lm_frame_partials(n_cap)), dtype=F64, device=dev)
+    if getattr(band, "ws4", None) is None:
+        band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8, device=dev)
+    vmap, nmap = maps
+    f = SbLMFrame()
+    f.points, f.knn_idx, f.knn_w, f.order = ptr(sf.points), ptr(sf.knn_indices), ptr(sf.knn_w), ptr(order)
+    f.n_cap, f.n_dev = n_cap, ptr(n_dev)
+    f.ed_points, f.ed_knn, f.J = ptr(ed.points), ptr(ed.knn_indices), J
+    f.vmap, f.nmap, f.H, f.W = ptr(vmap), ptr(nmap), cam.H, cam.W
+    f.intr = (ctypes.c_double * 4)(cam.fx, cam.fy, cam.cx, cam.cy)
+    f.lam_data, f.lam_arap, f.lam_rot = opt.sf_point_plane_weight, opt.mesh_arap_weight, opt.mesh_rot_weight
+    f.use_arap, f.use_rot = int(bool(opt.mesh_arap)), int(bool(opt.mesh_rot))
+    f.iterations, f.u, f.v, f.minimal_loss = int(opt.num_optimize_iterations), u, v, minimal_loss
+    f.state, f.beta, f.best = ptr(ws.state.buf), ptr(ws.beta), ptr(ws.best)
+    f.partials_jtj, f.n_partials_jtj = ptr(ws.partials_jtj), ws.partials_jtj.numel()
+    f.partials_loss, f.n_partials_loss = ptr(ws.partials), ws.partials.numel()
+    f.n, f.bw, f.ldab = band.n, band.bw, band.ldab
+    f.node_pos, f.pos_node = ptr(band.node_pos), ptr(band.pos_node)
+    f.fx_store = (ctypes.c_void_p * 2)(ptr(band.fx[0]), ptr(band.fx[1]))
+    f.fx_shift, f.fx_gshift = band.fx_shift, band.fx_gshift
+    f.AB, f.g = ptr(band._AB), ptr(band._g)
+    f.band_overflow, f.dinv, f.info = ptr(band.overflow), ptr(band.dinv), ptr(band.info)
+    f.solver_ws, f.solver_ws_bytes, f.n_ctas = ptr(band.ws4), band.ws4.numel(), int(cluster_size)
+    keep = []
+    for name, evs in (("jtj", jtj_events), ("solve", solve_events)):
+        if evs:
+            arr = (ctypes.c_void_p * len(evs))(*evs)
+            keep.append(arr)
+            setattr(f, name + "_events", ctypes.cast(arr, ctypes.c_void_p))
+            setattr(f, "n_" + name + "_events", len(evs))
+    call("sb_lm_frame", ctypes.byref(f), stream())
+    lib.LAUNCHES += 2 + 7 * f.iterations        # lm_begin, first J^T J; per iteration from_fixed + 5 (solve) + J^T J | loss
+    band._dirty = False
+    return ws.beta, ws
+
 
 
 def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
-             on_iter=None, band=None, cluster_size=16):
+             on_iter=None, band=None, cluster_size=16, jtj_events=None, solve_events=None):
     """sf: object with points (N,3) f64, knn_indices (N,4) i32, knn_w (N,4) f64 and ED (points, knn_indices i32).
     maps: (vmap, nmap) dense float4 images of the new frame.  Returns beta (J,7) f64 (a view of the
     workspace) -- the same value LM_Solver.LM returns.
@@ -47,6 +136,10 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
     dev = sf.points.device
     if ws is None or ws.J != J:
         ws = LMWorkspace(J, dev)
+    if (on_iter is None and band_frame_ok(band, cluster_size) and bool(opt.sf_point_plane)
+            and os.environ.get("SB_LM_STEPWISE", "0") != "1"):
+        return lm_frame(sf, maps, cam, opt, ws, band, u, v, minimal_loss, order, n_dev, cluster_size, jtj_events,
+                        solve_events)
     n_cap = sf.points.shape[0]
     nb = ops.data_loss_blocks(n_cap)
     if ws.partials is None or ws.partials.numel() != nb:
@@ -60,36 +153,19 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
     ws.loss2.zero_()
     if band is not None:
         band.info.zero_()
-    overlap = use_data and (use_arap or use_rot) and on_iter is None
-    cleared_ahead = False
     for it in range(opt.num_optimize_iterations):
         if band is not None:
-            if cleared_ahead:                # the side stream cleared the other store during the previous iteration
-                band.flip()
-                torch.cuda.current_stream().wait_event(ws.cleared)
-            else:
-                band.store.zero_()           # AB and g in one memset
+            band.store.zero_()               # AB and g in one memset (fixed-point store)
         else:
             ws.A.zero_()
             ws.g.zero_()
-        if overlap:      # fork: both kernels only add into the zeroed A, g
-            main = torch.cuda.current_stream()
-            ws.fork.record(main)
-            ws.side.wait_event(ws.fork)
-            with torch.cuda.stream(ws.side):
-                ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g, band=band)
-                ws.join.record(ws.side)
-                if band is not None:         # last read by the previous iteration's solve, which the fork is behind
-                    band.other_store.zero_()
-                    ws.cleared.record(ws.side)
-                    cleared_ahead = True
         if use_data:
             ops.data_term_jtj(sf.points, sf.knn_indices, sf.knn_w, order, ed.points, ws.beta, vmap, nmap, cam,
-                              lam_d, ws.A, ws.g, n_dev=n_dev, band=band)
-        if overlap:
-            main.wait_event(ws.join)
-        elif use_arap or use_rot:
-            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot, ws.A, ws.g, band=band)
+                              lam_d, ws.A if band is None else None, ws.g if band is None else None, n_dev=n_dev,
+                              band=band)
+        if use_arap or use_rot:
+            ops.reg_terms(ed.points, ed.knn_indices, ws.beta, lam_a, lam_r, use_arap, use_rot,
+                          ws.A if band is None else None, ws.g if band is None else None, band=band)
         if on_iter is not None:
             on_iter(it, "normal_equations", ws)
         if band is not None:

@@ -101,18 +101,29 @@ def data_term_rows(points, knn_idx, knn_w, ed_points, beta, vmap, nmap, cam, lam
 
 
 class Band:
-    """Band-storage target of the normal equations: AB (n, ldab) lower band row-major in the node order
-    `node_pos` (node id -> position), scalar half-bandwidth bw; `overflow` is raised by the assembly
-    kernels if an entry falls outside the band."""
+    """Band-storage target of the normal equations in the node order `node_pos` (node id -> position), scalar
+    half-bandwidth bw.
 
-    def __init__(self, n, bw, node_pos, device):
+    Two representations:
+      * `fx`: two int64 FIXED-POINT stores (AB | g; entries are multiples of 2^-fx_shift, 2^-fx_gshift) that the assembly
+        kernels add into with integer atomics -- order-independent, hence bitwise reproducible;
+      * `AB` (n, ldab) lower band row-major + `g` (n): the f64 work copy the solver factors in place (`finalize()` =
+        sb_band_from_fixed).  Reading `AB` / `g` / `to_dense()` after an assembly finalizes first.
+    `overflow`: bit 0 an entry fell outside the band, bit 1 an addend fell outside the fixed-point range."""
+
+    FX_SHIFT, FX_GSHIFT = 40, 48
+
+    def __init__(self, n, bw, node_pos, device, fx_shift=None, fx_gshift=None):
         self.n, self.bw = int(n), int(bw)
         self.ldab = self.bw + 1
-        # AB and g share one allocation so that one memset clears both; two of them, so that the LM loop can clear the
-        # next iteration's on a side stream while this iteration's is being solved (flip())
-        self._stores = [torch.zeros(self.n * self.ldab + self.n, dtype=F64, device=device) for _ in range(2)]
-        self._cur = 0
-        self._bind()
+        self.fx_shift = self.FX_SHIFT if fx_shift is None else int(fx_shift)
+        self.fx_gshift = self.FX_GSHIFT if fx_gshift is None else int(fx_gshift)
+        m = self.n * self.ldab + self.n
+        self.fx = [torch.zeros(m, dtype=torch.int64, device=device) for _ in range(2)]
+        self.work = torch.zeros(m, dtype=F64, device=device)
+        self._AB = self.work[: self.n * self.ldab].view(self.n, self.ldab)
+        self._g = self.work[self.n * self.ldab:]
+        self._dirty = False
         self.node_pos = node_pos
         # solver position -> node id (the step folded into the solve scatters x back to beta's node order)
         self.pos_node = None if node_pos is None else torch.argsort(node_pos.long()).to(I32).contiguous()
@@ -120,15 +131,28 @@ class Band:
         self.dinv = torch.zeros(self.n, dtype=F64, device=device)
         self.info = torch.zeros(1, dtype=I32, device=device)
 
-    def _bind(self):
-        self.store = self._stores[self._cur]
-        self.other_store = self._stores[self._cur ^ 1]
-        self.AB = self.store[: self.n * self.ldab].view(self.n, self.ldab)
-        self.g = self.store[self.n * self.ldab:]
+    @property
+    def store(self):
+        """The fixed-point store the stand-alone assembly entry points add into (zero it before a new assembly)."""
+        self._dirty = True
+        return self.fx[0]
 
-    def flip(self):
-        self._cur ^= 1
-        self._bind()
+    def finalize(self):
+        call("sb_band_from_fixed", ptr(self.fx[0]), self.n, self.ldab, self.fx_shift, self.fx_gshift, ptr(self._AB),
+             ptr(self._g), stream())
+        self._dirty = False
+
+    @property
+    def AB(self):
+        if self._dirty:
+            self.finalize()
+        return self._AB
+
+    @property
+    def g(self):
+        if self._dirty:
+            self.finalize()
+        return self._g
 
     def to_dense(self):
         """Symmetric dense matrix in the ORIGINAL node order (tests)."""
@@ -147,15 +171,21 @@ class Band:
         return A
 
 
+def _target(A, g, band):
+    """(A, lda, bw, node_pos, overflow, g, fx_shift, fx_gshift) of an assembly call: dense f64 or the band's store."""
+    if band is not None:
+        st = band.store
+        nab = band.n * band.ldab
+        return st[:nab], band.ldab, band.bw, band.node_pos, band.overflow, st[nab:], band.fx_shift, band.fx_gshift
+    return A, (A.stride(0) if A is not None else 0), -1, None, None, g, -1, -1
+
+
 def data_term_jtj(points, knn_idx, knn_w, order, ed_points, beta, vmap, nmap, cam, lam, A, g, loss_cur=None,
                   n_dev=None, band=None):
-    if band is not None:
-        A, lda, bw, pos, ovf, g = band.AB, band.ldab, band.bw, band.node_pos, band.overflow, band.g
-    else:
-        lda, bw, pos, ovf = A.stride(0), -1, None, None
+    A, lda, bw, pos, ovf, g, sh, gsh = _target(A, g, band)
     call("sb_data_term_jtj", ptr(points), ptr(knn_idx), ptr(knn_w), ptr(order), points.shape[0], ptr(n_dev),
          ptr(ed_points), ptr(beta), ed_points.shape[0], ptr(vmap), ptr(nmap), cam.H, cam.W, cam.c, float(lam),
-         ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss_cur), stream())
+         ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss_cur), sh, gsh, stream())
 
 
 def data_loss_blocks(n_cap):
@@ -189,45 +219,33 @@ def tuple_order(knn_idx, n_dev=None, node_pos=None, block_bw=None):
 
 # ---- LM regularisers / controller ----------------------------------------------------------------
 def reg_terms(ed_points, ed_knn, beta, lam_arap, lam_rot, use_arap, use_rot, A=None, g=None, loss2=None, band=None):
-    if band is not None:
-        A, lda, bw, pos, ovf, g = band.AB, band.ldab, band.bw, band.node_pos, band.overflow, band.g
-    else:
-        lda, bw, pos, ovf = (A.stride(0) if A is not None else 0), -1, None, None
+    A, lda, bw, pos, ovf, g, sh, gsh = _target(A, g, band)
     call("sb_reg_terms", ptr(ed_points), ptr(ed_knn), ptr(beta), ed_points.shape[0], float(lam_arap), float(lam_rot),
-         int(use_arap), int(use_rot), ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss2), stream())
+         int(use_arap), int(use_rot), ptr(A), lda, bw, ptr(pos), ptr(ovf), ptr(g), ptr(loss2), sh, gsh, stream())
 
 
 def band_solve(band, u_ptr=None, cluster_size=16, variant=None):
     """(A + u I) x = g in place: band.g <- x (solver node order).  u_ptr: device address of u.
     variant 4 (default): sb_band_solve4 (two-sided: variant 3's factorisation from both ends at once, middle block last);
-    variant 3: sb_band_solve3 (DMMA products with explicit block inverses, push-style back substitution);
-    variant 2: sb_band_solve2 (first pipelined kernel); variant 1: barrier-per-panel cluster kernel sb_band_solve."""
+    variant 3: sb_band_solve3 (one-sided; DMMA products with explicit block inverses, push-style back substitution)."""
     import os
     if variant is None:
         variant = int(os.environ.get("SB_BAND_VARIANT", "4"))
     l = lib.load()
-    if variant == 4 and cluster_size >= 8 and l.sb_band3_fits(band.n, band.bw):
+    if cluster_size < 3 or not l.sb_band3_fits(band.n, band.bw):
+        raise lib.SuperB200Error(f"band solver does not take n={band.n}, bw={band.bw} on {cluster_size} CTAs")
+    if variant == 4 and cluster_size >= 8:
         if getattr(band, "ws4", None) is None:
             band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8,
                                    device=band.AB.device)
         call("sb_band_solve4", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
              ptr(band.info), ptr(band.ws4), band.ws4.numel(), int(cluster_size), stream())
-    elif variant in (3, 4) and cluster_size >= 3 and l.sb_band3_fits(band.n, band.bw):
+    else:
         if getattr(band, "ws3", None) is None:
             band.ws3 = torch.zeros(int(l.sb_band3_workspace_bytes(band.n, band.bw)), dtype=torch.uint8,
                                    device=band.AB.device)
         call("sb_band_solve3", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
              ptr(band.info), ptr(band.ws3), band.ws3.numel(), int(cluster_size), stream())
-    elif variant >= 2 and cluster_size >= 3 and l.sb_band2_fits(band.n, band.bw):
-        if getattr(band, "ws2", None) is None:
-            band.ws2 = torch.zeros(int(l.sb_band2_workspace_bytes2(band.n, band.ldab)), dtype=torch.uint8,
-                                   device=band.AB.device)
-        call("sb_band_solve2", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
-             ptr(band.info), ptr(band.ws2), band.ws2.numel(), int(min(cluster_size, 128)), stream())
-    else:
-        cs = 16 if cluster_size >= 16 else 8 if cluster_size >= 8 else 4 if cluster_size >= 4 else 2 if cluster_size >= 2 else 1
-        call("sb_band_solve", ptr(band.AB), band.ldab, band.n, band.bw, ptr(band.g), u_ptr, ptr(band.dinv),
-             ptr(band.info), cs, stream())
 
 
 def band_solve_step(band, state, beta, cluster_size=148):

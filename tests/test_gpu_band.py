@@ -22,19 +22,15 @@ def _random_band_system(n, bw, seed):
     return A, b
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
-@pytest.mark.parametrize("n,bw,cluster", [(40, 5, 1), (97, 13, 2), (256, 40, 4), (1000, 150, 8), (1862, 300, 16),
+@pytest.mark.parametrize("variant", [3])
+@pytest.mark.parametrize("n,bw,cluster", [(40, 5, 3), (97, 13, 3), (256, 40, 4), (1000, 150, 8), (1862, 300, 16),
                                           (1862, 300, 8), (333, 332, 8), (64, 0, 4), (31, 6, 16), (200, 31, 3),
                                           (2000, 64, 16), (1862, 845, 16), (1862, 370, 128), (1862, 377, 64), (33, 32, 5),
-                                          (4000, 500, 148)])
+                                          (4000, 500, 148), (7917, 640, 148), (8463, 672, 148)])
 def test_band_solve_matches_dense(n, bw, cluster, variant):
-    if variant >= 2 and cluster < 3:
-        pytest.skip("pipelined kernels need >= 3 CTAs")
-    if variant == 1 and cluster not in (1, 2, 4, 8, 16):
-        pytest.skip("barrier kernel takes power-of-two clusters")
+    """One-sided solver (sb_band_solve3) against a dense solve.  (The two earlier solver generations of round 1 were
+    removed from the library in round 2.)"""
     from super_b200 import ops, lib
-    if variant == 2 and not lib.load().sb_band2_fits(n, bw):
-        pytest.skip("v2 shared-memory layout does not fit")
     A, b = _random_band_system(n, bw, seed=n + bw)
     band = ops.Band(n, bw, None, "cuda")
     AB = torch.zeros((n, bw + 1), dtype=torch.float64)
@@ -50,20 +46,15 @@ def test_band_solve_matches_dense(n, bw, cluster, variant):
     x_ref = torch.linalg.solve(A + 0.5 * torch.eye(n, dtype=torch.float64), b)
     assert int(band.info.item()) == 0
     assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
-    # the factor itself
-    L_ref = torch.linalg.cholesky(A + 0.5 * torch.eye(n, dtype=torch.float64))
-    Lb = band.AB.cpu()
-    for d in (bw, max(bw - 1, 0), 0):
-        off = bw - d
-        if off < n and variant == 1:                              # v2 writes L out of place (workspace)
-            assert (Lb[off:, d] - L_ref.diagonal(-off)).abs().max() < 1e-10
 
 
-@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (256, 40, 4), (97, 13, 3), (1000, 150, 64), (2000, 64, 16), (333, 332, 8)])
+@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 64), (256, 40, 3), (1000, 150, 8), (2000, 64, 3), (333, 332, 8),
+                                       (4000, 500, 100)])
 def test_band_solve_v3_tile_owner_update_path(n, bw, ctas):
-    """The wide-band update role (fixed tile owners, L(I,p) formed once per row) forced on shapes that normally take
-    the one-tile-per-CTA role."""
+    """The wide-band update role (fixed tile owners, L(I,p) formed once per row), taken when the band has more trailing
+    tiles per panel than there are update CTAs -- here by giving the solver few CTAs."""
     from super_b200 import ops, lib
+    assert lib.load().sb_band3_update_role(n, bw, ctas) == 2
     A, b = _random_band_system(n, bw, seed=n + bw + 1)
     band = ops.Band(n, bw, None, "cuda")
     AB = torch.zeros((n, bw + 1), dtype=torch.float64)
@@ -74,20 +65,19 @@ def test_band_solve_v3_tile_owner_update_path(n, bw, ctas):
     band.AB.copy_(AB.cuda())
     band.g.copy_(b.cuda())
     u = torch.tensor([0.5], dtype=torch.float64, device="cuda")
-    lib.load().sb_band3_debug(64)
-    try:
-        ops.band_solve(band, u.data_ptr(), ctas, variant=3)
-        x = band.g.cpu()
-    finally:
-        lib.load().sb_band3_debug(0)
+    ops.band_solve(band, u.data_ptr(), ctas, variant=3)
+    x = band.g.cpu()
     x_ref = torch.linalg.solve(A + 0.5 * torch.eye(n, dtype=torch.float64), b)
     assert int(band.info.item()) == 0
     assert (x - x_ref).abs().max() <= 1e-11 * max(1.0, float(x_ref.abs().max()))
 
 
-@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (1862, 320, 148), (1862, 300, 64), (1094, 33, 148), (3000, 352, 148), (1000, 150, 32), (4000, 500, 148), (2000, 64, 16), (700, 100, 8)])
+@pytest.mark.parametrize("n,bw,ctas", [(1862, 370, 148), (1862, 320, 148), (1862, 300, 64), (1094, 33, 148), (3000, 352, 148), (1000, 150, 32), (4000, 500, 148), (2000, 64, 16), (700, 100, 8),
+                                       (7917, 640, 148), (8463, 672, 148)])
 def test_band_solve_v4_two_sided(n, bw, ctas):
-    """Two-sided solve (both ends eliminated concurrently, middle block last) against a dense solve."""
+    """Two-sided solve (both ends eliminated concurrently, middle block last) against a dense solve.  The last two
+    shapes are BASELINE configs 3a (640x480, step 16) and 5 (1280x1024): 20-21 tiles wide, i.e. the tile-owner update
+    role and the wide-band back substitution, at their own size."""
     from super_b200 import ops
     A, b = _random_band_system(n, bw, seed=n + bw + 2)
     band = ops.Band(n, bw, None, "cuda")
