@@ -182,9 +182,9 @@ def run_cuda(args, rank, world, local_rank):
     sampler.mark_begin()
     lib.LAUNCHES = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    # (begin, end) CUDA events on the launch stream around the first 3 J^T J passes and the first 2 linear solves of
-    # every timed frame, recorded inside sb_lm_frame (SbLMFrame.jtj_events / solve_events)
+    # (begin, end) CUDA events on the launch stream around every J^T J pass and every linear solve of every timed frame, recorded inside sb_lm_frame (SbLMFrame.jtj_events / solve_events)
     trk.event_sink = {"jtj": [], "solve": []}
+    trk.events_per_frame = (LM_ITERS, LM_ITERS)            # every J^T J pass (the first one of a frame is L2-cold) and every solve
     t_wall = time.perf_counter()
     for k in range(K):
         i = 1 + Wm + k

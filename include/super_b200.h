@@ -98,10 +98,11 @@ typedef struct SbLMFrame {
     void* state;                /* sb_lm_state_bytes() */
     double* beta;               /* (J,7) out: the frame's result */
     double* best;               /* (J,7) scratch */
-    double* partials_jtj;       /* n_partials_jtj >= sb_lm_frame_partials(n_cap) doubles */
-    int n_partials_jtj;
-    double* partials_loss;      /* n_partials_loss == sb_data_loss_blocks(n_cap) doubles */
+    double* partials_loss;      /* n_partials_loss >= max(sb_data_loss_blocks(n_cap), 1024) doubles: per-block sums of r^2 */
     int n_partials_loss;
+    double* rows;               /* (29, row_stride) f64 scratch: Jacobian rows of the last evaluation pass */
+    unsigned long long* keys;   /* (row_stride,) u64 scratch: node-set key per slot */
+    int row_stride;             /* >= n_cap */
     /* normal equations, band storage in the solver's node order */
     int n, bw, ldab;            /* n = 7J, half bandwidth, row stride (>= bw+1) */
     const int* node_pos;        /* node id -> solver position, or NULL */
@@ -235,10 +236,9 @@ int sb_band_from_fixed(const long long* store, int n, int ldab, int fx_shift, in
 
 /* LM_Solver.LM, the whole loop of one frame: /root/reference/super/LM.py:81-122 (prepareCostTerm :53-79, Solver :38-51)
  * over DataLoss / ARAPLoss / RotLoss (/root/reference/super/loss.py:207-499), band path.  Enqueues
- * 1 + 7*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
+ * 3 + 8*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
  * result and the controller state the per-iteration trace (sb_lm_state_offsets).  A failed factorisation stops the
  * updates and leaves the last accepted beta (LM.py:99-103).  Bitwise reproducible. */
-int sb_lm_frame_partials(int n_cap);
 /* CUDA events for timing launches inside sb_lm_frame on the stream they run on (bench.py's roofline) */
 int sb_event_create(void** ev);
 int sb_event_destroy(void* ev);
@@ -332,6 +332,24 @@ int sb_gf_step(double* dv, double* grad, double* grad_morph, double* acc, double
 int sb_gf_global_update(double* points, double* norms, int n_cap, const int* n_dev, double* ed_points, double* ed_norms,
                         int J, const double* global_row, void* stream);
 
+
+/* ---- ED graph (once per sequence / at every re-initialisation) -------------------------------------------- */
+
+/* init_graph + DirectDeformGraph.init_ED_nodes, grid_mesh branch: /root/reference/super/graph_encoder.py:11-67,128-167.
+ * Nodes = anchors (k*step, l*step) on valid pixels of the frame's dense maps, ids row-major; per cell edges (a,r) (a,rd)
+ * (a,d) (r,d) and triangles (a,r,rd) (a,rd,d); prune_classes (--hard_seg with --mesh_face) drops those across classes;
+ * radii = mean incident edge length (nodes without edges: mean of the others); areas = 0.5 sqrt(|cross|^2 + 1e-13).
+ * Capacity G = sb_graph_anchors(H, W, step): workspace 3G ints; points, norms (G,3) f64; anchor_uv (G,2) i32 [u,v];
+ * seg (G,) i32 + ed_seg_conf (G,C) f64 when seg_conf (P,C) is given; edges (4G,2) i32; faces (2G,3) i32; edge_lens (4G);
+ * radii (G); areas (2G); node_pos (G,) i32 = position of each node in the band solver's order (sorted along the longer
+ * image axis; no reference counterpart); counts[3] = {J, E, F} (device).  One launch, fixed summation orders. */
+int sb_graph_anchors(int H, int W, int step);
+int sb_graph_build(const float* vmap, const float* nmap, const double* seg_conf, int C, int H, int W, int step,
+                   int prune_classes, int* workspace, double* points, double* norms, int* anchor_uv, int* seg,
+                   double* ed_seg_conf, int* edges, int* faces, double* edge_lens, double* radii, double* areas,
+                   int* node_pos, int* counts, void* stream);
+/* *out_max = max(*out_max, max_jk |node_pos[j] - node_pos[knn[j,k]]|): block half-bandwidth the ARAP pairs need */
+int sb_graph_pair_span(const int* knn, const int* node_pos, int J, int K, int* out_max, void* stream);
 
 /* ---- per-frame producer ---------------------------------------------------------------------------- */
 

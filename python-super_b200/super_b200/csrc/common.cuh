@@ -97,27 +97,34 @@ struct MatView {
     const int* node_pos;
     int* overflow;
     double* g;
-    int shift, gshift;       // fixed-point exponents, or -1
+    double scale, gscale;    // fixed point: 2^shift, 2^gshift (multiplying by a power of two is exact); 0 = f64 atomics
+    __host__ __device__ __forceinline__ void set_shift(int shift, int gshift) {
+        scale = shift >= 0 ? (double)(1ull << shift) : 0.0;
+        gscale = shift >= 0 ? (double)(1ull << gshift) : 0.0;
+    }
     __device__ __forceinline__ int pos(int node) const { return node_pos ? node_pos[node] : node; }
-    __device__ __forceinline__ void put(double* p, double v, int sh) const {
-        if (sh < 0) {
+    // MODE 0: decided at run time by the scale; 1: fixed point known at compile time (the frame loop's kernel: one atomic
+    // per call site keeps its flush loop small enough for the instruction cache)
+    template <int MODE = 0>
+    __device__ __forceinline__ void put(double* p, double v, double sc) const {
+        if (MODE == 0 && sc == 0.0) {
             atomicAdd(p, v);
         } else {
-            const double sv = scalbn(v, sh);
-            if (!(fabs(sv) < 4.6e18)) { atomicOr(overflow, 2); return; }
-            atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double2ll_rn(sv));
+            const double sv = v * sc;
+            if (fabs(sv) < 4.6e18) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double2ll_rn(sv));
+            else atomicOr(overflow, 2);
         }
     }
+    template <int MODE = 0>
     __device__ __forceinline__ void add(int row, int col, double v) const {   // requires row >= col
-        if (bw < 0) {
-            put(A + (size_t)row * lda + col, v, shift);
-        } else if (row - col <= bw) {
-            put(A + (size_t)row * lda + (col - row + bw), v, shift);
+        if (bw < 0 || row - col <= bw) {
+            put<MODE>(A + (bw < 0 ? (size_t)row * lda + col : (size_t)row * lda + (col - row + bw)), v, scale);
         } else {
             atomicOr(overflow, 1);
         }
     }
-    __device__ __forceinline__ void add_g(int i, double v) const { put(g + i, v, gshift); }
+    template <int MODE = 0>
+    __device__ __forceinline__ void add_g(int i, double v) const { put<MODE>(g + i, v, gscale); }
 };
 
 // ---- block-wide deterministic sum (fixed tree), result valid in thread 0 -----------------------

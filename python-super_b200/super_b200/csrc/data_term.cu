@@ -202,6 +202,7 @@ __device__ __forceinline__ void build_flush_table(unsigned short* tab, int tid, 
     }
 }
 
+template <int MODE>
 __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, const MatView& M,
                                           double* loss_cur, double& warp_loss, double* __restrict__ St,
                                           const unsigned short* __restrict__ tab) {
@@ -224,6 +225,7 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
     const int my_pos = (lane < 4) ? M.pos((int)(key >> (48 - 16 * lane)) & 0xffff) : 0;
     const int p0 = __shfl_sync(0xffffffffu, my_pos, 0), p1 = __shfl_sync(0xffffffffu, my_pos, 1);
     const int p2 = __shfl_sync(0xffffffffu, my_pos, 2), p3 = __shfl_sync(0xffffffffu, my_pos, 3);
+#pragma unroll 1
     for (int e = lane; e < 435; e += 32) {
         const double val = St[e];
         if (val == 0.0) continue;
@@ -232,143 +234,138 @@ __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long lo
         const int pm = km == 0 ? p0 : km == 1 ? p1 : km == 2 ? p2 : p3;
         if (kn == 4) {                       // column 28: -J^T r, and r^T r in the corner
             if (km == 4) { warp_loss += val; if (loss_cur) atomicAdd(loss_cur, val); }   // entry 434: always lane 18
-            else M.add_g(7 * pm + cm, -val);
+            else M.add_g<MODE>(7 * pm + cm, -val);
             continue;
         }
         const int pn = kn == 0 ? p0 : kn == 1 ? p1 : kn == 2 ? p2 : p3;
         const int gm = 7 * pm + cm, gn = 7 * pn + cn;
-        M.add(max(gm, gn), min(gm, gn), val);
+        M.add<MODE>(max(gm, gn), min(gm, gn), val);
     }
     __syncwarp();
 }
 
-// Extras of the frame loop (sb_lm_frame, lm_frame.cu): the pass assembles into the fixed-point store that is NOT the
-// current one, the trailing blocks of the grid assemble the ARAP / Rot terms into the same store, every J^T J warp
-// delivers its own sum of r^2, and the block that draws the last ticket sums them in index order, adds the regularisers'
-// losses and takes the LM decision for the beta this pass was evaluated at.
-struct FrameFuse {
-    double* store[2];     // (AB | g) as int64 fixed point; target = store[1 - st->sel]
-    long long g_off;      // elements from the start of a store to its g
-    LMState* st;
-    double* partials;     // >= JTJ_WARPS * (J^T J blocks) doubles
-    int n_reg_blocks;
+// Frame loop (sb_lm_frame, lm_frame.cu): the evaluation and the Gram accumulation are TWO launches.
+//   data_eval_decide_kernel<true>  one thread per slot of the visiting order, 64-80 registers, 24+ warps per SM: warp ->
+//       project -> bilinear -> residual -> Jacobian row, written as 29 coalesced column stores (rows, SoA) + the node-set
+//       key; sum r^2 per block; the last block takes the LM decision for the beta the pass was evaluated at.
+//   data_jtj_kernel<true>          (below) reads the rows back (L2), stages them in the same shared panel and runs the
+//       DMMA Gram products + flush; assembles into the store the decision made current; skipped after a reject.
+// The fused single-launch form needs 128 registers (16 warps per SM) and walks every warp through 4 chunks of dependent
+// gathers + FP64 chains one after the other: 134 us per pass at 3.0e5 surfels (ncu r2c) against the sum of the two here.
+struct GramArgs {
+    double* store[2];          // (AB | g) as int64 fixed point; the pass assembles into store[st->sel]
+    long long g_off;           // elements from the start of a store to its g
+    const LMState* st;
+    const double* rows;        // (29, row_stride) f64: column c of the Jacobian row of slot s at rows[c*row_stride + s]
+    const unsigned long long* keys;   // (n,) node-set key per slot, ~0 = no correspondence
+    int row_stride;
+    int reg_threads;           // ARAP pairs + Rot nodes: one item per lane of the LAST warps of the grid (the least loaded)
     RegArgs reg;
-    double* beta; double* best;
-    int adopt;            // prologue: adopt the system, no decision
 };
 
-// the two rarely-taken parts of the fused pass, kept out of line so that their registers and local arrays do not weigh on
-// the surfel loop (inlined they cost it 450 bytes of spills)
-__device__ __noinline__ void fused_reg_block(const FrameFuse& f, const MatView& M, int tid) {
+// the regularisers' items, kept out of line (and its arguments BY VALUE: a reference would force the kernel's copy of M
+// into local memory for the whole kernel) so that their registers and local arrays do not weigh on the chunk loop
+__device__ __noinline__ void gram_reg_item(RegArgs reg, MatView M, int tid) {
     double la, lr;
-    reg_terms_item(f.reg, tid, M, true, la, lr);
-}
-__device__ __noinline__ void fused_decide(const FrameFuse& f, int n_partials) {
-    const RegLossArgs rg{f.reg.ed_points, f.reg.ed_knn, f.reg.J, f.reg.lam_arap, f.reg.lam_rot, f.reg.use_arap,
-                         f.reg.use_rot};
-    lm_decide_body<JTJ_WARPS * 32>(f.st, f.partials, n_partials, nullptr, f.beta, f.best, 7 * f.reg.J, rg, true,
-                                   f.adopt != 0);
+    reg_terms_item(reg, tid, M, true, la, lr);
 }
 
-template <bool FUSED>
+template <bool SPLIT>
 __global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
-data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, FrameFuse f) {
+data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
     extern __shared__ double smem[];
     __shared__ unsigned short fl_tab[448];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int jtj_blocks = gridDim.x;
-    if (FUSED) {
-        M.A = f.store[1 - f.st->sel];
+    if (SPLIT) {
+        if (!f.st->last_accept) return;             // rejected step: the current system is kept, nothing to assemble
+        M.A = f.store[f.st->sel];
         M.g = M.A + f.g_off;
-        jtj_blocks -= f.n_reg_blocks;
     }
-    if (!FUSED || (int)blockIdx.x < jtj_blocks) {
-        double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
-        double* St = Jt + JT_DOUBLES;
-        for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
-        build_flush_table(fl_tab, threadIdx.x, JTJ_WARPS * 32);
-        __syncthreads();
+    double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
+    double* St = Jt + JT_DOUBLES;
+    for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
+    build_flush_table(fl_tab, threadIdx.x, JTJ_WARPS * 32);
+    __syncthreads();
 
-        const int n = n_active(a.n_cap, a.n_dev);
-        const int n_chunks = (n + 31) >> 5;
-        const int total_warps = jtj_blocks * JTJ_WARPS;
-        const int gw = blockIdx.x * JTJ_WARPS + warp;
-        const int per = (n_chunks + total_warps - 1) / total_warps;
-        const int c0 = gw * per, c1 = min(n_chunks, c0 + per);
+    const int n = n_active(a.n_cap, a.n_dev);
+    const int n_chunks = (n + 31) >> 5;
+    const int total_warps = gridDim.x * JTJ_WARPS;
+    const int gw = blockIdx.x * JTJ_WARPS + warp;
+    const int per = (n_chunks + total_warps - 1) / total_warps;
+    const int c0 = gw * per, c1 = min(n_chunks, c0 + per);
 
-        double acc[10][2];
+    double acc[10][2];
 #pragma unroll
-        for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
-        unsigned long long acc_key = 0;
-        bool have = false;
-        double warp_loss = 0.0;      // sum of r^2 over this warp's surfels, in flush order (held by lane 18)
+    for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
+    unsigned long long acc_key = 0;
+    bool have = false;
+    double warp_loss = 0.0;
 
-        // one extra "tail" pass with a sentinel key flushes the last accumulator through the same code as a tuple
-        // change inside the loop (a single inlined copy of the flush)
-        for (int c = c0; c <= c1; ++c) {
-            const bool tail = (c == c1);
-            const int slot = c * 32 + lane;
+    // one extra "tail" pass with a sentinel key flushes the last accumulator through the same code as a tuple
+    // change inside the loop (a single inlined copy of the flush)
+    for (int c = c0; c <= c1; ++c) {
+        const bool tail = (c == c1);
+        const int slot = c * 32 + lane;
+        bool matched = false;
+        unsigned long long key = ~0ull;
+        if (SPLIT) {
+            if (!tail && slot < n) key = f.keys[slot];
+            matched = key != ~0ull;
+            double v[29];
+#pragma unroll
+            for (int col = 0; col < 29; ++col) v[col] = matched ? __ldcg(f.rows + (size_t)col * f.row_stride + slot) : 0.0;
+            if (!tail) {
+#pragma unroll
+                for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = v[col];
+            }
+        } else {
             Eval ev;
-            bool matched = false;
             if (!tail && slot < n) {
                 const int sid = a.order ? a.order[slot] : slot;
                 matched = eval_surfel<true, true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
             }
             if (matched) {
                 Jt[28 * JT_STRIDE + lane] = ev.r;
+                key = pack_key(ev.idx);
             } else if (!tail) {
 #pragma unroll
                 for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
             }
-            __syncwarp();
-            const unsigned long long key = matched ? pack_key(ev.idx) : ~0ull;
-            unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
-            while (remaining) {
-                const int leader = __ffs(remaining) - 1;
-                const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
-                const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
-                if (!have || k != acc_key) {
-                    if (have) flush_acc(acc, acc_key, lane, M, loss_cur, warp_loss, St, fl_tab);
-                    acc_key = k;
-                    have = !tail;
-                }
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const unsigned m4 = (m >> (4 * ks)) & 0xfu;
-                    if (m4 == 0u) continue;   // warp-uniform
-                    // rows of other tuples in this k-step are masked out (1.0 / 0.0 factor)
-                    const double keep = ((m4 >> (lane & 3)) & 1u) ? 1.0 : 0.0;
-                    double x[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        x[t] = keep * Jt[(8 * t + (lane >> 2)) * JT_STRIDE + 4 * ks + (lane & 3)];
-                    int t = 0;
-#pragma unroll
-                    for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-                        for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], x[ti], x[tj]);
-                }
-                remaining = tail ? 0u : (remaining & ~m);
+        }
+        __syncwarp();
+        unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
+        while (remaining) {
+            const int leader = __ffs(remaining) - 1;
+            const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
+            const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
+            if (!have || k != acc_key) {
+                if (have) flush_acc<SPLIT ? 1 : 0>(acc, acc_key, lane, M, loss_cur, warp_loss, St, fl_tab);
+                acc_key = k;
+                have = !tail;
             }
-            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const unsigned m4 = (m >> (4 * ks)) & 0xfu;
+                if (m4 == 0u) continue;   // warp-uniform
+                // rows of other tuples in this k-step are masked out (1.0 / 0.0 factor)
+                const double keep = ((m4 >> (lane & 3)) & 1u) ? 1.0 : 0.0;
+                double x[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    x[t] = keep * Jt[(8 * t + (lane >> 2)) * JT_STRIDE + 4 * ks + (lane & 3)];
+                int t = 0;
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                    for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], x[ti], x[tj]);
+            }
+            remaining = tail ? 0u : (remaining & ~m);
         }
-        if (FUSED && lane == 18) f.partials[gw] = warp_loss;
-    } else {
-        fused_reg_block(f, M, ((int)blockIdx.x - jtj_blocks) * (JTJ_WARPS * 32) + threadIdx.x);
+        __syncwarp();
     }
-    if (FUSED) {
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int ticket = atomicAdd(&f.st->ticket, 1u);
-            s_last = ticket == gridDim.x - 1;
-            if (s_last) f.st->ticket = 0;
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        fused_decide(f, jtj_blocks * JTJ_WARPS);
+    if (SPLIT) {
+        const int tid = (total_warps - 1 - gw) * 32 + lane;         // warp-uniform condition
+        if ((total_warps - 1 - gw) * 32 < f.reg_threads) gram_reg_item(f.reg, M, tid);
     }
 }
 
@@ -390,17 +387,34 @@ __global__ void __launch_bounds__(LOSS_BLOCK) data_loss_kernel(DataArgs a, doubl
 // The same pass with the LM accept/reject step behind it IN the launch: every block delivers its partial and takes a
 // ticket; the block that draws the last one sums all partials in their fixed order, evaluates the regularisers' losses
 // and runs lm_decide_body (lm_state.cuh) -- what sb_lm_decide_reg does as a launch of its own.
-struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; };
-__global__ void __launch_bounds__(LOSS_BLOCK) data_loss_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d) {
-    __shared__ double red[LOSS_BLOCK / 32];
+// ROWS: the evaluation pass of the frame loop -- slots of the visiting order instead of surfel ids, and the Jacobian row
+// of every slot is written out for the Gram pass (data_jtj_kernel<true>).
+struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; int flip_sel; int adopt; };
+struct RowsOut { double* rows; unsigned long long* keys; int row_stride; };
+constexpr int EVAL_BLOCK = 128;          // ROWS: 128 threads x 5 blocks per SM at <= 102 registers (20 warps, no spills)
+template <bool ROWS>
+__global__ void __launch_bounds__(ROWS ? EVAL_BLOCK : LOSS_BLOCK, ROWS ? 5 : 4)
+data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d, RowsOut ro) {
+    constexpr int BLOCK = ROWS ? EVAL_BLOCK : LOSS_BLOCK;
+    __shared__ double red[BLOCK / 32];
     __shared__ bool s_last;
     const int n = n_active(a.n_cap, a.n_dev);
     double s = 0.0;
-    for (int i = blockIdx.x * LOSS_BLOCK + threadIdx.x; i < n; i += gridDim.x * LOSS_BLOCK) {
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
         Eval ev;
-        if (eval_surfel<false>(a, i, ev, nullptr, 1)) s += ev.r * ev.r;
+        if (ROWS) {
+            const int sid = a.order ? a.order[i] : i;
+            const bool ok = eval_surfel<true, true>(a, sid, ev, ro.rows + i, ro.row_stride);
+            if (ok) {
+                ro.rows[(size_t)28 * ro.row_stride + i] = ev.r;
+                s += ev.r * ev.r;
+            }
+            ro.keys[i] = ok ? pack_key(ev.idx) : ~0ull;
+        } else if (eval_surfel<false>(a, i, ev, nullptr, 1)) {
+            s += ev.r * ev.r;
+        }
     }
-    s = block_sum<LOSS_BLOCK>(s, red);
+    s = block_sum<BLOCK>(s, red);
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = s;
         __threadfence();
@@ -411,7 +425,8 @@ __global__ void __launch_bounds__(LOSS_BLOCK) data_loss_decide_kernel(DataArgs a
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    lm_decide_body<LOSS_BLOCK>(d.st, partials, (int)gridDim.x, nullptr, d.beta, d.best, d.n, d.rg);
+    lm_decide_body<BLOCK>(d.st, partials, (int)gridDim.x, nullptr, d.beta, d.best, d.n, d.rg, d.flip_sel != 0,
+                          d.adopt != 0);
 }
 
 // Per-surfel rows for parity tests and for the drop-in DataLoss.forward face.
@@ -527,7 +542,7 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
     if (fx_shift >= 0 && (!band_overflow || fx_gshift < 0 || fx_shift > 60 || fx_gshift > 60)) return SB_ERR_ARG;
     MatView M;
     M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow; M.g = g;
-    M.shift = fx_shift >= 0 ? fx_shift : -1; M.gshift = fx_shift >= 0 ? fx_gshift : -1;
+    M.set_shift(fx_shift, fx_gshift);
     if (n_cap <= 0) return SB_OK;
     DataArgs a = make_args(points, knn_idx, knn_w, order, n_cap, n_dev, ed_points, beta, J, vmap, nmap, H, W,
                            intr, lambda);
@@ -538,7 +553,7 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    FrameFuse none{};
+    GramArgs none{};
     data_jtj_kernel<false><<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, loss_cur, none);
     SB_CHECK_LAUNCH();
     return SB_OK;
@@ -570,7 +585,8 @@ int sb_data_term_loss_decide(const double* points, const int* knn_idx, const dou
     DecideArgs d;
     d.st = (LMState*)state; d.beta = beta; d.best = best; d.n = 7 * J;
     d.rg = RegLossArgs{ed_points, ed_knn, J, lam_arap, lam_rot, use_arap, use_rot};
-    data_loss_decide_kernel<<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials, d);
+    d.flip_sel = 0; d.adopt = 0;
+    data_eval_decide_kernel<false><<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials, d, RowsOut{nullptr, nullptr, 0});
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -593,41 +609,71 @@ int sb_data_term_rows(const double* points, const int* knn_idx, const double* kn
 // ---- frame loop (lm_frame.cu) ---------------------------------------------------------------------------------
 namespace sbi {
 
-int jtj_fused_partials(int n_cap) {      // upper bound on the per-warp partials a fused pass writes (any device)
-    (void)n_cap;
-    return JTJ_WARPS * 4 * 256;          // <= 4 CTAs per SM (launch bounds), <= 256 SMs
+// resident blocks of the evaluation pass on the current device (one wave: the grid-stride loop balances the rest)
+static int eval_resident() {
+    static int resident[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (resident[dev] == 0) {
+        int per_sm = 0, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_eval_decide_kernel<true>, EVAL_BLOCK, 0);
+        resident[dev] = (per_sm > 0 ? per_sm : 1) * sms;
+    }
+    return resident[dev];
 }
 
-int launch_jtj_fused(const SbLMFrame* f, int adopt, cudaStream_t st) {
+// evaluation pass at f->beta: rows + keys for the Gram pass, loss partials, LM decision in the last block.
+// adopt != 0: prologue (the system assembled next becomes current without a decision).
+int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st) {
+    DataArgs a = make_args(f->points, f->knn_idx, f->knn_w, f->order, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
+                           f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data);
+    DecideArgs d;
+    d.st = (LMState*)f->state; d.beta = f->beta; d.best = f->best; d.n = 7 * f->J;
+    d.rg = RegLossArgs{f->ed_points, f->ed_knn, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
+    d.flip_sel = 1; d.adopt = adopt;
+    int blocks = (f->n_cap + EVAL_BLOCK - 1) / EVAL_BLOCK;
+    const int resident = eval_resident();
+    if (resident <= 0) return SB_ERR_CUDA;
+    if (blocks > resident) blocks = resident;
+    if (blocks > f->n_partials_loss) blocks = f->n_partials_loss;
+    if (blocks < 1) blocks = 1;
+    data_eval_decide_kernel<true><<<blocks, EVAL_BLOCK, 0, st>>>(a, f->partials_loss, d,
+                                                                RowsOut{f->rows, f->keys, f->row_stride});
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+// Gram pass over the rows of the last evaluation: J^T J, -J^T r and the ARAP / Rot terms into the store the decision
+// made current; returns at once on the device when the step was rejected.
+int launch_gram(const SbLMFrame* f, cudaStream_t st) {
     MatView M;
     M.A = nullptr; M.g = nullptr;        // chosen in the kernel from the device-resident selector
     M.lda = f->ldab; M.bw = f->bw; M.node_pos = f->node_pos; M.overflow = f->band_overflow;
-    M.shift = f->fx_shift; M.gshift = f->fx_gshift;
+    M.set_shift(f->fx_shift, f->fx_gshift);
     DataArgs a = make_args(f->points, f->knn_idx, f->knn_w, f->order, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
                            f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data);
-    FrameFuse ff;
-    ff.store[0] = reinterpret_cast<double*>(f->fx_store[0]);
-    ff.store[1] = reinterpret_cast<double*>(f->fx_store[1]);
-    ff.g_off = (long long)f->n * f->ldab;
-    ff.st = (LMState*)f->state;
-    ff.partials = f->partials_jtj;
-    ff.reg = RegArgs{f->ed_points, f->ed_knn, f->beta, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
-    ff.beta = f->beta; ff.best = f->best;
-    ff.adopt = adopt;
-    const int reg_threads = (f->use_arap ? f->J * SB_KNN : 0) + (f->use_rot ? f->J : 0);
-    ff.n_reg_blocks = (reg_threads + JTJ_WARPS * 32 - 1) / (JTJ_WARPS * 32);
+    GramArgs ga;
+    ga.store[0] = reinterpret_cast<double*>(f->fx_store[0]);
+    ga.store[1] = reinterpret_cast<double*>(f->fx_store[1]);
+    ga.g_off = (long long)f->n * f->ldab;
+    ga.st = (const LMState*)f->state;
+    ga.rows = f->rows; ga.keys = f->keys; ga.row_stride = f->row_stride;
+    ga.reg = RegArgs{f->ed_points, f->ed_knn, f->beta, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
+    ga.reg_threads = (f->use_arap ? f->J * SB_KNN : 0) + (f->use_rot ? f->J : 0);
     const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
     const int resident = jtj_resident<true>(smem);
     if (resident <= 0) return SB_ERR_CUDA;
     const int n_chunks = (f->n_cap + 31) / 32;
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
-    if (blocks > resident - ff.n_reg_blocks) blocks = resident - ff.n_reg_blocks;   // J^T J + regulariser blocks: one wave
+    const int reg_blocks = (ga.reg_threads + JTJ_WARPS * 32 - 1) / (JTJ_WARPS * 32);
+    if (blocks < reg_blocks) blocks = reg_blocks;          // enough lanes for the regularisers' items
+    if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    if (JTJ_WARPS * blocks > f->n_partials_jtj) return SB_ERR_WORKSPACE;
-    data_jtj_kernel<true><<<blocks + ff.n_reg_blocks, JTJ_WARPS * 32, smem, st>>>(a, M, nullptr, ff);
+    if (JTJ_WARPS * 32 * blocks < ga.reg_threads) return SB_ERR_WORKSPACE;
+    data_jtj_kernel<true><<<blocks, JTJ_WARPS * 32, smem, st>>>(a, M, nullptr, ga);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
 
 }  // namespace sbi
-

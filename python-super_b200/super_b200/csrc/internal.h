@@ -5,9 +5,8 @@
 
 namespace sbi {
 
-// data_term.cu: the J^T J pass of the frame loop (fixed-point target chosen on the device, regularisers in the trailing
-// blocks, per-warp loss partials, LM decision in the last block).  adopt != 0: prologue (no decision).
-int launch_jtj_fused(const SbLMFrame* f, int adopt, cudaStream_t st);
-int jtj_fused_partials(int n_cap);
+// data_term.cu: the two passes of the frame loop over the data term
+int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st);   // rows + keys + loss + LM decision (adopt: none)
+int launch_gram(const SbLMFrame* f, cudaStream_t st);                      // J^T J, -J^T r, ARAP / Rot into the current store
 
 }  // namespace sbi

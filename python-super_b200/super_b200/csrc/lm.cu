@@ -29,7 +29,7 @@ __global__ void lm_begin_kernel(LMState* st, double* beta, double* best, int J, 
                                 double minimal_loss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
-        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0; st->ticket = 0; st->sel = 0;
+        st->u = u; st->v = v; st->minimal_loss = minimal_loss; st->iter = 0; st->failed = 0; st->ticket = 0; st->sel = 0; st->last_accept = 0;
     }
     if (i < 7 * J) {
         const double val = (i % 7 == 0) ? 1.0 : 0.0;
@@ -92,7 +92,7 @@ int sb_reg_terms(const double* ed_points, const int* ed_knn, const double* beta,
     if (A && fx_shift >= 0 && (!band_overflow || fx_gshift < 0 || fx_shift > 60 || fx_gshift > 60)) return SB_ERR_ARG;
     MatView M;
     M.A = A; M.lda = lda; M.bw = bw; M.node_pos = node_pos; M.overflow = band_overflow; M.g = g;
-    M.shift = fx_shift >= 0 ? fx_shift : -1; M.gshift = fx_shift >= 0 ? fx_gshift : -1;
+    M.set_shift(fx_shift, fx_gshift);
     const int threads = (use_arap ? J * SB_KNN : 0) + (use_rot ? J : 0);
     if (threads == 0) return SB_OK;
     RegArgs ra{ed_points, ed_knn, beta, J, lam_arap, lam_rot, use_arap, use_rot};

@@ -13,8 +13,10 @@
 //     system and the one being assembled at the trial beta; LMState.sel says which is which, on the device.
 //   * band_from_fixed_kernel turns the current store into the f64 band the solver factors (the solver overwrites its
 //     input, so a copy is needed anyway) and clears the other store for the next assembly: no memset nodes, no side stream.
-// One iteration = 7 launches: from_fixed, band_reverse, band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
-// data_jtj<fused> (+ ARAP/Rot blocks + decision).  No host synchronisation, no allocation.
+//   * the data term runs as TWO launches: a high-occupancy evaluation pass that writes the Jacobian rows (and takes the
+//     LM decision in its last block) and a Gram pass that reads them back; after a reject the Gram pass returns at once.
+// One iteration = 8 launches: from_fixed, band_reverse, band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
+// data_eval_decide (+ decision), data_jtj<rows> (+ ARAP/Rot).  No host synchronisation, no allocation.
 #include "common.cuh"
 #include "lm_state.cuh"
 #include "internal.h"
@@ -59,7 +61,6 @@ int sb_band_from_fixed(const long long* store, int n, int ldab, int fx_shift, in
     return from_fixed(store, store, nullptr, n, ldab, fx_shift, fx_gshift, AB, g, 0, (cudaStream_t)stream);
 }
 
-int sb_lm_frame_partials(int n_cap) { return sbi::jtj_fused_partials(n_cap); }
 
 int sb_event_create(void** ev) {
     if (!ev) return SB_ERR_ARG;
@@ -75,10 +76,13 @@ int sb_event_elapsed_ms(void* ev_begin, void* ev_end, float* ms) {
     return cudaEventElapsedTime(ms, (cudaEvent_t)ev_begin, (cudaEvent_t)ev_end) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
+// k-th data-term pass of the frame: evaluation (+ decision) and Gram accumulation
 static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st) {
     const bool timed = f->jtj_events && 2 * k + 1 < f->n_jtj_events;
     if (timed && cudaEventRecord((cudaEvent_t)f->jtj_events[2 * k], st) != cudaSuccess) return SB_ERR_CUDA;
-    const int rc = sbi::launch_jtj_fused(f, adopt, st);
+    int rc = sbi::launch_eval_decide(f, adopt, st);
+    if (rc != SB_OK) return rc;
+    rc = sbi::launch_gram(f, st);
     if (rc != SB_OK) return rc;
     if (timed && cudaEventRecord((cudaEvent_t)f->jtj_events[2 * k + 1], st) != cudaSuccess) return SB_ERR_CUDA;
     return SB_OK;
@@ -86,14 +90,16 @@ static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st) {
 
 int sb_lm_frame(const SbLMFrame* f, void* stream) {
     if (!f || !f->points || !f->knn_idx || !f->knn_w || !f->ed_points || !f->ed_knn || !f->vmap || !f->nmap) return SB_ERR_ARG;
-    if (!f->state || !f->beta || !f->best || !f->partials_jtj || !f->partials_loss) return SB_ERR_ARG;
+    if (!f->state || !f->beta || !f->best || !f->partials_loss || !f->rows || !f->keys || f->row_stride < f->n_cap)
+        return SB_ERR_ARG;
     if (!f->fx_store[0] || !f->fx_store[1] || !f->AB || !f->g || !f->band_overflow || !f->dinv || !f->info || !f->solver_ws)
         return SB_ERR_ARG;
     if (f->J <= 0 || f->J > 65535 || f->n != 7 * f->J || f->bw < 0 || f->ldab < f->bw + 1 || f->iterations < 1 ||
         f->iterations > 64 || f->n_cap <= 0)
         return SB_ERR_ARG;
     if (f->fx_shift < 0 || f->fx_shift > 60 || f->fx_gshift < 0 || f->fx_gshift > 60) return SB_ERR_ARG;
-    if (f->n_partials_loss != sb_data_loss_blocks(f->n_cap)) return SB_ERR_WORKSPACE;
+    const int n_loss_blocks = sb_data_loss_blocks(f->n_cap);
+    if (f->n_partials_loss < n_loss_blocks) return SB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     LMState* state = (LMState*)f->state;
     const long long n_tot = (long long)f->n * f->ldab + f->n;
@@ -118,7 +124,7 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
         } else {      // after the last solve only the loss of the trial beta is needed
             rc = sb_data_term_loss_decide(f->points, f->knn_idx, f->knn_w, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
                                           f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data, f->partials_loss,
-                                          f->n_partials_loss, f->state, f->ed_knn, f->lam_arap, f->lam_rot, f->use_arap,
+                                          n_loss_blocks, f->state, f->ed_knn, f->lam_arap, f->lam_rot, f->use_arap,
                                           f->use_rot, f->beta, f->best, stream);
         }
         if (rc != SB_OK) return rc;

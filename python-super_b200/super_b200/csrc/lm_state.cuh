@@ -17,6 +17,7 @@ struct LMState {
     int accept[64];
     double u_trace[64];
     unsigned int ticket;  // blocks of the fused loss pass that have delivered their partial (self-resetting)
+    int last_accept;      // frame loop: 1 when the last decision accepted the step (the Gram pass then assembles), else 0
     int sel;              // frame loop (sb_lm_frame): which of the two fixed-point stores holds the normal equations of the
                           // CURRENT beta; the J^T J pass at a trial beta assembles into the other one, an accepted step flips
 };
@@ -61,7 +62,7 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
                                                double* beta, double* best, int n, RegLossArgs rg, bool flip_sel = false,
                                                bool adopt = false) {
     if (adopt) {
-        if (threadIdx.x == 0) st->sel ^= 1;
+        if (threadIdx.x == 0) { st->sel ^= 1; st->last_accept = 1; }
         return;
     }
     __shared__ double red[BLOCK / 32];
@@ -84,6 +85,7 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
         const int it = st->iter;
         if (st->failed) {
             s_accept = -1;
+            st->last_accept = 0;
         } else {
             const double la = rg.ed_points ? s_reg[0] : loss_arap_rot[0], lr = rg.ed_points ? s_reg[1] : loss_arap_rot[1];
             const double loss = s + la + lr;
@@ -97,6 +99,7 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
             if (acc) { st->minimal_loss = loss; st->u /= st->v; if (flip_sel) st->sel ^= 1; }
             else st->u *= st->v;
             st->iter = it + 1;
+            st->last_accept = acc ? 1 : 0;
             s_accept = acc ? 1 : 0;
         }
         if (loss_arap_rot) {

@@ -152,65 +152,51 @@ def extra_invalid_mask(opt, depth, seg=None, mask=None):
 
 # ---- ED graph (once per sequence) -------------------------------------------------------------------
 def build_graph(opt, frame):
-    """init_graph + DirectDeformGraph grid_mesh (/root/reference/super/graph_encoder.py:11-67,128-193)
-    from the dense maps.  Runs once per sequence: plain torch indexing on the device."""
+    """init_graph + DirectDeformGraph grid_mesh (/root/reference/super/graph_encoder.py:11-67,128-193) from the dense maps:
+    one launch (sb_graph_build, csrc/graph.cu), then update_ed (nodes.py:154-168).  One host read of the three counts."""
     H, W, s = frame.H, frame.W, opt.mesh_step_size
     dev = frame.vmap.device
-    valid = frame.valid.view(H, W)
-    us = torch.arange(0, W - 1, s, device=dev)
-    vs = torch.arange(0, H - 1, s, device=dev)
-    vv, uu = torch.meshgrid(vs, us, indexing="ij")
-    av = valid[vv, uu]
-    u, v = uu[av], vv[av]
-    J = int(u.numel())
-    nid = torch.full((H + s, W + s), -1, dtype=I64, device=dev)
-    nid[v, u] = torch.arange(J, device=dev)
-
-    a, r, d, rd = nid[v, u], nid[v, u + s], nid[v + s, u], nid[v + s, u + s]
-    e = torch.stack([torch.stack([a, r], 1), torch.stack([a, rd], 1), torch.stack([a, d], 1),
-                     torch.stack([r, d], 1)], 1).reshape(-1, 2)
-    e = e[(e >= 0).all(1)]
-    f = torch.stack([torch.stack([a, r, rd], 1), torch.stack([a, rd, d], 1)], 1).reshape(-1, 3)
-    f = f[(f >= 0).all(1)]
-    pix = v * W + u
+    l = lib.load()
+    G = int(l.sb_graph_anchors(H, W, s))
+    C = frame.seg_conf.shape[1] if frame.seg_conf is not None else 0
+    prune = bool(C) and bool(getattr(opt, "hard_seg", False)) and bool(opt.mesh_face)     # graph_encoder.py:141-149
+    ws = torch.zeros(3 * G, dtype=I32, device=dev)
+    points, norms = torch.zeros((G, 3), dtype=F64, device=dev), torch.zeros((G, 3), dtype=F64, device=dev)
+    uv = torch.zeros((G, 2), dtype=I32, device=dev)
+    seg = torch.zeros(G, dtype=I32, device=dev) if C else None
+    seg_conf = torch.zeros((G, C), dtype=F64, device=dev) if C else None
+    edges, faces = torch.zeros((4 * G, 2), dtype=I32, device=dev), torch.zeros((2 * G, 3), dtype=I32, device=dev)
+    lens, radii = torch.zeros(4 * G, dtype=F64, device=dev), torch.zeros(G, dtype=F64, device=dev)
+    areas = torch.zeros(2 * G, dtype=F64, device=dev)
+    node_pos, counts = torch.zeros(G, dtype=I32, device=dev), torch.zeros(3, dtype=I32, device=dev)
+    call("sb_graph_build", ptr(frame.vmap), ptr(frame.nmap), ptr(frame.seg_conf), C, H, W, s, int(prune), ptr(ws),
+         ptr(points), ptr(norms), ptr(uv), ptr(seg), ptr(seg_conf), ptr(edges), ptr(faces), ptr(lens), ptr(radii),
+         ptr(areas), ptr(node_pos), ptr(counts), stream())
+    J, E, Fc = (int(x) for x in counts.tolist())                # init only: a sync is fine here
+    if J < opt.num_ED_neighbors + 1:
+        raise lib.SuperB200Error(f"only {J} ED nodes on valid pixels: the graph needs more than num_ED_neighbors")
     g = NS()
-    g.points = frame.vmap[pix, :3].to(F64).contiguous()
-    g.norms = frame.nmap[pix, :3].to(F64).contiguous()
-    if frame.seg_conf is not None:                       # graph_encoder.py:134-150,190-192
-        g.seg_conf = frame.seg_conf[pix].contiguous()
-        g.seg = torch.argmax(g.seg_conf, dim=1)
-        if getattr(opt, "hard_seg", False) and opt.mesh_face:   # no edges / faces across classes
-            e = e[g.seg[e[:, 0]] == g.seg[e[:, 1]]]
-            f = f[(g.seg[f[:, 0]] == g.seg[f[:, 1]]) & (g.seg[f[:, 0]] == g.seg[f[:, 2]])]
-    g.edge_index, g.triangles = e.t().contiguous(), f.t().contiguous()
-    lens = torch.linalg.norm(g.points[e[:, 0]] - g.points[e[:, 1]], dim=1)
-    ssum = torch.zeros(J, dtype=F64, device=dev).index_add_(0, e.reshape(-1), lens.repeat_interleave(2))
-    cnt = torch.zeros(J, dtype=F64, device=dev).index_add_(0, e.reshape(-1), torch.ones(2 * len(e), dtype=F64, device=dev))
-    radii = ssum / cnt                                   # mean incident edge length; 0/0 -> NaN like .mean() of empty
-    bad = torch.isnan(radii)
-    radii = torch.where(bad, radii[~bad].mean(), radii)
-    g.radii = radii.contiguous()
-    g.edges_lens = lens
-    ta = torch.linalg.cross(g.points[f[:, 1]] - g.points[f[:, 0]], g.points[f[:, 2]] - g.points[f[:, 0]], dim=1)
-    g.triangles_areas = 0.5 * torch.sqrt((ta ** 2).sum(1) + 1e-13)
+    g.points, g.norms, g.radii = points[:J].contiguous(), norms[:J].contiguous(), radii[:J].contiguous()
+    g.anchor_uv, g.node_pos = uv[:J].to(I64), node_pos[:J].contiguous()
+    g.edge_index = edges[:E].t().to(I64).contiguous()
+    g.triangles = faces[:Fc].t().to(I64).contiguous()
+    g.triangles_i32 = faces[:Fc].t().contiguous()
+    g.edges_lens, g.triangles_areas = lens[:E].contiguous(), areas[:Fc].contiguous()
     g.num, g.param_num = J, 7 * J
-    g.triangles_i32 = g.triangles.to(I32).contiguous()
-    # Solver node order (no reference counterpart): nodes sorted along the LONGER image axis, so that the
-    # block half-bandwidth of J^T J is ~3 grid lines of the shorter axis (measured 42 vs 57 blocks at C1).
-    key = (u * (H + s) + v) if W >= H else (v * (W + s) + u)
-    order = torch.argsort(key)
-    g.node_pos = torch.empty(J, dtype=I32, device=dev)
-    g.node_pos[order] = torch.arange(J, dtype=I32, device=dev)
-    g.anchor_uv = torch.stack([u, v], 1)
+    if C:
+        g.seg_conf, g.seg_i32 = seg_conf[:J].contiguous(), seg[:J].contiguous()
+        g.seg = g.seg_i32.to(I64)
+    else:
+        g.seg_i32 = None
     # update_ed (/root/reference/super/nodes.py:154-168): K+1 nearest, drop self, weights use the query radius
-    g.seg_i32 = g.seg.to(I32).contiguous() if hasattr(g, "seg") else None
     hard = bool(getattr(opt, "hard_seg", False)) and g.seg_i32 is not None
     dist, idx = ops.knn(g.points, g.points, opt.num_ED_neighbors + 1, qseg=g.seg_i32 if hard else None,
                         rseg=g.seg_i32 if hard else None)                  # nodes.py:157-163
     g.knn_indices = idx[:, 1:].contiguous()
     g.knn_w = ops.knn_weights(dist[:, 1:].contiguous(), g.knn_indices, g.radii, radius_mode=1)
-    pos = g.node_pos.long()
-    g.block_bw_ed = int((pos[:, None] - pos[g.knn_indices.long()]).abs().max())     # ARAP pairs (init-time sync)
+    span = torch.zeros(1, dtype=I32, device=dev)
+    call("sb_graph_pair_span", ptr(g.knn_indices), ptr(g.node_pos), J, g.knn_indices.shape[1], ptr(span), stream())
+    g.block_bw_ed = int(span.item())                                        # ARAP pairs (init-time sync)
     return g
 
 
@@ -430,7 +416,7 @@ class Tracker:
                 self.event_sink["solve"] += list(zip(sev[0::2], sev[1::2]))
             beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, n_dev=self.cur.n_dev,
                                         order=order, band=self.band, cluster_size=self.cluster_size, jtj_events=jev,
-                                        solve_events=sev)
+                                        solve_events=sev, row_capacity=self.cap)
             self.last_beta = beta
             ops.warp_update(sfv.points, sfv.norms, sfv.knn_indices, sfv.knn_w, self.ED.points, self.ED.norms, beta,
                             n_dev=self.cur.n_dev)

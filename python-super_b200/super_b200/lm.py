@@ -33,7 +33,7 @@ class SbLMFrame(ctypes.Structure):
                 ("lam_data", _D), ("lam_arap", _D), ("lam_rot", _D), ("use_arap", _I), ("use_rot", _I),
                 ("iterations", _I), ("u", _D), ("v", _D), ("minimal_loss", _D),
                 ("state", _P), ("beta", _P), ("best", _P),
-                ("partials_jtj", _P), ("n_partials_jtj", _I), ("partials_loss", _P), ("n_partials_loss", _I),
+                ("partials_loss", _P), ("n_partials_loss", _I), ("rows", _P), ("keys", _P), ("row_stride", _I),
                 ("n", _I), ("bw", _I), ("ldab", _I), ("node_pos", _P), ("pos_node", _P),
                 ("fx_store", _P * 2), ("fx_shift", _I), ("fx_gshift", _I),
                 ("AB", _P), ("g", _P), ("band_overflow", _P), ("dinv", _P), ("info", _P),
@@ -54,7 +54,7 @@ class LMWorkspace:
         self.loss2 = torch.zeros(2, dtype=F64, device=device)
         self.state = ops.LMState(device)
         self.partials = None
-        self.partials_jtj = None
+        self.rows = self.keys = None        # Jacobian rows (29, stride) + node-set keys of the frame loop's evaluation pass
 
     @property
     def A(self):
@@ -75,19 +75,24 @@ def band_frame_ok(band, cluster_size):
 
 
 def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None, cluster_size=148,
-             jtj_events=None, solve_events=None):
+             jtj_events=None, solve_events=None, row_capacity=None):
     """The whole LM loop of one frame in one C call (sb_lm_frame).  Same arguments and result as lm_solve.
+    row_capacity: rows to size the Jacobian-row scratch for (the tracker passes its surfel capacity, so that the buffer
+    is allocated once per sequence).
     jtj_events: optional list of raw cudaEvent_t handles (2 per J^T J pass: begin, end) recorded around those launches."""
     ed = sf.ED
     J = ed.points.shape[0]
     dev = sf.points.device
     l = lib.load()
     n_cap = sf.points.shape[0]
-    nb = ops.data_loss_blocks(n_cap)
-    if ws.partials is None or ws.partials.numel() != nb:
-        ws.partials = torch.zeros(nb, dtype=F64, device=dev)
-    if ws.partials_jtj is None:
-        ws.partials_jtj = torch.zeros(int(l.sb_lm_frame_partials(n_cap)), dtype=F64, device=dev)
+    nb = max(1024, ops.data_loss_blocks(n_cap))
+    if getattr(ws, "partials_frame", None) is None or ws.partials_frame.numel() != nb:
+        ws.partials_frame = torch.zeros(nb, dtype=F64, device=dev)
+    if ws.keys is None or ws.keys.numel() < n_cap:
+        stride = max(n_cap, int(row_capacity or 0))
+        stride = (stride + 31) // 32 * 32
+        ws.rows = torch.empty((29, stride), dtype=F64, device=dev)
+        ws.keys = torch.empty(stride, dtype=torch.int64, device=dev)
     if getattr(band, "ws4", None) is None:
         band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8, device=dev)
     vmap, nmap = maps
@@ -101,8 +106,8 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
     f.use_arap, f.use_rot = int(bool(opt.mesh_arap)), int(bool(opt.mesh_rot))
     f.iterations, f.u, f.v, f.minimal_loss = int(opt.num_optimize_iterations), u, v, minimal_loss
     f.state, f.beta, f.best = ptr(ws.state.buf), ptr(ws.beta), ptr(ws.best)
-    f.partials_jtj, f.n_partials_jtj = ptr(ws.partials_jtj), ws.partials_jtj.numel()
-    f.partials_loss, f.n_partials_loss = ptr(ws.partials), ws.partials.numel()
+    f.partials_loss, f.n_partials_loss = ptr(ws.partials_frame), ws.partials_frame.numel()
+    f.rows, f.keys, f.row_stride = ptr(ws.rows), ptr(ws.keys), ws.keys.numel()
     f.n, f.bw, f.ldab = band.n, band.bw, band.ldab
     f.node_pos, f.pos_node = ptr(band.node_pos), ptr(band.pos_node)
     f.fx_store = (ctypes.c_void_p * 2)(ptr(band.fx[0]), ptr(band.fx[1]))
@@ -118,14 +123,14 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
             setattr(f, name + "_events", ctypes.cast(arr, ctypes.c_void_p))
             setattr(f, "n_" + name + "_events", len(evs))
     call("sb_lm_frame", ctypes.byref(f), stream())
-    lib.LAUNCHES += 2 + 7 * f.iterations        # lm_begin, first J^T J; per iteration from_fixed + 5 (solve) + J^T J | loss
+    lib.LAUNCHES += 2 + 8 * f.iterations        # lm_begin, eval, Gram; per iteration from_fixed + 5 (solve) + eval + Gram | loss
     band._dirty = False
     return ws.beta, ws
 
 
 
 def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
-             on_iter=None, band=None, cluster_size=16, jtj_events=None, solve_events=None):
+             on_iter=None, band=None, cluster_size=16, jtj_events=None, solve_events=None, row_capacity=None):
     """sf: object with points (N,3) f64, knn_indices (N,4) i32, knn_w (N,4) f64 and ED (points, knn_indices i32).
     maps: (vmap, nmap) dense float4 images of the new frame.  Returns beta (J,7) f64 (a view of the
     workspace) -- the same value LM_Solver.LM returns.
@@ -139,7 +144,7 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
     if (on_iter is None and band_frame_ok(band, cluster_size) and bool(opt.sf_point_plane)
             and os.environ.get("SB_LM_STEPWISE", "0") != "1"):
         return lm_frame(sf, maps, cam, opt, ws, band, u, v, minimal_loss, order, n_dev, cluster_size, jtj_events,
-                        solve_events)
+                        solve_events, row_capacity)
     n_cap = sf.points.shape[0]
     nb = ops.data_loss_blocks(n_cap)
     if ws.partials is None or ws.partials.numel() != nb:

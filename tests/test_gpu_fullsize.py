@@ -116,3 +116,41 @@ def test_one_tracked_frame_against_the_cpu_port(scene):
     p0, e0 = v.points.clone(), trk.ED.points.clone()
     ops.warp_update(v.points, v.norms, v.knn_indices, v.knn_w, trk.ED.points, trk.ED.norms, ident)
     assert float((v.points - p0).abs().max()) < 1e-15 and torch.equal(trk.ED.points, e0)
+
+
+@pytest.mark.parametrize("H,W,step,data,hard", [(480, 640, 32, "superv1", False), (480, 640, 16, "superv1", False),
+                                                (1024, 1280, 32, "superv1", False), (480, 640, 32, "superv2", True),
+                                                (96, 128, 8, "superv1", False), (200, 120, 16, "superv1", False)])
+def test_graph_build_kernel_matches_oracle(H, W, step, data, hard):
+    """sb_graph_build (one launch) against the oracle's init_graph / DirectDeformGraph restatement: node set, edge and
+    triangle lists and the solver order are integers (bit-exact); lengths, radii and areas to f64 rounding.  A hole is
+    cut into the depth so that some anchors are invalid and some nodes lose edges."""
+    from super_b200 import engine, synth
+    over = dict(height=H, width=W, mesh_step_size=step, data=data)
+    if hard:
+        over.update(method="semantic-super", num_classes=3, hard_seg=True, mesh_face=True, del_seg_classes=[])
+    opt = so.default_opt(**over)
+    f = synth.frame_inputs(3, H, W, data=data, with_seg=hard)
+    f["depth"] = f["depth"].copy()
+    f["depth"][0, H // 3: H // 3 + 2 * step + 5, W // 4: W // 4 + 3 * step + 7] = 0.0        # invalid block
+    nd = so.preprocess(opt, f)
+    ref = so.build_graph(opt, nd)
+    fr = engine.preprocess(opt, torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["color"]).cuda(),
+                           torch.from_numpy(f["K"]), torch.from_numpy(f["inv_K"]), f["time"],
+                           seg_scores=torch.from_numpy(f["seg_conf"]).cuda() if hard else None)
+    g = engine.build_graph(opt, fr)
+    assert g.num == ref.num
+    assert torch.equal(g.points.cpu(), ref.points) and torch.equal(g.norms.cpu(), ref.norms)
+    assert torch.equal(g.edge_index.cpu(), ref.edge_index)
+    assert torch.equal(g.triangles.cpu(), ref.triangles)
+    assert (g.edges_lens.cpu() - ref.edges_lens).abs().max() < 1e-15
+    assert (g.radii.cpu() - ref.radii).abs().max() < 1e-15
+    assert (g.triangles_areas.cpu() - ref.triangles_areas).abs().max() < 1e-15
+    if hard:
+        assert torch.equal(g.seg.cpu(), ref.seg)
+    # solver order: a permutation that sorts the nodes along the longer image axis
+    pos = g.node_pos.cpu().long()
+    assert torch.equal(torch.sort(pos).values, torch.arange(g.num))
+    uv = g.anchor_uv.cpu()
+    key = uv[:, 0] * (H + step) + uv[:, 1] if W >= H else uv[:, 1] * (W + step) + uv[:, 0]
+    assert torch.equal(torch.argsort(torch.argsort(key)), pos)
