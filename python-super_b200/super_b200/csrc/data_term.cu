@@ -181,66 +181,104 @@ __device__ __forceinline__ unsigned long long pack_key(const int* idx) {
     return key;
 }
 
-constexpr int FL_DOUBLES = 436;          // flush scratch: packed upper triangle (m <= n <= 28) of the Gram matrix, one per warp
+constexpr int FL_DOUBLES = 436 + 8;      // flush scratch per warp: packed upper triangle (m <= n <= 28) of the Gram matrix + 16 ints of bases
 
-// Flush one warp accumulator (10 tiles x 2 doubles per lane) into the lower-triangular A (dense or band,
-// common.cuh MatView), g (= -J^T r) and the optional sum r^2.  The tiles go through a shared 32x32 scratch and
-// a run-time loop over the 29x29 upper triangle: the fully unrolled version was 2 x 2.4 k instructions and made
-// the kernel miss the instruction cache (ncu r1c: "no instruction" stalls 3.0 per issue, as much as memory).
-// table of the 435 packed upper-triangle entries e -> (node slot, component) of its row m and column n:
-// km | cm << 3 | kn << 6 | cn << 9 with m = 7 km + cm, n = 7 kn + cn  (km = 4: the residual row/column 28).
-// Built once per CTA (ncu r1e: decoding m, n by sqrt + correction loops in every flush iteration was 115 instructions per
-// iteration and the flush 30 % of the kernel's issue slots and 32 % of its stall samples).
-__device__ __forceinline__ void build_flush_table(unsigned short* tab, int tid, int nthreads) {
+// Flush one warp accumulator (10 tiles x 2 doubles per lane) into the lower-triangular A (dense or band, common.cuh
+// MatView) and g (= -J^T r).  A flush costs the same whether the node set had 1 or 1 000 surfels and sits on the critical
+// path of the warp that meets many small node sets, so everything that can be is moved out of its per-entry loop:
+//   * per CTA, once: tables over the 435 packed upper-triangle entries e = (m, n), m = 7 km + cm, n = 7 kn + cn --
+//     which of the 10 node pairs (or 4 right-hand-side segments) the entry belongs to, and its offset inside that pair's
+//     7x7 block of the matrix in both orientations (cm L + cn and cn L + cm, L = the matrix' row pitch); and the packed
+//     position of every accumulator fragment (st_idx).
+//   * per flush, once: the 14 block origins -- lane p < 10 turns the solver positions of its node pair into the origin of
+//     that block in the lower triangle and the orientation (which node is the row), lanes 10..13 the origins in g.
+//   * per entry: two table reads, one select, one add, the atomic.
+// (ncu r2c: 135 instructions per entry and 1 900 per flush before; the warps with ~10 node-set changes in their 128
+// surfels set the kernel's duration.)
+struct FlushTables {
+    unsigned int off_a[435];     // cm * L + cn  (block stored with node km as the row)   | for g entries: cm
+    unsigned int off_b[435];     // cn * L + cm  (block stored with node kn as the row)
+    unsigned char pair[435];     // 0..9 node pair (km <= kn), 10..13 g segment of node km, 15 = the r^2 corner
+    unsigned short st_idx[20][32];   // accumulator fragment (tile t, element e) of lane l -> packed entry, 0xffff = outside
+};
+
+__device__ __forceinline__ void build_flush_tables(FlushTables& T, int tid, int nthreads, int L) {
     for (int e = tid; e < 435; e += nthreads) {
         int m = (int)((59.f - sqrtf(3481.f - 8.f * (float)e)) * 0.5f);
         while ((m + 1) * 29 - (m + 1) * m / 2 <= e) ++m;
         while (m * 29 - m * (m - 1) / 2 > e) --m;
         const int n = m + (e - (m * 29 - m * (m - 1) / 2));
         const int km = m / 7, cm = m - 7 * km, kn = n / 7, cn = n - 7 * kn;
-        tab[e] = (unsigned short)(km | (cm << 3) | (kn << 6) | (cn << 9));
+        if (kn == 4) {
+            T.pair[e] = (unsigned char)(km == 4 ? 15 : 10 + km);
+            T.off_a[e] = T.off_b[e] = (unsigned)cm;
+        } else {
+            T.pair[e] = (unsigned char)(km * 4 - km * (km - 1) / 2 + (kn - km));
+            T.off_a[e] = (unsigned)(cm * L + cn);
+            T.off_b[e] = (unsigned)(cn * L + cm);
+        }
+    }
+    for (int i = tid; i < 20 * 32; i += nthreads) {
+        const int t = i >> 6, el = (i >> 5) & 1, lane = i & 31;
+        int ti = 0, rem = t;                                    // tile t -> (ti, tj), ti <= tj, row-major over the 10 tiles
+        while (rem >= 4 - ti) { rem -= 4 - ti; ++ti; }
+        const int tj = ti + rem;
+        const int m = 8 * ti + (lane >> 2), n = 8 * tj + 2 * (lane & 3) + el;
+        T.st_idx[2 * t + el][lane] = (unsigned short)((m <= n && n <= 28) ? m * 29 - m * (m - 1) / 2 + (n - m) : 0xffff);
     }
 }
 
 template <int MODE>
 __device__ __forceinline__ void flush_acc(double (&acc)[10][2], unsigned long long key, int lane, const MatView& M,
-                                          double* loss_cur, double& warp_loss, double* __restrict__ St,
-                                          const unsigned short* __restrict__ tab) {
-    int t = 0;
+                                          double* loss_cur, double* __restrict__ St, const FlushTables& T) {
 #pragma unroll
-    for (int ti = 0; ti < 4; ++ti)
+    for (int t = 0; t < 10; ++t)
 #pragma unroll
-        for (int tj = ti; tj < 4; ++tj, ++t) {
-            const int m = 8 * ti + (lane >> 2);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int n = 8 * tj + 2 * (lane & 3) + e;
-                if (m <= n && n <= 28) St[m * 29 - m * (m - 1) / 2 + (n - m)] = acc[t][e];     // packed row m, column n
-                acc[t][e] = 0.0;
-            }
+        for (int e = 0; e < 2; ++e) {
+            const unsigned idx = T.st_idx[2 * t + e][lane];
+            if (idx != 0xffffu) St[idx] = acc[t][e];
+            acc[t][e] = 0.0;
         }
-    __syncwarp();
-    // the 435 entries (m <= n <= 28) of the upper triangle are dealt round-robin to the lanes (14 each).  Lane k < 4 looks
-    // up the solver position of node k once; everybody fetches the four of them by shuffle before the loop.
+    // block origins of this node set: lane k < 4 looks up the solver position of node k (ascending node id = the order of
+    // the row's blocks), lanes 0..9 turn their pair into (origin << 1 | orientation), lanes 10..13 the origins in g
+    int* bases = reinterpret_cast<int*>(St + 436);
     const int my_pos = (lane < 4) ? M.pos((int)(key >> (48 - 16 * lane)) & 0xffff) : 0;
-    const int p0 = __shfl_sync(0xffffffffu, my_pos, 0), p1 = __shfl_sync(0xffffffffu, my_pos, 1);
-    const int p2 = __shfl_sync(0xffffffffu, my_pos, 2), p3 = __shfl_sync(0xffffffffu, my_pos, 3);
-#pragma unroll 1
-    for (int e = lane; e < 435; e += 32) {
+    {
+        int a = 0, rem = lane;
+        while (a < 3 && rem >= 4 - a) { rem -= 4 - a; ++a; }
+        const int b2 = lane < 10 ? a + rem : 0;
+        const int pa = __shfl_sync(0xffffffffu, my_pos, lane < 10 ? a : (lane - 10) & 3);
+        const int pb = __shfl_sync(0xffffffffu, my_pos, b2);
+        int v;
+        if (lane < 10) {
+            const int pr = max(pa, pb), pc = min(pa, pb);        // row block = the later position: lower triangle
+            const bool as_a = pa > pb;                           // node a is the row: offsets cm L + cn; else cn L + cm
+            if (M.bw >= 0 && 7 * (pr - pc) + 6 > M.bw) {
+                v = -1;
+                atomicOr(M.overflow, 1);
+            } else {
+                const int L = M.bw < 0 ? M.lda : M.lda - 1;
+                v = ((7 * pr * L + 7 * pc + (M.bw < 0 ? 0 : M.bw)) << 1) | (as_a ? 0 : 1);
+            }
+        } else {
+            v = 7 * pa;
+        }
+        if (lane < 14) bases[lane] = v;
+    }
+    __syncwarp();
+#pragma unroll 2
+    for (int e = lane; e < 434; e += 32) {                       // entry 434 = sum r^2: dealt with below
         const double val = St[e];
         if (val == 0.0) continue;
-        const unsigned tb = tab[e];
-        const int km = tb & 7, cm = (tb >> 3) & 7, kn = (tb >> 6) & 7, cn = (tb >> 9) & 7;
-        const int pm = km == 0 ? p0 : km == 1 ? p1 : km == 2 ? p2 : p3;
-        if (kn == 4) {                       // column 28: -J^T r, and r^T r in the corner
-            if (km == 4) { warp_loss += val; if (loss_cur) atomicAdd(loss_cur, val); }   // entry 434: always lane 18
-            else M.add_g<MODE>(7 * pm + cm, -val);
-            continue;
+        const int p = T.pair[e];
+        const int base = bases[p];
+        if (p >= 10) {
+            M.put<MODE>(M.g + base + T.off_a[e], -val, M.gscale);
+        } else if (base >= 0) {
+            M.put<MODE>(M.A + (size_t)(base >> 1) + ((base & 1) ? T.off_b[e] : T.off_a[e]), val, M.scale);
         }
-        const int pn = kn == 0 ? p0 : kn == 1 ? p1 : kn == 2 ? p2 : p3;
-        const int gm = 7 * pm + cm, gn = 7 * pn + cn;
-        M.add<MODE>(max(gm, gn), min(gm, gn), val);
     }
+    if (loss_cur && lane == 18) atomicAdd(loss_cur, St[434]);
     __syncwarp();
 }
 
@@ -259,22 +297,13 @@ struct GramArgs {
     const double* rows;        // (29, row_stride) f64: column c of the Jacobian row of slot s at rows[c*row_stride + s]
     const unsigned long long* keys;   // (n,) node-set key per slot, ~0 = no correspondence
     int row_stride;
-    int reg_threads;           // ARAP pairs + Rot nodes: one item per lane of the LAST warps of the grid (the least loaded)
-    RegArgs reg;
 };
-
-// the regularisers' items, kept out of line (and its arguments BY VALUE: a reference would force the kernel's copy of M
-// into local memory for the whole kernel) so that their registers and local arrays do not weigh on the chunk loop
-__device__ __noinline__ void gram_reg_item(RegArgs reg, MatView M, int tid) {
-    double la, lr;
-    reg_terms_item(reg, tid, M, true, la, lr);
-}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
 data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
     extern __shared__ double smem[];
-    __shared__ unsigned short fl_tab[448];
+    __shared__ FlushTables fl_tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (SPLIT) {
         if (!f.st->last_accept) return;             // rejected step: the current system is kept, nothing to assemble
@@ -284,7 +313,7 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
     double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
     double* St = Jt + JT_DOUBLES;
     for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
-    build_flush_table(fl_tab, threadIdx.x, JTJ_WARPS * 32);
+    build_flush_tables(fl_tab, threadIdx.x, JTJ_WARPS * 32, M.bw < 0 ? M.lda : M.lda - 1);
     __syncthreads();
 
     const int n = n_active(a.n_cap, a.n_dev);
@@ -299,7 +328,6 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
     for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
     unsigned long long acc_key = 0;
     bool have = false;
-    double warp_loss = 0.0;
 
     // one extra "tail" pass with a sentinel key flushes the last accumulator through the same code as a tuple
     // change inside the loop (a single inlined copy of the flush)
@@ -339,7 +367,7 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
             const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
             const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
             if (!have || k != acc_key) {
-                if (have) flush_acc<SPLIT ? 1 : 0>(acc, acc_key, lane, M, loss_cur, warp_loss, St, fl_tab);
+                if (have) flush_acc<SPLIT ? 1 : 0>(acc, acc_key, lane, M, loss_cur, St, fl_tab);
                 acc_key = k;
                 have = !tail;
             }
@@ -362,10 +390,6 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
             remaining = tail ? 0u : (remaining & ~m);
         }
         __syncwarp();
-    }
-    if (SPLIT) {
-        const int tid = (total_warps - 1 - gw) * 32 + lane;         // warp-uniform condition
-        if ((total_warps - 1 - gw) * 32 < f.reg_threads) gram_reg_item(f.reg, M, tid);
     }
 }
 
@@ -391,16 +415,34 @@ __global__ void __launch_bounds__(LOSS_BLOCK) data_loss_kernel(DataArgs a, doubl
 // of every slot is written out for the Gram pass (data_jtj_kernel<true>).
 struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; int flip_sel; int adopt; };
 struct RowsOut { double* rows; unsigned long long* keys; int row_stride; };
+// The regularisers of the frame loop ride in the evaluation launch: its FIRST reg_blocks blocks assemble the ARAP / Rot
+// normal-equation terms at the pass' beta (one item per thread, ~5 k instructions of straight-line atomics: 20-30 us for
+// the one warp that runs them, which is why they are given blocks of their own instead of a place behind a surfel loop)
+// into the store that is NOT current -- the one the Gram pass fills if the step is accepted; after a reject that store is
+// cleared again by band_from_fixed_kernel before it is next used.
+struct RegAsm { RegArgs reg; MatView M; double* store[2]; long long g_off; int reg_blocks; };
+__device__ __noinline__ void eval_reg_item(RegArgs reg, MatView M, int tid) {     // by value: see data_jtj_kernel
+    double la, lr;
+    reg_terms_item(reg, tid, M, true, la, lr);
+}
 constexpr int EVAL_BLOCK = 128;          // ROWS: 128 threads x 5 blocks per SM at <= 102 registers (20 warps, no spills)
 template <bool ROWS>
 __global__ void __launch_bounds__(ROWS ? EVAL_BLOCK : LOSS_BLOCK, ROWS ? 5 : 4)
-data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d, RowsOut ro) {
+data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d, RowsOut ro, RegAsm ra) {
     constexpr int BLOCK = ROWS ? EVAL_BLOCK : LOSS_BLOCK;
     __shared__ double red[BLOCK / 32];
     __shared__ bool s_last;
     const int n = n_active(a.n_cap, a.n_dev);
     double s = 0.0;
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+    const int rb = ROWS ? ra.reg_blocks : 0;
+    if (ROWS && (int)blockIdx.x < rb) {
+        MatView M = ra.M;
+        M.A = ra.store[1 - d.st->sel];
+        M.g = M.A + ra.g_off;
+        eval_reg_item(ra.reg, M, blockIdx.x * BLOCK + threadIdx.x);
+    }
+    for (int i = ((int)blockIdx.x - rb) * BLOCK + threadIdx.x; i < n && (int)blockIdx.x >= rb;
+         i += ((int)gridDim.x - rb) * BLOCK) {
         Eval ev;
         if (ROWS) {
             const int sid = a.order ? a.order[i] : i;
@@ -586,7 +628,8 @@ int sb_data_term_loss_decide(const double* points, const int* knn_idx, const dou
     d.st = (LMState*)state; d.beta = beta; d.best = best; d.n = 7 * J;
     d.rg = RegLossArgs{ed_points, ed_knn, J, lam_arap, lam_rot, use_arap, use_rot};
     d.flip_sel = 0; d.adopt = 0;
-    data_eval_decide_kernel<false><<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials, d, RowsOut{nullptr, nullptr, 0});
+    data_eval_decide_kernel<false><<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials, d, RowsOut{nullptr, nullptr, 0},
+                                                                                  RegAsm{});
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -632,20 +675,30 @@ int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st) {
     d.st = (LMState*)f->state; d.beta = f->beta; d.best = f->best; d.n = 7 * f->J;
     d.rg = RegLossArgs{f->ed_points, f->ed_knn, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
     d.flip_sel = 1; d.adopt = adopt;
-    int blocks = (f->n_cap + EVAL_BLOCK - 1) / EVAL_BLOCK;
+    RegAsm ra;
+    ra.reg = RegArgs{f->ed_points, f->ed_knn, f->beta, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
+    ra.M.A = nullptr; ra.M.g = nullptr;
+    ra.M.lda = f->ldab; ra.M.bw = f->bw; ra.M.node_pos = f->node_pos; ra.M.overflow = f->band_overflow;
+    ra.M.set_shift(f->fx_shift, f->fx_gshift);
+    ra.store[0] = reinterpret_cast<double*>(f->fx_store[0]);
+    ra.store[1] = reinterpret_cast<double*>(f->fx_store[1]);
+    ra.g_off = (long long)f->n * f->ldab;
+    const int reg_threads = (f->use_arap ? f->J * SB_KNN : 0) + (f->use_rot ? f->J : 0);
+    ra.reg_blocks = (reg_threads + EVAL_BLOCK - 1) / EVAL_BLOCK;
+    int blocks = (f->n_cap + EVAL_BLOCK - 1) / EVAL_BLOCK + ra.reg_blocks;
     const int resident = eval_resident();
     if (resident <= 0) return SB_ERR_CUDA;
-    if (blocks > resident) blocks = resident;
+    if (blocks > resident && resident > 2 * ra.reg_blocks) blocks = resident;     // one wave: regulariser + surfel blocks
     if (blocks > f->n_partials_loss) blocks = f->n_partials_loss;
-    if (blocks < 1) blocks = 1;
+    if (blocks <= ra.reg_blocks) return SB_ERR_WORKSPACE;
     data_eval_decide_kernel<true><<<blocks, EVAL_BLOCK, 0, st>>>(a, f->partials_loss, d,
-                                                                RowsOut{f->rows, f->keys, f->row_stride});
+                                                                RowsOut{f->rows, f->keys, f->row_stride}, ra);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
 
-// Gram pass over the rows of the last evaluation: J^T J, -J^T r and the ARAP / Rot terms into the store the decision
-// made current; returns at once on the device when the step was rejected.
+// Gram pass over the rows of the last evaluation: J^T J and -J^T r into the store the decision made current (the
+// regularisers' terms are already there); returns at once on the device when the step was rejected.
 int launch_gram(const SbLMFrame* f, cudaStream_t st) {
     MatView M;
     M.A = nullptr; M.g = nullptr;        // chosen in the kernel from the device-resident selector
@@ -659,18 +712,13 @@ int launch_gram(const SbLMFrame* f, cudaStream_t st) {
     ga.g_off = (long long)f->n * f->ldab;
     ga.st = (const LMState*)f->state;
     ga.rows = f->rows; ga.keys = f->keys; ga.row_stride = f->row_stride;
-    ga.reg = RegArgs{f->ed_points, f->ed_knn, f->beta, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
-    ga.reg_threads = (f->use_arap ? f->J * SB_KNN : 0) + (f->use_rot ? f->J : 0);
     const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
     const int resident = jtj_resident<true>(smem);
     if (resident <= 0) return SB_ERR_CUDA;
     const int n_chunks = (f->n_cap + 31) / 32;
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
-    const int reg_blocks = (ga.reg_threads + JTJ_WARPS * 32 - 1) / (JTJ_WARPS * 32);
-    if (blocks < reg_blocks) blocks = reg_blocks;          // enough lanes for the regularisers' items
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    if (JTJ_WARPS * 32 * blocks < ga.reg_threads) return SB_ERR_WORKSPACE;
     data_jtj_kernel<true><<<blocks, JTJ_WARPS * 32, smem, st>>>(a, M, nullptr, ga);
     SB_CHECK_LAUNCH();
     return SB_OK;
