@@ -102,7 +102,11 @@ typedef struct SbLMFrame {
     int n_partials_loss;
     double* rows;               /* (29, row_stride) f64 scratch: Jacobian rows of the last evaluation pass */
     unsigned long long* keys;   /* (row_stride,) u64 scratch: node-set key per slot */
-    int row_stride;             /* >= n_cap */
+    int row_stride;             /* >= n_cap, multiple of 32 */
+    double* rec_vals;           /* (rec_cap, 436) f64 scratch: Gram records of the pass (one per node-set run and warp) */
+    unsigned long long* rec_keys;   /* (rec_cap,) u64 */
+    int* rec_count;             /* device counter */
+    int rec_cap;                /* suggested: 2 * ceil(n_cap / 32) + 4096; beyond it warps add their accumulators directly */
     /* normal equations, band storage in the solver's node order */
     int n, bw, ldab;            /* n = 7J, half bandwidth, row stride (>= bw+1) */
     const int* node_pos;        /* node id -> solver position, or NULL */
@@ -236,7 +240,7 @@ int sb_band_from_fixed(const long long* store, int n, int ldab, int fx_shift, in
 
 /* LM_Solver.LM, the whole loop of one frame: /root/reference/super/LM.py:81-122 (prepareCostTerm :53-79, Solver :38-51)
  * over DataLoss / ARAPLoss / RotLoss (/root/reference/super/loss.py:207-499), band path.  Enqueues
- * 3 + 8*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
+ * 4 + 9*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
  * result and the controller state the per-iteration trace (sb_lm_state_offsets).  A failed factorisation stops the
  * updates and leaves the last accepted beta (LM.py:99-103).  Bitwise reproducible. */
 /* CUDA events for timing launches inside sb_lm_frame on the stream they run on (bench.py's roofline) */

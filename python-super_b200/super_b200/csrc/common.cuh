@@ -108,10 +108,14 @@ struct MatView {
     template <int MODE = 0>
     __device__ __forceinline__ void put(double* p, double v, double sc) const {
         if (MODE == 0 && sc == 0.0) {
-            atomicAdd(p, v);
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
         } else {
             const double sv = v * sc;
-            if (fabs(sv) < 4.6e18) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double2ll_rn(sv));
+            // red.global: fire-and-forget.  atomicAdd on the (generic) pointer compiles to a synchronous ATOM + a
+            // shared-window test whose round trip the warp waits for -- 14 of them in a row made a flush cost ~10 k
+            // cycles (ncu r2c-r2f: the Gram pass at 65-90 us for ~20 us of loads and products).
+            if (fabs(sv) < 4.6e18)
+                asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(__double2ll_rn(sv)) : "memory");
             else atomicOr(overflow, 2);
         }
     }

@@ -297,19 +297,24 @@ struct GramArgs {
     const double* rows;        // (29, row_stride) f64: column c of the Jacobian row of slot s at rows[c*row_stride + s]
     const unsigned long long* keys;   // (n,) node-set key per slot, ~0 = no correspondence
     int row_stride;
+    // Gram records: instead of walking the 434 matrix entries of a finished accumulator itself (~900 instructions on the
+    // critical path of the warp; warps that meet 5-7 node sets in their 128 surfels set the pass' duration), a warp
+    // dumps the accumulator as one RECORD (fragment order -> packed upper triangle, 20 predicated stores per lane) and
+    // moves on; jtj_scatter_kernel adds all records into the store with one thread per entry.  The adds are integer, so
+    // neither the order in which records are claimed nor the order in which they are scattered changes the result.
+    double* rec_vals;          // (rec_cap, REC_STRIDE) f64
+    unsigned long long* rec_keys;   // (rec_cap,)
+    int* rec_count;            // records claimed in this pass (zeroed by the evaluation pass' deciding block)
+    int rec_cap;               // beyond it a warp falls back to adding its accumulator directly
 };
+constexpr int REC_STRIDE = 436;
 
-template <bool SPLIT>
+// Stand-alone J^T J pass (sb_data_term_jtj): evaluation and Gram products in one launch, rows staged in a shared panel.
 __global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
-data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
+data_jtj_kernel(DataArgs a, MatView M, double* loss_cur) {
     extern __shared__ double smem[];
     __shared__ FlushTables fl_tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (SPLIT) {
-        if (!f.st->last_accept) return;             // rejected step: the current system is kept, nothing to assemble
-        M.A = f.store[f.st->sel];
-        M.g = M.A + f.g_off;
-    }
     double* Jt = smem + warp * (JT_DOUBLES + FL_DOUBLES);
     double* St = Jt + JT_DOUBLES;
     for (int c = 29; c < 32; ++c) Jt[c * JT_STRIDE + lane] = 0.0;   // padding columns stay zero
@@ -336,29 +341,17 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
         const int slot = c * 32 + lane;
         bool matched = false;
         unsigned long long key = ~0ull;
-        if (SPLIT) {
-            if (!tail && slot < n) key = f.keys[slot];
-            matched = key != ~0ull;
-            double v[29];
+        Eval ev;
+        if (!tail && slot < n) {
+            const int sid = a.order ? a.order[slot] : slot;
+            matched = eval_surfel<true, true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
+        }
+        if (matched) {
+            Jt[28 * JT_STRIDE + lane] = ev.r;
+            key = pack_key(ev.idx);
+        } else if (!tail) {
 #pragma unroll
-            for (int col = 0; col < 29; ++col) v[col] = matched ? __ldcg(f.rows + (size_t)col * f.row_stride + slot) : 0.0;
-            if (!tail) {
-#pragma unroll
-                for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = v[col];
-            }
-        } else {
-            Eval ev;
-            if (!tail && slot < n) {
-                const int sid = a.order ? a.order[slot] : slot;
-                matched = eval_surfel<true, true>(a, sid, ev, Jt + lane, JT_STRIDE);   // row -> panel column `lane`
-            }
-            if (matched) {
-                Jt[28 * JT_STRIDE + lane] = ev.r;
-                key = pack_key(ev.idx);
-            } else if (!tail) {
-#pragma unroll
-                for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
-            }
+            for (int col = 0; col < 29; ++col) Jt[col * JT_STRIDE + lane] = 0.0;
         }
         __syncwarp();
         unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
@@ -367,7 +360,7 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
             const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
             const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
             if (!have || k != acc_key) {
-                if (have) flush_acc<SPLIT ? 1 : 0>(acc, acc_key, lane, M, loss_cur, St, fl_tab);
+                if (have) flush_acc<0>(acc, acc_key, lane, M, loss_cur, St, fl_tab);
                 acc_key = k;
                 have = !tail;
             }
@@ -393,6 +386,152 @@ data_jtj_kernel(DataArgs a, MatView M, double* loss_cur, GramArgs f) {
     }
 }
 
+// Gram pass of the frame loop: the rows of the last evaluation pass (SoA, rows[c * row_stride + slot]) are the operands
+// of the FP64 tensor-core products AS THEY LIE IN MEMORY -- the m8n8k4 A/B fragment of k-step ks and tile t is
+// rows[(8 t + lane/4) * stride + 32 chunk + 4 ks + lane%4]: the four lanes of a row read one full 32-byte sector, so a
+// fragment load uses every byte it moves and no shared-memory panel, no staging stores and no barrier is needed.  All 32
+// fragment loads of a chunk are issued before its 80 products (64 registers in flight per lane).
+__global__ void __launch_bounds__(JTJ_WARPS * 32, 4)
+jtj_gram_kernel(int n_cap, const int* __restrict__ n_dev, MatView M, GramArgs f) {
+    extern __shared__ double smem[];
+    __shared__ FlushTables fl_tab;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!f.st->last_accept) return;             // rejected step: the current system is kept, nothing to assemble
+    M.A = f.store[f.st->sel];
+    M.g = M.A + f.g_off;
+    double* St = smem + warp * FL_DOUBLES;
+    build_flush_tables(fl_tab, threadIdx.x, JTJ_WARPS * 32, M.bw < 0 ? M.lda : M.lda - 1);
+    __syncthreads();
+
+    const int n = n_active(n_cap, n_dev);
+    const int n_chunks = (n + 31) >> 5;
+    const int total_warps = gridDim.x * JTJ_WARPS;
+    const int gw = blockIdx.x * JTJ_WARPS + warp;
+    const int per = (n_chunks + total_warps - 1) / total_warps;
+    const int c0 = gw * per, c1 = min(n_chunks, c0 + per);
+
+    double acc[10][2];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
+    unsigned long long acc_key = 0;
+    bool have = false;
+    const int frow = lane >> 2, fcol = lane & 3;
+
+    // the key of the NEXT chunk is fetched one iteration ahead: its latency would otherwise sit in front of the fragment
+    // loads of every chunk (ncu r2g: the shuffle that first uses the key was the kernel's top stall)
+    unsigned long long key_next = (c0 < c1 && c0 * 32 + lane < n) ? __ldcg(f.keys + c0 * 32 + lane) : ~0ull;
+    for (int c = c0; c <= c1; ++c) {
+        const bool tail = (c == c1);
+        const unsigned long long key = tail ? ~0ull : key_next;
+        key_next = (c + 1 < c1 && (c + 1) * 32 + lane < n) ? __ldcg(f.keys + (c + 1) * 32 + lane) : ~0ull;
+        const bool matched = key != ~0ull;
+        unsigned remaining = tail ? (have ? 1u : 0u) : __ballot_sync(0xffffffffu, matched);
+        // fragments of the whole chunk: x[ks][t] = row 8t + frow, surfel 4ks + fcol  (rows 29..31 do not exist: zero).
+        // Slots >= n or without correspondence hold stale values: they are masked by select below, never multiplied.
+        double x[8][4];
+        if (remaining && !tail) {
+            const double* src = f.rows + (size_t)frow * f.row_stride + (size_t)c * 32 + fcol;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    x[ks][t] = (8 * t + frow < 29) ? __ldcg(src + (size_t)(8 * t) * f.row_stride + 4 * ks) : 0.0;
+        }
+        while (remaining) {
+            const int leader = __ffs(remaining) - 1;
+            const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);      // tail: the sentinel ~0
+            const unsigned m = tail ? 0u : (__ballot_sync(0xffffffffu, key == k) & remaining);
+            if (!have || k != acc_key) {
+                if (have) {
+                    int rec = 0;
+                    if (lane == 0) rec = atomicAdd(f.rec_count, 1);
+                    rec = __shfl_sync(0xffffffffu, rec, 0);
+                    if (rec < f.rec_cap) {
+                        if (lane == 0) f.rec_keys[rec] = acc_key;
+                        double* out = f.rec_vals + (size_t)rec * REC_STRIDE;
+                        int t = 0;
+#pragma unroll
+                        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                            for (int tj = ti; tj < 4; ++tj, ++t) {
+                                const int mm = 8 * ti + frow;
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int nn = 8 * tj + 2 * fcol + e;
+                                    if (mm <= nn && nn <= 28) __stcg(out + mm * 29 - mm * (mm - 1) / 2 + (nn - mm), acc[t][e]);
+                                    acc[t][e] = 0.0;
+                                }
+                            }
+                    } else {
+                        flush_acc<1>(acc, acc_key, lane, M, nullptr, St, fl_tab);
+                    }
+                }
+                acc_key = k;
+                have = !tail;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const unsigned m4 = (m >> (4 * ks)) & 0xfu;
+                if (m4 == 0u) continue;   // warp-uniform
+                const bool keep = (m4 >> fcol) & 1u;          // surfels of other node sets in this k-step are masked out
+                double y[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) y[t] = keep ? x[ks][t] : 0.0;
+                int t = 0;
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                    for (int tj = ti; tj < 4; ++tj, ++t) dmma884(acc[t][0], acc[t][1], y[ti], y[tj]);
+            }
+            remaining = tail ? 0u : (remaining & ~m);
+        }
+    }
+}
+
+// entry e of the packed upper triangle -> (pair 0..9 | g segment 10..13 | 15 = r^2 corner, cm, cn): built once per block
+__device__ __forceinline__ void build_entry_codes(unsigned short* code, int tid, int nthreads) {
+    for (int e = tid; e < 435; e += nthreads) {
+        int m = (int)((59.f - sqrtf(3481.f - 8.f * (float)e)) * 0.5f);
+        while ((m + 1) * 29 - (m + 1) * m / 2 <= e) ++m;
+        while (m * 29 - m * (m - 1) / 2 > e) --m;
+        const int n = m + (e - (m * 29 - m * (m - 1) / 2));
+        const int km = m / 7, cm = m - 7 * km, kn = n / 7, cn = n - 7 * kn;
+        code[e] = (unsigned short)(km | (cm << 3) | (kn << 6) | (cn << 9));
+    }
+}
+
+// One thread per (record, entry): adds the Gram records of the pass into the current store.
+__global__ void __launch_bounds__(256) jtj_scatter_kernel(MatView M, GramArgs f) {
+    __shared__ unsigned short code[448];
+    if (!f.st->last_accept) return;
+    M.A = f.store[f.st->sel];
+    M.g = M.A + f.g_off;
+    build_entry_codes(code, threadIdx.x, 256);
+    __syncthreads();
+    const int n_rec = min(*f.rec_count, f.rec_cap);
+    const long long total = (long long)n_rec * REC_STRIDE;
+    const int L = M.bw < 0 ? M.lda : M.lda - 1, bwoff = M.bw < 0 ? 0 : M.bw;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int rec = (int)(i / REC_STRIDE), e = (int)(i - (long long)rec * REC_STRIDE);
+        if (e >= 434) continue;                              // 434 = sum r^2 (the evaluation pass owns the loss), 435 = pad
+        const double val = __ldcg(f.rec_vals + i);
+        if (val == 0.0) continue;
+        const unsigned long long key = __ldg(f.rec_keys + rec);
+        const unsigned c = code[e];
+        const int km = c & 7, cm = (c >> 3) & 7, kn = (c >> 6) & 7, cn = (c >> 9) & 7;
+        const int pm = M.pos((int)(key >> (48 - 16 * km)) & 0xffff);
+        if (kn == 4) {
+            M.put<1>(M.g + 7 * pm + cm, -val, M.gscale);
+            continue;
+        }
+        const int pn = M.pos((int)(key >> (48 - 16 * kn)) & 0xffff);
+        const int gm = 7 * pm + cm, gn = 7 * pn + cn;
+        const int row = max(gm, gn), col = min(gm, gn);
+        if (M.bw >= 0 && row - col > M.bw) { atomicOr(M.overflow, 1); continue; }
+        M.put<1>(M.A + (size_t)row * L + col + bwoff, val, M.scale);
+    }
+}
+
 constexpr int LOSS_BLOCK = 256;
 
 // Loss-only pass (DataLoss.forward(grad=False)): sum r^2, one deterministic partial per block.
@@ -413,7 +552,7 @@ __global__ void __launch_bounds__(LOSS_BLOCK) data_loss_kernel(DataArgs a, doubl
 // and runs lm_decide_body (lm_state.cuh) -- what sb_lm_decide_reg does as a launch of its own.
 // ROWS: the evaluation pass of the frame loop -- slots of the visiting order instead of surfel ids, and the Jacobian row
 // of every slot is written out for the Gram pass (data_jtj_kernel<true>).
-struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; int flip_sel; int adopt; };
+struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; int flip_sel; int adopt; int* rec_count; };
 struct RowsOut { double* rows; unsigned long long* keys; int row_stride; };
 // The regularisers of the frame loop ride in the evaluation launch: its FIRST reg_blocks blocks assemble the ARAP / Rot
 // normal-equation terms at the pass' beta (one item per thread, ~5 k instructions of straight-line atomics: 20-30 us for
@@ -421,9 +560,9 @@ struct RowsOut { double* rows; unsigned long long* keys; int row_stride; };
 // into the store that is NOT current -- the one the Gram pass fills if the step is accepted; after a reject that store is
 // cleared again by band_from_fixed_kernel before it is next used.
 struct RegAsm { RegArgs reg; MatView M; double* store[2]; long long g_off; int reg_blocks; };
-__device__ __noinline__ void eval_reg_item(RegArgs reg, MatView M, int tid) {     // by value: see data_jtj_kernel
+__device__ __noinline__ void eval_reg_item(const RegArgs* reg, const MatView* M, int tid) {   // both in SHARED memory
     double la, lr;
-    reg_terms_item(reg, tid, M, true, la, lr);
+    reg_terms_item(*reg, tid, *M, true, la, lr);
 }
 constexpr int EVAL_BLOCK = 128;          // ROWS: 128 threads x 5 blocks per SM at <= 102 registers (20 warps, no spills)
 template <bool ROWS>
@@ -436,10 +575,18 @@ data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d,
     double s = 0.0;
     const int rb = ROWS ? ra.reg_blocks : 0;
     if (ROWS && (int)blockIdx.x < rb) {
-        MatView M = ra.M;
-        M.A = ra.store[1 - d.st->sel];
-        M.g = M.A + ra.g_off;
-        eval_reg_item(ra.reg, M, blockIdx.x * BLOCK + threadIdx.x);
+        // arguments through shared memory: taking the address of a kernel parameter would move the whole parameter
+        // block into local memory for every thread of the launch
+        __shared__ RegArgs s_reg;
+        __shared__ MatView s_M;
+        if (threadIdx.x == 0) {
+            s_reg = ra.reg;
+            s_M = ra.M;
+            s_M.A = ra.store[1 - d.st->sel];
+            s_M.g = s_M.A + ra.g_off;
+        }
+        __syncthreads();
+        eval_reg_item(&s_reg, &s_M, (int)(blockIdx.x * BLOCK + threadIdx.x));
     }
     for (int i = ((int)blockIdx.x - rb) * BLOCK + threadIdx.x; i < n && (int)blockIdx.x >= rb;
          i += ((int)gridDim.x - rb) * BLOCK) {
@@ -467,6 +614,7 @@ data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d,
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (d.rec_count && threadIdx.x == 0) *d.rec_count = 0;       // Gram records of the pass that follows
     lm_decide_body<BLOCK>(d.st, partials, (int)gridDim.x, nullptr, d.beta, d.best, d.n, d.rg, d.flip_sel != 0,
                           d.adopt != 0);
 }
@@ -540,20 +688,21 @@ DataArgs make_args(const double* points, const int* knn_idx, const double* knn_w
 
 // One resident wave of the J^T J kernel on the current device (a partial second wave was a 40 % tail, ncu r1), and the
 // kernel's shared-memory opt-in: both are per DEVICE, so the cache is indexed by the device ordinal.
-template <bool FUSED>
-static int jtj_resident(size_t smem) {
-    static int resident[64] = {0};
+template <typename K>
+static int jtj_resident(K kernel, size_t smem, int which) {
+    static int resident[2][64] = {{0}};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-    if (resident[dev] == 0) {
+    if (resident[which][dev] == 0) {
         int per_sm = 0, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(data_jtj_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_jtj_kernel<FUSED>, JTJ_WARPS * 32, smem);
-        resident[dev] = (per_sm > 0 ? per_sm : 1) * sms;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, JTJ_WARPS * 32, smem);
+        resident[which][dev] = (per_sm > 0 ? per_sm : 1) * sms;
     }
-    return resident[dev];
+    return resident[which][dev];
 }
 
 extern "C" {
@@ -590,13 +739,12 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
                            intr, lambda);
     const int n_chunks = (n_cap + 31) / 32;
     const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
-    const int resident = jtj_resident<false>(smem);
+    const int resident = jtj_resident(data_jtj_kernel, smem, 0);
     if (resident <= 0) return SB_ERR_CUDA;
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    GramArgs none{};
-    data_jtj_kernel<false><<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, loss_cur, none);
+    data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, loss_cur);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -627,7 +775,7 @@ int sb_data_term_loss_decide(const double* points, const int* knn_idx, const dou
     DecideArgs d;
     d.st = (LMState*)state; d.beta = beta; d.best = best; d.n = 7 * J;
     d.rg = RegLossArgs{ed_points, ed_knn, J, lam_arap, lam_rot, use_arap, use_rot};
-    d.flip_sel = 0; d.adopt = 0;
+    d.flip_sel = 0; d.adopt = 0; d.rec_count = nullptr;
     data_eval_decide_kernel<false><<<n_partials, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, partials, d, RowsOut{nullptr, nullptr, 0},
                                                                                   RegAsm{});
     SB_CHECK_LAUNCH();
@@ -674,7 +822,7 @@ int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st) {
     DecideArgs d;
     d.st = (LMState*)f->state; d.beta = f->beta; d.best = f->best; d.n = 7 * f->J;
     d.rg = RegLossArgs{f->ed_points, f->ed_knn, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
-    d.flip_sel = 1; d.adopt = adopt;
+    d.flip_sel = 1; d.adopt = adopt; d.rec_count = f->rec_count;
     RegAsm ra;
     ra.reg = RegArgs{f->ed_points, f->ed_knn, f->beta, f->J, f->lam_arap, f->lam_rot, f->use_arap, f->use_rot};
     ra.M.A = nullptr; ra.M.g = nullptr;
@@ -704,22 +852,26 @@ int launch_gram(const SbLMFrame* f, cudaStream_t st) {
     M.A = nullptr; M.g = nullptr;        // chosen in the kernel from the device-resident selector
     M.lda = f->ldab; M.bw = f->bw; M.node_pos = f->node_pos; M.overflow = f->band_overflow;
     M.set_shift(f->fx_shift, f->fx_gshift);
-    DataArgs a = make_args(f->points, f->knn_idx, f->knn_w, f->order, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
-                           f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data);
     GramArgs ga;
     ga.store[0] = reinterpret_cast<double*>(f->fx_store[0]);
     ga.store[1] = reinterpret_cast<double*>(f->fx_store[1]);
     ga.g_off = (long long)f->n * f->ldab;
     ga.st = (const LMState*)f->state;
     ga.rows = f->rows; ga.keys = f->keys; ga.row_stride = f->row_stride;
-    const size_t smem = JTJ_WARPS * (JT_DOUBLES + FL_DOUBLES) * sizeof(double);
-    const int resident = jtj_resident<true>(smem);
+    ga.rec_vals = f->rec_vals; ga.rec_keys = f->rec_keys; ga.rec_count = f->rec_count; ga.rec_cap = f->rec_cap;
+    const size_t smem = JTJ_WARPS * FL_DOUBLES * sizeof(double);
+    const int resident = jtj_resident(jtj_gram_kernel, smem, 1);
     if (resident <= 0) return SB_ERR_CUDA;
     const int n_chunks = (f->n_cap + 31) / 32;
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    data_jtj_kernel<true><<<blocks, JTJ_WARPS * 32, smem, st>>>(a, M, nullptr, ga);
+    jtj_gram_kernel<<<blocks, JTJ_WARPS * 32, smem, st>>>(f->n_cap, f->n_dev, M, ga);
+    SB_CHECK_LAUNCH();
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    jtj_scatter_kernel<<<8 * sms, 256, 0, st>>>(M, ga);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

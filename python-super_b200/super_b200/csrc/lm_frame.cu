@@ -15,8 +15,8 @@
 //     input, so a copy is needed anyway) and clears the other store for the next assembly: no memset nodes, no side stream.
 //   * the data term runs as TWO launches: a high-occupancy evaluation pass that writes the Jacobian rows (and takes the
 //     LM decision in its last block) and a Gram pass that reads them back; after a reject the Gram pass returns at once.
-// One iteration = 8 launches: from_fixed, band_reverse, band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
-// data_eval_decide (+ decision), data_jtj<rows> (+ ARAP/Rot).  No host synchronisation, no allocation.
+// One iteration = 9 launches: from_fixed, band_reverse, band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
+// data_eval_decide (+ ARAP/Rot blocks + decision), jtj_gram (records), jtj_scatter.  No host synchronisation, no allocation.
 #include "common.cuh"
 #include "lm_state.cuh"
 #include "internal.h"
@@ -90,8 +90,10 @@ static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st) {
 
 int sb_lm_frame(const SbLMFrame* f, void* stream) {
     if (!f || !f->points || !f->knn_idx || !f->knn_w || !f->ed_points || !f->ed_knn || !f->vmap || !f->nmap) return SB_ERR_ARG;
-    if (!f->state || !f->beta || !f->best || !f->partials_loss || !f->rows || !f->keys || f->row_stride < f->n_cap)
+    if (!f->state || !f->beta || !f->best || !f->partials_loss || !f->rows || !f->keys || f->row_stride < f->n_cap ||
+        (f->row_stride & 31))
         return SB_ERR_ARG;
+    if (!f->rec_vals || !f->rec_keys || !f->rec_count || f->rec_cap < 1) return SB_ERR_ARG;
     if (!f->fx_store[0] || !f->fx_store[1] || !f->AB || !f->g || !f->band_overflow || !f->dinv || !f->info || !f->solver_ws)
         return SB_ERR_ARG;
     if (f->J <= 0 || f->J > 65535 || f->n != 7 * f->J || f->bw < 0 || f->ldab < f->bw + 1 || f->iterations < 1 ||
@@ -106,6 +108,7 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
     // prologue: controller state, the store the first assembly goes to, the normal equations at the initial beta
     if (cudaMemsetAsync(f->fx_store[1], 0, (size_t)n_tot * sizeof(long long), st) != cudaSuccess) return SB_ERR_CUDA;
     if (cudaMemsetAsync(f->info, 0, sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    if (cudaMemsetAsync(f->rec_count, 0, sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
     int rc = sb_lm_begin(f->state, f->beta, f->best, f->J, f->u, f->v, f->minimal_loss, stream);
     if (rc != SB_OK) return rc;
     rc = jtj_pass(f, 1, 0, st);

@@ -34,6 +34,7 @@ class SbLMFrame(ctypes.Structure):
                 ("iterations", _I), ("u", _D), ("v", _D), ("minimal_loss", _D),
                 ("state", _P), ("beta", _P), ("best", _P),
                 ("partials_loss", _P), ("n_partials_loss", _I), ("rows", _P), ("keys", _P), ("row_stride", _I),
+                ("rec_vals", _P), ("rec_keys", _P), ("rec_count", _P), ("rec_cap", _I),
                 ("n", _I), ("bw", _I), ("ldab", _I), ("node_pos", _P), ("pos_node", _P),
                 ("fx_store", _P * 2), ("fx_shift", _I), ("fx_gshift", _I),
                 ("AB", _P), ("g", _P), ("band_overflow", _P), ("dinv", _P), ("info", _P),
@@ -93,6 +94,10 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
         stride = (stride + 31) // 32 * 32
         ws.rows = torch.empty((29, stride), dtype=F64, device=dev)
         ws.keys = torch.empty(stride, dtype=torch.int64, device=dev)
+        ws.rec_cap = 2 * (stride // 32) + 4096
+        ws.rec_vals = torch.empty((ws.rec_cap, 436), dtype=F64, device=dev)
+        ws.rec_keys = torch.empty(ws.rec_cap, dtype=torch.int64, device=dev)
+        ws.rec_count = torch.zeros(1, dtype=torch.int32, device=dev)
     if getattr(band, "ws4", None) is None:
         band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8, device=dev)
     vmap, nmap = maps
@@ -108,6 +113,7 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
     f.state, f.beta, f.best = ptr(ws.state.buf), ptr(ws.beta), ptr(ws.best)
     f.partials_loss, f.n_partials_loss = ptr(ws.partials_frame), ws.partials_frame.numel()
     f.rows, f.keys, f.row_stride = ptr(ws.rows), ptr(ws.keys), ws.keys.numel()
+    f.rec_vals, f.rec_keys, f.rec_count, f.rec_cap = ptr(ws.rec_vals), ptr(ws.rec_keys), ptr(ws.rec_count), ws.rec_cap
     f.n, f.bw, f.ldab = band.n, band.bw, band.ldab
     f.node_pos, f.pos_node = ptr(band.node_pos), ptr(band.pos_node)
     f.fx_store = (ctypes.c_void_p * 2)(ptr(band.fx[0]), ptr(band.fx[1]))
@@ -123,7 +129,7 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
             setattr(f, name + "_events", ctypes.cast(arr, ctypes.c_void_p))
             setattr(f, "n_" + name + "_events", len(evs))
     call("sb_lm_frame", ctypes.byref(f), stream())
-    lib.LAUNCHES += 2 + 8 * f.iterations        # lm_begin, eval, Gram; per iteration from_fixed + 5 (solve) + eval + Gram | loss
+    lib.LAUNCHES += 2 + 9 * f.iterations        # lm_begin, eval, Gram, scatter; per iteration from_fixed + 5 (solve) + eval + Gram + scatter | loss
     band._dirty = False
     return ws.beta, ws
 
