@@ -337,6 +337,54 @@ int sb_gf_global_update(double* points, double* norms, int n_cap, const int* n_d
                         int J, const double* global_row, void* stream);
 
 
+/* ---- helpers the reference exports by name (Python face: super/utils.py, utils/utils.py, super/loss.py) ------------- */
+
+/* get_skew: /root/reference/super/utils.py:4-14.  a (n,3) -> out (n,3,3) = [a]x  (the layout the reference produces for
+ * its 3-D inputs) */
+int sb_get_skew(const double* a, long long n, double* out, void* stream);
+/* transformQuatT: /root/reference/super/utils.py:41-71.  v (n,3), beta (n,beta_dim) with beta_dim 4 (rotation only) or
+ * 7 (q; b), q NOT normalised -> tv (n,3); jac (n,3,4) = d tv / d q when non-NULL (grad=True) */
+int sb_transform_quat(const double* v, const double* beta, long long n, int beta_dim, double* tv, double* jac, void* stream);
+/* Trans_points: /root/reference/super/utils.py:17-38.  d, g (n,K,3), beta (n,K,7), w (n,K) or NULL (weights 1) ->
+ * out (n,3) = sum_k w_k [T(q_k,b_k) d_k + g_k]; jac (n,K,3,4) = w_k d[R(q_k) d_k]/dq_k when non-NULL */
+int sb_trans_points(const double* d, const double* g, const double* beta, const double* w, long long n, int K, double* out,
+                    double* jac, void* stream);
+/* pcd2depth: /root/reference/utils/utils.py:161-184.  pcd (n,3) f64, intr = host {fx,fy,cx,cy} -> unrounded (v,u) f64
+ * and/or rounded (v,u) i64 (half to even), coords = round(v) W + round(u) i64, valid = margin <= v < H-1-margin and
+ * margin <= u < W-1-margin on the ROUNDED values (u8).  Either pair of (v,u) outputs may be NULL. */
+int sb_pcd2depth(const double* pcd, long long n, const double* intr, int H, int W, int valid_margin, double* v_float,
+                 double* u_float, long long* v_round, long long* u_round, long long* coords, unsigned char* valid,
+                 void* stream);
+/* KLD / JSD over the last axis: /root/reference/utils/utils.py:244-254.  P, Q (n,C) f64, C <= 8 -> out (n,) */
+int sb_kld_jsd(const double* P, const double* Q, long long n, int C, double eps, int jsd, double* out, void* stream);
+/* ARAPLoss / RotLoss .forward(grad=False): /root/reference/super/loss.py:428-437,452-455 and :487-490,497-499.
+ * arap_r2 (J*K*3,) f64 squared residuals in (node, neighbour, xyz) order, rot_r2 (J,) f32; either may be NULL */
+int sb_reg_residuals(const double* ed_points, const int* ed_knn, const double* beta, int J, double lam_arap, double lam_rot,
+                     double* arap_r2, float* rot_r2, void* stream);
+
+/* ---- producer-side pieces next to the path ------------------------------------------------------------------------ */
+
+/* torch_dilate on one channel: /root/reference/utils/utils.py:152-157 (box filter > 0, conv2d padding='same': for an even
+ * kernel the extra tap is on the bottom / right).  in, out (H,W) u8, out != in; invert_in / invert_out apply ~ to the
+ * operand / result, so that the reference's open-then-dilate of the invalid mask (utils/data_loader.py:394-397) is two calls */
+int sb_dilate_box(const unsigned char* in, int H, int W, int kernel, int invert_in, int invert_out, unsigned char* out,
+                  void* stream);
+/* SSIM depth confidence (run_semantic_super.py's default): /root/reference/utils/data_loader.py:360-372,477-479 with
+ * Project3D (/root/reference/depth/monodepth2/layers.py:173-193), F.grid_sample defaults and
+ * skimage.metrics.structural_similarity(channel_axis=0, full=True) defaults (7x7 uniform window, sample covariance,
+ * K1 0.01, K2 0.03; data_range as given -- skimage, absent here, derives 2.0 from a float image: parity UNPINNED).
+ * depth (H,W) f32, color (3,H,W) f32, inv_K3x3 host float[9], KT3x4 host float[12] = (K @ stereo_T)[:3], warp_scratch
+ * (3,H,W) f32.  In place: confs <- 0.5 confs + 0.5 sigmoid(mean_c SSIM).  ssim_out (H,W) optional. */
+int sb_ssim_conf(const float* depth, const float* color, const float* inv_K3x3, const float* KT3x4, int H, int W,
+                 double data_range, float* warp_scratch, float* confs, float* ssim_out, void* stream);
+/* Surfel splat renderer in pulsar's role: /root/reference/renderer/renderer.py:50-78 as called by
+ * /root/reference/super/nodes.py:630-642.  Every (masked-in) surfel is a sphere of radius rad; the nearest sphere along a
+ * pixel's ray wins (pulsar with gamma -> 0); img (H,W,3) f32 = its colour, bg3 (host float[3]) elsewhere; optional depth
+ * (H,W) f32 of the hit and index (H,W) i32 of the winning surfel (-1 = background).  zbuf: H*W u64 scratch. */
+int sb_render_splats(const double* points, const float* colors, const unsigned char* mask, int n_cap, const int* n_dev,
+                     const double* intr, int H, int W, double rad, const float* bg3, unsigned long long* zbuf, float* img,
+                     float* depth, int* index, void* stream);
+
 /* ---- ED graph (once per sequence / at every re-initialisation) -------------------------------------------- */
 
 /* init_graph + DirectDeformGraph.init_ED_nodes, grid_mesh branch: /root/reference/super/graph_encoder.py:11-67,128-167.

@@ -20,6 +20,8 @@ def main(argv=None, options=SuPerOptions):
     models = InitNets(opt)
     for inputs in tqdm(loader):
         models.super(models, inputs)
+    if models.super.sf is not None:          # the reference evaluates every save_sample_freq frames (super.py:79-80);
+        models.super.sf.evaluate()           # one more at the end so that the last frames are in tracking_rst.npy
     return models
 
 

@@ -84,6 +84,7 @@ class Frame:
         self.cam = None
         self.time = 0.0
         self.c = None
+        self.ED_nodes = None     # set by SuPer.forward on the first frame (the reference's sfdata.ED_nodes)
         self.seg = None          # (P,) i32, (P,C) f64, (C,H,W) f64 scores: semantic inputs (preprocess fills them)
         self.seg_conf = None
         self.scores = None
@@ -134,24 +135,92 @@ def preprocess(opt, depth, color, K, inv_K, time, frame=None, inval=None, divter
 
 def extra_invalid_mask(opt, depth, seg=None, mask=None):
     """The morphology part of the reference's invalid mask (data_loader.py:374-397): only needed when a
-    valid mask is loaded or classes are deleted; otherwise the open/dilate of an all-false mask is a no-op."""
+    valid mask is loaded or classes are deleted; otherwise the open/dilate of an all-false mask is a no-op.
+    mask: (H,W) bool VALID mask (--load_valid_mask), seg: (H,W) integer labels (--del_seg_classes).  Two launches of
+    sb_dilate_box: inval = ~dilate(~inval, k); inval = dilate(inval, 2k)  (:394-397)."""
     if mask is None and not getattr(opt, "del_seg_classes", []):
         return None
-    import torch.nn.functional as Fn
     H, W = opt.height, opt.width
-    inval = torch.zeros((1, 1, H, W), dtype=torch.bool, device=depth.device) if mask is None else ~mask.reshape(1, 1, H, W)
+    inval = torch.zeros((H, W), dtype=torch.bool, device=depth.device) if mask is None else ~mask.reshape(H, W).bool()
     for c in getattr(opt, "del_seg_classes", []):
-        inval |= seg.reshape(1, 1, H, W) == c
+        inval |= seg.reshape(H, W) == c
+    inval = inval.to(U8).contiguous()
     if opt.data == "superv1" and opt.dilate_invalid_kernel > 0:
-        def dil(x, k):
-            return Fn.conv2d(x, torch.ones((1, 1, k, k), device=x.device), padding="same") > 0
-        inval = ~dil((~inval).float(), opt.dilate_invalid_kernel)
-        inval = dil(inval.float(), 2 * opt.dilate_invalid_kernel)
-    return inval.reshape(H, W).to(U8).contiguous()
+        tmp, out = torch.empty_like(inval), torch.empty_like(inval)
+        call("sb_dilate_box", ptr(inval), H, W, int(opt.dilate_invalid_kernel), 1, 1, ptr(tmp), stream())
+        call("sb_dilate_box", ptr(tmp), H, W, 2 * int(opt.dilate_invalid_kernel), 0, 0, ptr(out), stream())
+        inval = out
+    return inval
+
+
+def ssim_confidence(opt, frame, depth, color, K, inv_K, stereo_T, data_range=2.0):
+    """The SSIM depth-confidence term of run_semantic_super.py's default configuration (data_loader.py:360-372,477-479):
+    confs <- 0.5 confs + 0.5 sigmoid(mean_c SSIM(warp, image)), in place on frame.confs.  Two launches (sb_ssim_conf).
+    data_range: skimage (absent here) derives 2.0 from a float image -- parity unpinned, see include/super_b200.h."""
+    H, W = opt.height, opt.width
+    Kh = torch.as_tensor(K).detach().cpu().reshape(-1, 4, 4)[0].float()
+    iKh = torch.as_tensor(inv_K).detach().cpu().reshape(-1, 4, 4)[0].float()
+    Th = torch.as_tensor(stereo_T).detach().cpu().reshape(-1, 4, 4)[0].float()
+    P = torch.matmul(Kh, Th)[:3, :]
+    ik = (ctypes.c_float * 9)(*[float(iKh[i, j]) for i in range(3) for j in range(3)])
+    kt = (ctypes.c_float * 12)(*[float(P[i, j]) for i in range(3) for j in range(4)])
+    warp = torch.empty((3, H, W), dtype=F32, device=depth.device)
+    frame.ssim = torch.empty((H, W), dtype=F32, device=depth.device)
+    call("sb_ssim_conf", ptr(depth.reshape(H, W).contiguous()), ptr(color.reshape(3, H, W).contiguous()), ik, kt, H, W,
+         float(data_range), ptr(warp), ptr(frame.confs), ptr(frame.ssim), stream())
+
+
+def dist2edge(opt, frame):
+    """Normalised distance of every valid pixel's projection to the nearest edge pixel of its own class
+    (data_loader.py:494-517): a per-class nearest-neighbour search in 2-D (sb_knn_class, K = 1).  Stored by the reference
+    on new_data and carried onto new surfels; nothing on the tracking path reads it.  Returns (P,) f64 (0 where invalid)."""
+    H, W, C = opt.height, opt.width, opt.num_classes
+    dev = frame.vmap.device
+    pts, off = graphfit.edge_points(frame.seg.view(H, W), C, H, W, margin=-(10 ** 6))       # no margin frame here
+    out = torch.zeros(frame.P, dtype=F64, device=dev)
+    valid = frame.valid
+    n = int(valid.sum())
+    if n == 0 or pts.shape[0] == 0:
+        return out
+    from .utils.utils import pcd2depth
+    v, u, _, _ = pcd2depth({("color", 0): torch.empty((1, 3, H, W), device="meta"), "K": _K44(frame.cam)},
+                           frame.vmap[valid, :3].to(F64), round_coords=False)
+    q = torch.stack([u / W, v / H], dim=1).contiguous()
+    r = torch.stack([pts[:, 0] / W, pts[:, 1] / H], dim=1).contiguous()
+    rseg = torch.repeat_interleave(torch.arange(C, device=dev, dtype=I32), (off[1:] - off[:-1]).long())
+    d, _ = ops.knn(q, r, 1, qseg=frame.seg[valid].contiguous(), rseg=rseg.contiguous())
+    out[valid] = d[:, 0]
+    return out
+
+
+def _K44(cam):
+    K = torch.eye(4, dtype=torch.float64)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = cam.fx, cam.fy, cam.cx, cam.cy
+    return K[None]
+
+
+def depth_preprocessing(opt, models, inputs, frame=None, return_valid_map=False):
+    """depth_preprocessing (/root/reference/utils/data_loader.py:333-523), same call: returns (data, inputs) with `data`
+    the engine.Frame holding points / norms / radii / confs / validity (and seg, seg_conf) as dense device images."""
+    depth, color = inputs[("depth", 0)], inputs[("color", 0)]
+    time = float(torch.as_tensor(inputs["time"]).reshape(-1)[0]) if "time" in inputs else float(inputs["filename"][0])
+    seg = inputs.get(("seg", 0))
+    inval = extra_invalid_mask(opt, depth, seg=seg, mask=inputs.get("valid_mask"))
+    divterm = inputs.get("divterm", 1.0 / (2.0 * 0.6 * 0.6))
+    frame = preprocess(opt, depth, color, inputs["K"], inputs["inv_K"], time, frame=frame, inval=inval,
+                       divterm=float(torch.as_tensor(divterm).reshape(-1)[0]), seg_scores=inputs.get(("seg_conf", 0)))
+    if hasattr(opt, "disable_ssim_conf") and not opt.disable_ssim_conf:
+        if "stereo_T" not in inputs:
+            raise lib.SuperB200Error("the SSIM confidence term (default of run_semantic_super.py) needs inputs['stereo_T']; "
+                                     "pass --disable_ssim_conf otherwise")
+        ssim_confidence(opt, frame, depth, color, inputs["K"], inputs["inv_K"], inputs["stereo_T"])
+    if return_valid_map:
+        return frame, inputs, frame.valid.view(opt.height, opt.width)
+    return frame, inputs
 
 
 # ---- ED graph (once per sequence) -------------------------------------------------------------------
-def build_graph(opt, frame):
+def build_graph(opt, frame, topology_only=False):
     """init_graph + DirectDeformGraph grid_mesh (/root/reference/super/graph_encoder.py:11-67,128-193) from the dense maps:
     one launch (sb_graph_build, csrc/graph.cu), then update_ed (nodes.py:154-168).  One host read of the three counts."""
     H, W, s = frame.H, frame.W, opt.mesh_step_size
@@ -173,7 +242,7 @@ def build_graph(opt, frame):
          ptr(points), ptr(norms), ptr(uv), ptr(seg), ptr(seg_conf), ptr(edges), ptr(faces), ptr(lens), ptr(radii),
          ptr(areas), ptr(node_pos), ptr(counts), stream())
     J, E, Fc = (int(x) for x in counts.tolist())                # init only: a sync is fine here
-    if J < opt.num_ED_neighbors + 1:
+    if not topology_only and J < opt.num_ED_neighbors + 1:
         raise lib.SuperB200Error(f"only {J} ED nodes on valid pixels: the graph needs more than num_ED_neighbors")
     g = NS()
     g.points, g.norms, g.radii = points[:J].contiguous(), norms[:J].contiguous(), radii[:J].contiguous()
@@ -188,6 +257,8 @@ def build_graph(opt, frame):
         g.seg = g.seg_i32.to(I64)
     else:
         g.seg_i32 = None
+    if topology_only:
+        return g
     # update_ed (/root/reference/super/nodes.py:154-168): K+1 nearest, drop self, weights use the query radius
     hard = bool(getattr(opt, "hard_seg", False)) and g.seg_i32 is not None
     dist, idx = ops.knn(g.points, g.points, opt.num_ED_neighbors + 1, qseg=g.seg_i32 if hard else None,
@@ -228,7 +299,7 @@ class Tracker:
         self.n_tmp = torch.zeros(1, dtype=I32, device=self.dev)
         self.overflow = torch.zeros(1, dtype=I32, device=self.dev)
         self.track_id = None
-        self.frames = [Frame(self.H, self.W, self.dev), Frame(self.H, self.W, self.dev)]
+        self.frames = None           # two Frame buffers for step(), allocated on first use
         self._fi = 0
         self.time = None
         self.last_beta = None
@@ -338,18 +409,54 @@ class Tracker:
 
     # -- frame stages -------------------------------------------------------------------------------------
     def next_frame(self):
+        if self.frames is None:
+            self.frames = [Frame(self.H, self.W, self.dev), Frame(self.H, self.W, self.dev)]
         self._fi ^= 1
         return self.frames[self._fi]
 
-    def init(self, frame):
-        """Surfels.__init__ + update_sfed_knn + first compaction (nodes.py:93-191, super.py:60-63)."""
+    def reset(self):
+        """Forget the sequence but keep every allocation (surfel buffers, band stores, solver workspaces, Jacobian-row
+        scratch): the next init_state() starts a new sequence of the same image size without touching the allocator --
+        for runs over many short sequences."""
+        self._spare = (self.cur, self.alt, self.fuse_ws) if self.cur is not None else getattr(self, "_spare", None)
+        self.cur = self.alt = self.ED = None
+        self.n_bound = 0
+        self._n_event = self._order = None
+        self._order_rows = 0
+        self._n_exact = None
+        self._last_growth = 0
+        self.band = None
+        self.track_id = None if getattr(self, "gt", None) is None else -torch.ones_like(self.track_id)
+        self.track_rsts = {}
+        self.time = self.last_beta = None
+        self._finished_once = False
+        self.overflow.zero_()
+        for b in self._bands.values():
+            b.overflow.zero_()
+
+    def init(self, frame, filename=None):
+        """Surfels.__init__ + the first prepareStableIndexNSwapAllModel (nodes.py:93-191, super.py:60-63)."""
+        self.init_state(frame)
+        self.finish_frame(frame, filename)
+
+    def init_state(self, frame):
+        """Surfels.__init__ (nodes.py:93-149): ED graph, one surfel per valid pixel, update_ed, update_sfed_knn."""
         opt, dev = self.opt, self.dev
-        self.ED = build_graph(opt, frame)
+        # the reference hands the graph over on the data object (sfdata.ED_nodes = models.mesh_encoder(...), super.py:49-50)
+        self.ED = getattr(frame, "ED_nodes", None) or build_graph(opt, frame)
+        frame.ED_nodes = None
         self.semantic = frame.seg_conf is not None
         C = frame.seg_conf.shape[1] if self.semantic else 0
         self.sem_weights = self.semantic and getattr(opt, "method", "super") == "semantic-super"
-        self.cur, self.alt = SurfelBuffers(self.cap, dev, C), SurfelBuffers(self.cap, dev, C)
-        self.fuse_ws = torch.zeros(int(lib.load().sb_fuse_workspace_bytes(self.H, self.W, self.cap)), dtype=U8, device=dev)
+        spare = getattr(self, "_spare", None)
+        if spare is not None and spare[0].n_classes == C:
+            self.cur, self.alt, self.fuse_ws = spare          # reset(): reuse the previous sequence's buffers
+            self.cur.stable.zero_()
+        else:
+            self.cur, self.alt = SurfelBuffers(self.cap, dev, C), SurfelBuffers(self.cap, dev, C)
+            self.fuse_ws = torch.zeros(int(lib.load().sb_fuse_workspace_bytes(self.H, self.W, self.cap)), dtype=U8, device=dev)
+        self._spare = None
+        self._finished_once = False
         valid = frame.valid
         n = int(valid.sum())                               # init only: a sync is fine here
         if n > self.cap:
@@ -381,11 +488,19 @@ class Tracker:
         b.projdata[:n, 1] = (pix // self.W).to(F32)
         self.n_bound = n
         self.time = frame.time
-        self._compact(frame, keep_projdata=True)
-        # band plan from the pattern of the initial tuples + ARAP pairs
-        self.block_bw.zero_()
+
+    def finish_frame(self, frame, filename=None):
+        """Surfels.prepareStableIndexNSwapAllModel (nodes.py:543-599): stability / time-stamp rule, compaction, tracked
+        points; then the hand-over of the row count, the next frame's visiting order and the band plan."""
+        first = not getattr(self, "_finished_once", False)
+        self._compact(frame, keep_projdata=first)
+        self._track_points(frame, filename if filename is not None else f"{int(frame.time):06d}")
+        if first:                # band plan from the pattern of the initial tuples + ARAP pairs
+            self.block_bw.zero_()
         self._publish_count()
-        self._refresh_bound()
+        if first:
+            self._refresh_bound()
+        self._finished_once = True
 
     def _compact(self, frame, keep_projdata=False):
         opt = self.opt
@@ -400,8 +515,9 @@ class Tracker:
             self.alt.projdata[:m] = proj[:n][keep]
         self.cur, self.alt = self.alt, self.cur
 
-    def track(self, frame):
-        """SuPer.fusion (/root/reference/super/super.py:66-83), LM path."""
+    def solve(self, frame, u=10.0, v=7.5, minimal_loss=1e10):
+        """The frame's deformation: LM_Solver.LM (LM.py:81-122) or GraphFit.forward (deform_mesh.py:232-379).
+        Returns beta (J,7) [LM] or deform_verts (J+1,7) [autograd configuration]."""
         opt = self.opt
         self._refresh_bound()
         sfv = self.view(self.n_bound)
@@ -414,12 +530,10 @@ class Tracker:
                 jev, sev = self._new_events(2 * self.events_per_frame[0]), self._new_events(2 * self.events_per_frame[1])
                 self.event_sink["jtj"] += list(zip(jev[0::2], jev[1::2]))
                 self.event_sink["solve"] += list(zip(sev[0::2], sev[1::2]))
-            beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, n_dev=self.cur.n_dev,
-                                        order=order, band=self.band, cluster_size=self.cluster_size, jtj_events=jev,
-                                        solve_events=sev, row_capacity=self.cap)
-            self.last_beta = beta
-            ops.warp_update(sfv.points, sfv.norms, sfv.knn_indices, sfv.knn_w, self.ED.points, self.ED.norms, beta,
-                            n_dev=self.cur.n_dev)
+            beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, u=u, v=v,
+                                        minimal_loss=minimal_loss, n_dev=self.cur.n_dev, order=order, band=self.band,
+                                        cluster_size=self.cluster_size, jtj_events=jev, solve_events=sev,
+                                        row_capacity=self.cap)
         else:
             # autograd configuration of the reference (GraphFit, super.py:70-71): fused loss+gradient kernels
             seg = None
@@ -435,13 +549,24 @@ class Tracker:
                         triangles=self.ED.triangles_i32, triangles_areas=self.ED.triangles_areas)
             beta, self.gf_ws = graphfit.graph_fit(sfv, (frame.vmap, frame.nmap), frame.cam, opt,
                                                   ws=getattr(self, "gf_ws", None), n_dev=self.cur.n_dev, seg=seg)
-            self.last_beta = beta
-            J = self.ED.num
-            ops.warp_update(self.cur.points[: self.n_bound], self.cur.norms[: self.n_bound],
-                            self.cur.knn_idx[: self.n_bound], self.cur.knn_w[: self.n_bound], self.ED.points,
-                            self.ED.norms, beta[:J], n_dev=self.cur.n_dev)
-            graphfit.update_global(self.cur.points[: self.n_bound], self.cur.norms[: self.n_bound], self.ED.points,
-                                   self.ED.norms, beta, n_dev=self.cur.n_dev)
+        self.last_beta = beta
+        return beta
+
+    def apply(self, deform):
+        """Surfels.update (nodes.py:193-223): warp surfels and nodes by the frame's deformation; a (J+1)-row deformation
+        carries the global transform of the autograd configuration in its last row (:204-205,211-212,219-222)."""
+        if deform is None:
+            return
+        J, nb = self.ED.num, self.n_bound
+        b = self.cur
+        deform = deform.contiguous()
+        ops.warp_update(b.points[:nb], b.norms[:nb], b.knn_idx[:nb], b.knn_w[:nb], self.ED.points, self.ED.norms,
+                        deform[:J], n_dev=b.n_dev)
+        if deform.shape[0] == J + 1:
+            graphfit.update_global(b.points[:nb], b.norms[:nb], self.ED.points, self.ED.norms, deform, n_dev=b.n_dev)
+
+    def fuse(self, frame):
+        """Surfels.fuseInputData (nodes.py:270-541)."""
         pr = self.fuse_params(frame)
         call("sb_fuse", self.cur.ref(), frame.ref(), ptr(self.ED.points), ptr(self.ED.radii), self.ED.num,
              ctypes.byref(pr), ptr(self.track_id), 0 if self.track_id is None else self.track_id.numel(),
@@ -449,8 +574,13 @@ class Tracker:
         self.cur.n_dev.copy_(self.n_tmp)
         self.n_bound = min(self.cap, self.n_bound + self.P)
         self.time = frame.time
-        self._compact(frame)
-        self._publish_count()
+
+    def track(self, frame, filename=None):
+        """SuPer.fusion (/root/reference/super/super.py:66-83): solve -> update -> fuse -> compact."""
+        beta = self.solve(frame)
+        self.apply(beta)
+        self.fuse(frame)
+        self.finish_frame(frame, filename)
         return beta
 
     def enable_tracking(self, gt):
@@ -497,12 +627,9 @@ class Tracker:
         if filename is None:
             filename = f"{int(time):06d}"
         if self.cur is None:
-            self.init(frame)
-            self._track_points(frame, filename)
+            self.init(frame, filename)
             return None
-        beta = self.track(frame)
-        self._track_points(frame, filename)
-        return beta
+        return self.track(frame, filename)
 
     def snapshot(self):
         """Exact-size copies of the state in the reference's layouts (synchronises)."""

@@ -11,8 +11,6 @@ from __future__ import annotations
 
 import torch
 
-from .. import graphfit as _gf
-
 
 class GraphFit(torch.nn.Module):
     def __init__(self, opt):
@@ -21,7 +19,6 @@ class GraphFit(torch.nn.Module):
         self.valid_margin = 1
         self.optim = opt.optimizer
         self.Niter = opt.num_optimize_iterations
-        self.ws = None
 
     def forward(self, inputs, src, trg, models=None):
         if getattr(self.opt, "deform_udpate_method", "super_edg") != "super_edg":
@@ -29,11 +26,4 @@ class GraphFit(torch.nn.Module):
         return self.deform_superedg(inputs, src, trg, models)
 
     def deform_superedg(self, inputs, src, trg, models=None):
-        from types import SimpleNamespace as NS
-        trk = src._trk
-        view = trk.view(trk.n_bound)
-        view.isStable = trk.cur.stable[: trk.n_bound]
-        view.ED = NS(points=trk.ED.points, knn_indices=trk.ED.knn_indices, knn_w=trk.ED.knn_w,
-                     triangles=trk.ED.triangles_i32, triangles_areas=trk.ED.triangles_areas)
-        dv, self.ws = _gf.graph_fit(view, (trg.vmap, trg.nmap), trg.cam, self.opt, ws=self.ws, n_dev=trk.cur.n_dev)
-        return dv
+        return src.solve(trg)

@@ -2,10 +2,12 @@
 
     models.super(models, inputs)      # once per frame, inputs = one DataLoader item (batch 1)
 
-Host->device staging of the frame (super.py:31-34), producer, then init or fusion
-(LM -> update -> fuse -> compact), all through super_b200.engine.Tracker, i.e. libsuper_b200.so.
+Same structure as the reference: stage the inputs on the device (super.py:31-34), depth_preprocessing, then either
+init_surfels (mesh_encoder -> Surfels -> prepareStableIndexNSwapAllModel) or fusion (LM_Solver.LM | GraphFit ->
+Surfels.update -> fuseInputData -> prepareStableIndexNSwapAllModel -> evaluate every save_sample_freq frames).  Every
+stage is a handful of launches of libsuper_b200.so; the host waits once per tracked frame (engine.Tracker).
 Both optimisers of the reference are available: the derived-gradient LM solver (--use_derived_gradient, super.py:68)
-and the autograd-style GraphFit with SGD/Adam (super.py:70-71), the latter for the non-semantic configuration.
+and the autograd-style GraphFit with SGD/Adam (super.py:70-71).
 """
 from __future__ import annotations
 
@@ -20,7 +22,8 @@ class SuPer(torch.nn.Module):
         super().__init__()
         self.opt = opt
         self.sf = None
-        self._trk = None
+        self._frames = None
+        self._fi = 0
         if opt.use_derived_gradient:
             from .LM import LM_Solver
             self.lm = LM_Solver(opt)
@@ -28,46 +31,53 @@ class SuPer(torch.nn.Module):
             from .deform_mesh import GraphFit
             self.graph_fit = GraphFit(opt)
 
+    def _next_frame(self, dev):
+        if self._frames is None:
+            self._frames = [engine.Frame(self.opt.height, self.opt.width, dev) for _ in range(2)]
+        self._fi ^= 1
+        return self._frames[self._fi]
+
     def forward(self, models, inputs):
         dev = torch.device("cuda", torch.cuda.current_device())
-        if self._trk is None:
-            self._trk = engine.Tracker(self.opt, device=dev)
-            if getattr(self.opt, "tracking_gt_file", None):          # nodes.py:96,115-126, utils/utils.py:383-391
-                import os
-                import numpy as np
-                gt = np.load(os.path.join(os.path.expanduser(self.opt.data_dir), self.opt.tracking_gt_file),
-                             allow_pickle=True).tolist()["gt"]
-                self._trk.enable_tracking({f"{int(k):06d}": np.asarray(v) for k, v in gt.items()})
         staged = {}
         for key, ipt in inputs.items():                          # super.py:31-34
             if torch.is_tensor(ipt):
                 if key == "divterm":
                     staged[key] = float(ipt.reshape(-1)[0])
-                elif key in ("K", "inv_K", "time", "ID"):
+                elif key in ("K", "inv_K", "stereo_T", "time", "ID"):
                     staged[key] = ipt                            # small host-side parameters
                 else:
                     staged[key] = ipt.to(dev, non_blocking=True)
             else:
                 staged[key] = ipt
         inputs.update(staged)
-        depth, color = inputs[("depth", 0)], inputs[("color", 0)]
-        time = float(torch.as_tensor(inputs["time"]).reshape(-1)[0])
-        seg = inputs.get(("seg", 0))
-        inval = engine.extra_invalid_mask(self.opt, depth, seg=seg, mask=inputs.get("valid_mask"))
-        frame = engine.preprocess(self.opt, depth, color, inputs["K"], inputs["inv_K"], time,
-                                  frame=self._trk.next_frame(), inval=inval,
-                                  divterm=inputs.get("divterm", 1.0 / (2.0 * 0.6 * 0.6)),
-                                  seg_scores=inputs.get(("seg_conf", 0)))
-        self.last_frame = frame
-        fname = inputs["filename"][0] if "filename" in inputs else f"{int(time):06d}"
-        if self._trk.cur is None:
-            self._trk.init(frame)
-            self.sf = Surfels(self.opt, self._trk)
+        sfdata, inputs = engine.depth_preprocessing(self.opt, models, inputs, frame=self._next_frame(dev))
+        self.last_frame = sfdata
+        if self.sf is None:                                      # super.py:47-54
+            if getattr(self.opt, "deform_udpate_method", "super_edg") == "super_edg" and hasattr(models, "mesh_encoder"):
+                sfdata.ED_nodes = models.mesh_encoder(inputs, sfdata)
+            self.init_surfels(models, inputs, sfdata)
             deform_param = None
         else:
-            deform_param = self.fusion(models, inputs, frame)
-        self._trk._track_points(frame, fname)
+            deform_param = self.fusion(models, inputs, sfdata)
         return deform_param
 
+    def init_surfels(self, models, inputs, sfdata):
+        self.sf = Surfels(self.opt, models, inputs, sfdata)
+        if self.opt.phase == "test":
+            self.sf.prepareStableIndexNSwapAllModel(inputs, sfdata)
+
     def fusion(self, models, inputs, sfdata):
-        return self._trk.track(sfdata)
+        if self.opt.use_derived_gradient:
+            deform_param = self.lm.LM(self.sf, inputs, sfdata)
+        else:
+            deform_param = self.graph_fit(inputs, self.sf, sfdata, models)
+            if deform_param is not None:
+                deform_param = deform_param.detach()
+        self.sf.update(deform_param)
+        if self.opt.phase == "test":
+            self.sf.fuseInputData(inputs, sfdata)                # fuse the input data into the reference model
+            self.sf.prepareStableIndexNSwapAllModel(inputs, sfdata)
+            if int(self.sf.time) % int(getattr(self.opt, "save_sample_freq", 10)) == 0:
+                self.sf.evaluate()
+        return deform_param

@@ -1,0 +1,280 @@
+"""GPU: the Python face of the drop-in -- the helper functions and term classes the reference exports by
+name -- and the pieces next to the path (renderer, SSIM confidence, morphology, dist2edge), against the oracle."""
+import os
+import re
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import super_oracle as so
+from oracle import face_oracle as fo
+from golden_util import Golden
+
+pytestmark = pytest.mark.gpu
+G = Golden()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+
+
+def test_transform_quat_trans_points_get_skew():
+    from super_b200.super.utils import Trans_points, get_skew, transformQuatT
+    N, K = 300, 4
+    d, g = _rand(N, K, 3, seed=1), _rand(N, K, 3, seed=2)
+    beta = _rand(N, K, 7, seed=3) * 0.1
+    beta[..., 0] += 1.0
+    w = torch.rand(N, K, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    # transformQuatT, 7 and 4 columns, with the Jacobian
+    for cols in (7, 4):
+        tv, jac = transformQuatT(d.cuda(), beta[..., :cols].cuda(), grad=True)
+        tv_ref, cp = so.quat_apply(d, beta[..., :cols])
+        assert torch.equal(tv.cpu(), tv_ref)                                  # reference operation order: bit-exact
+        assert (jac.cpu() - so.quat_jac(d, beta[..., :cols], cp)).abs().max() < 1e-14
+        tv2, zero = transformQuatT(d.cuda(), beta[..., :cols].cuda())
+        assert zero == 0 and torch.equal(tv2, tv)
+    # broadcasting beta (1, ..., 7) as ARAPLoss uses it
+    tvb, _ = transformQuatT(d.cuda(), beta[:1].cuda())
+    assert torch.equal(tvb.cpu(), so.quat_apply(d, beta[:1].expand(N, K, 7))[0])
+    # Trans_points
+    out, jac = Trans_points(d.cuda(), g.cuda(), beta.cuda(), w.cuda(), grad=True)
+    tv_ref, cp = so.quat_apply(d, beta)
+    ref = torch.sum(w[..., None] * (tv_ref + g), dim=-2)
+    assert (out.cpu() - ref).abs().max() < 1e-14
+    assert (jac.cpu() - so.quat_jac(d, beta, cp) * w[..., None, None]).abs().max() < 1e-14
+    # get_skew: [a]x b = a x b
+    S = get_skew(d.cuda()).cpu()
+    b = _rand(N, K, 3, seed=5)
+    assert (torch.einsum("nkij,nkj->nki", S, b) - torch.linalg.cross(d, b)).abs().max() < 1e-14
+
+
+def test_pcd2depth_find_knn_kld_jsd():
+    from super_b200.utils.utils import JSD, KLD, find_knn, pcd2depth
+    H, W = 96, 128
+    f = G.frame(G.frames[0])
+    inputs = {("color", 0): torch.from_numpy(f["color"])[None].cuda(), "K": torch.from_numpy(f["K"])[None]}
+    pts = _rand(5000, 3, seed=6) * 0.05 + torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64)
+    K = torch.from_numpy(f["K"])
+    for margin in (0, 1):
+        v_ref, u_ref, coords_ref, ok_ref = so.project(K, pts, H, W, margin)
+        v, u, coords, ok = pcd2depth(inputs, pts.cuda(), round_coords=False, valid_margin=margin)
+        assert torch.equal(v.cpu(), v_ref) and torch.equal(u.cpu(), u_ref)     # reference operation order: bit-exact
+        assert torch.equal(coords.cpu(), coords_ref) and torch.equal(ok.cpu(), ok_ref)
+        vr, ur, _, _ = pcd2depth(inputs, pts.cuda(), round_coords=True, valid_margin=margin)
+        assert torch.equal(vr.cpu(), torch.round(v_ref).long()) and torch.equal(ur.cpu(), torch.round(u_ref).long())
+    # find_knn, plain and per class
+    p1, p2 = _rand(2000, 3, seed=7), _rand(150, 3, seed=8)
+    d, i = find_knn(p1.cuda(), p2.cuda(), k=4)
+    d_ref, i_ref = so.knn(p1, p2, 4)
+    assert i.dtype == torch.int64 and torch.equal(i.cpu(), i_ref) and (d.cpu() - d_ref).abs().max() < 1e-15
+    s1 = torch.randint(0, 3, (2000,), generator=torch.Generator().manual_seed(9))
+    s2 = torch.randint(0, 3, (150,), generator=torch.Generator().manual_seed(10))
+    d, i = find_knn(p1.cuda(), p2.cuda(), num_classes=3, seg1=s1.cuda(), seg2=s2.cuda(), k=4)
+    d_ref, i_ref = so.knn_class(p1, p2, 4, s1, s2, 3)
+    assert torch.equal(i.cpu(), i_ref) and (d.cpu() - d_ref).abs().max() < 1e-15
+    # KLD / JSD
+    P = torch.softmax(_rand(700, 3, seed=11), -1)
+    Q = torch.softmax(_rand(700, 3, seed=12), -1)
+    assert (KLD(P.cuda(), Q.cuda()).cpu() - so.kld(P, Q)).abs().max() < 1e-14
+    assert (JSD(P.cuda(), Q.cuda()).cpu() - so.jsd(P, Q)).abs().max() < 1e-14
+
+
+def _ref_like_state(t):
+    """Reference-shaped objects on the GPU from the golden state: sf (points, knn_indices i64, knn_w, ED_nodes),
+    new_data (compact points / norms / valid / index_map), inputs (K, colour for the image size)."""
+    sf, nd = G.state(t - 1), G.new_data(t)
+    f = G.frame(t)
+    dsf = NS(points=sf.points.cuda(), knn_indices=sf.knn_indices.cuda(), knn_w=sf.knn_w.cuda(),
+             ED_nodes=NS(points=sf.ED.points.cuda(), knn_indices=sf.ED.knn_indices.cuda(), num=sf.ED.num,
+                         param_num=7 * sf.ED.num))
+    dnd = NS(points=nd.points.cuda(), norms=nd.norms.cuda(), valid=nd.valid.cuda(), index_map=nd.index_map.cuda())
+    inputs = {("color", 0): torch.from_numpy(f["color"])[None].cuda(), "K": torch.from_numpy(f["K"])[None]}
+    return sf, nd, dsf, dnd, inputs
+
+
+def test_loss_classes_match_oracle():
+    """DataLoss / ARAPLoss / RotLoss .prepare / .forward as LM_Solver.prepareCostTerm drives them (LM.py:54-79)."""
+    from super_b200.super.LM import LM_Solver
+    t = G.frames[1]
+    sf, nd, dsf, dnd, inputs = _ref_like_state(t)
+    beta = torch.from_numpy(G[f"f{t}.lm.beta_try"][1].copy())
+    A_ref, g_ref, _ = so.lm_normal_equations(G.opt, sf, nd, beta, "blocks")
+    loss_ref, _ = so.lm_cost(G.opt, sf, nd, beta)
+    lm = LM_Solver(G.opt)
+    assert [type(x).__name__ for x in lm.losses] == ["DataLoss", "ARAPLoss", "RotLoss"]
+    for term in lm.losses:
+        term.prepare(dsf, dnd)
+    jtj, jtl = lm.prepareCostTerm(dsf, inputs, dnd, beta.cuda(), grad=True)
+    assert (jtj.cpu() - A_ref).abs().max() < 1e-10 * A_ref.abs().max()
+    assert (jtl.cpu() - g_ref).abs().max() < 1e-10 * max(1.0, float(g_ref.abs().max()))
+    loss = lm.prepareCostTerm(dsf, inputs, dnd, beta.cuda())
+    assert abs(float(loss) - float(loss_ref)) < 1e-8 * float(loss_ref)
+    # per-term shapes and values
+    dt = so.data_term(G.opt, sf, nd, beta, G.opt.sf_point_plane_weight, False)
+    r2 = lm.losses[0].forward(lm.lambdas[0], beta.cuda(), inputs, dnd)
+    assert r2.shape == (len(dt["ids"]), 1) and (r2[:, 0].cpu() - dt["r"] ** 2).abs().max() < 1e-14
+    a_jtj, a_jtl = lm.losses[1].forward(lm.lambdas[1], beta.cuda(), inputs, dnd, grad=True)
+    assert a_jtj.is_sparse and a_jtl.shape == (7 * sf.ED.num, 1)
+    ar2 = lm.losses[1].forward(lm.lambdas[1], beta.cuda(), inputs, dnd)
+    assert ar2.shape == (sf.ED.num * 4 * 3, 1)
+    r_arap, _ = so.arap_term(sf, beta, lm.lambdas[1], False)
+    assert (ar2[:, 0].cpu() - r_arap.reshape(-1) ** 2).abs().max() < 1e-12
+    rr2 = lm.losses[2].forward(lm.lambdas[2], beta.cuda(), inputs, dnd)
+    r_rot, _ = so.rot_term(beta, lm.lambdas[2], False)
+    assert rr2.dtype == torch.float32 and (rr2[:, 0].cpu().double() - r_rot.reshape(-1).double() ** 2).abs().max() < 1e-9
+
+
+def test_integration_md_dataloss_stub_runs_verbatim():
+    """INTEGRATION.md section B shows the ctypes stub a reference maintainer would put into super/loss.py.  It is
+    executed here exactly as printed and checked against the oracle, so that the document cannot drift from the ABI."""
+    from super_b200 import lib
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# super/loss.py  \(reference side\).*?)```", md, flags=re.S)
+    assert m, "the reference-side DataLoss example is missing from INTEGRATION.md"
+    os.environ["SUPER_B200_LIB"] = lib.LIB_PATH
+    ns = {}
+    exec(compile(m.group(1), "INTEGRATION.md", "exec"), ns)
+    t = G.frames[1]
+    sf, nd, dsf, dnd, inputs = _ref_like_state(t)
+    beta = torch.from_numpy(G[f"f{t}.lm.beta_try"][1].copy())
+    term = ns["DataLoss"]()
+    term.prepare(dsf, dnd)
+    A, g = term.forward(G.opt.sf_point_plane_weight, beta.cuda(), inputs, dnd, grad=True)
+    opt_data_only = so.default_opt(height=G.H, width=G.W, mesh_step_size=G.step, mesh_arap=False, mesh_rot=False)
+    A_ref, g_ref, _ = so.lm_normal_equations(opt_data_only, sf, nd, beta, "blocks")
+    A = A.cpu()
+    A = A + torch.tril(A, -1).t()
+    assert (A - A_ref).abs().max() < 1e-10 * A_ref.abs().max()
+    assert (g.cpu() - g_ref).abs().max() < 1e-10 * max(1.0, float(g_ref.abs().max()))
+
+
+def test_renderer_matches_sphere_zbuffer_oracle():
+    from super_b200.renderer import Renderer, conf2color
+    H, W = 60, 80
+    opt = NS(height=H, width=W)
+    gen = torch.Generator().manual_seed(3)
+    n = 400
+    pts = torch.rand(n, 3, generator=gen, dtype=torch.float64)
+    pts = torch.stack([(pts[:, 0] - 0.5) * 0.08, (pts[:, 1] - 0.5) * 0.06, 0.9 + 0.3 * pts[:, 2]], 1)
+    cols = torch.rand(n, 3, generator=gen)
+    K = torch.eye(4)
+    K[0, 0] = K[1, 1] = 700.0
+    K[0, 2], K[1, 2] = 39.3, 29.6
+    inputs = {"K": K[None]}
+    r = Renderer(opt)
+    for rad in (0.004, 0.0002):          # discs of several pixels; sub-pixel spheres (the reference's default rad)
+        img, depth = r(inputs, NS(points=pts.cuda(), colors=cols.cuda()), rad=rad, bg_col=torch.tensor([0.1, 0.2, 0.3]),
+                       return_depth=True)
+        img_ref, depth_ref, idx_ref = fo.render_spheres(pts.numpy(), cols.numpy(), K.numpy(), H, W, rad, bg=(0.1, 0.2, 0.3))
+        assert img.shape == (H, W, 3) and img.dtype == torch.float32
+        assert np.array_equal(img.cpu().numpy(), img_ref)
+        assert np.array_equal(depth.cpu().numpy(), depth_ref)
+        assert (idx_ref >= 0).sum() > 50
+    # masked-out surfels do not render; the heat map is a (N,3) colour table in [0,1]
+    mask = (torch.arange(n) % 2 == 0).to(torch.uint8)
+    img = r(inputs, NS(points=pts.cuda(), colors=cols.cuda(), mask=mask.cuda()), rad=0.004)
+    img_ref, _, _ = fo.render_spheres(pts[mask.bool()].numpy(), cols[mask.bool()].numpy(), K.numpy(), H, W, 0.004)
+    assert np.array_equal(img.cpu().numpy(), img_ref)
+    heat = conf2color(torch.linspace(0, 1, 11).cuda())
+    assert heat.shape == (11, 3) and float(heat.min()) >= 0 and float(heat.max()) <= 1 and float(heat[0].sum()) < 0.05
+
+
+def test_ssim_confidence_and_morphology_and_dist2edge():
+    from super_b200 import engine
+    from super_b200.utils.utils import torch_dilate
+    g = Golden("gf_sem_128x96")
+    H, W = g.H, g.W
+    f = g.frame(g.frames[1])
+    opt = g.opt
+    # SSIM confidence (run_semantic_super.py's default): device vs the numpy restatement
+    opt_ssim = so.default_opt(**{**vars(opt), "disable_ssim_conf": False})
+    stereo_T = np.eye(4, dtype=np.float32)
+    stereo_T[0, 3] = -0.1
+    inputs = {("depth", 0): torch.from_numpy(f["depth"])[None].cuda(), ("color", 0): torch.from_numpy(f["color"])[None].cuda(),
+              "K": torch.from_numpy(f["K"])[None], "inv_K": torch.from_numpy(f["inv_K"])[None],
+              "stereo_T": torch.from_numpy(stereo_T)[None], "time": torch.tensor([f["time"]]), "divterm": f["divterm"],
+              ("seg_conf", 0): torch.from_numpy(f["seg_conf"])[None].cuda()}
+    fr, _ = engine.depth_preprocessing(opt_ssim, None, dict(inputs))
+    fr0, _ = engine.depth_preprocessing(opt, None, dict(inputs))
+    conf_ref, s_ref = fo.ssim_confidence(torch.from_numpy(f["depth"])[0], torch.from_numpy(f["color"]), torch.from_numpy(f["K"]),
+                                         torch.from_numpy(f["inv_K"]), torch.from_numpy(stereo_T), fr0.confs.cpu().view(H, W))
+    assert np.abs(fr.ssim.cpu().numpy() - s_ref).max() < 2e-5            # float32 warp, float64 statistics
+    assert (fr.confs.cpu().view(H, W) - conf_ref).abs().max() < 1e-5
+    assert (fr.confs - fr0.confs).abs().max() > 1e-3                    # the term is active
+    # morphology: torch_dilate and the open-then-dilate of the invalid mask, odd and even kernels
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.rand(1, 1, H, W, generator=gen) > 0.97).float()
+    for k in (3, 5, 10):
+        assert torch.equal(torch_dilate(x.cuda(), kernel=k).cpu(), so.dilate(x, k))
+    mask = torch.rand(H, W, generator=gen) > 0.02                        # valid mask with holes
+    opt1 = so.default_opt(height=H, width=W, data="superv1", dilate_invalid_kernel=5)
+    inval = engine.extra_invalid_mask(opt1, torch.zeros(H, W).cuda(), mask=mask.cuda())
+    ref = ~so.dilate(mask[None, None].float(), 5)
+    ref = so.dilate(ref.float(), 10)
+    assert torch.equal(inval.cpu().bool(), ref[0, 0])
+    # dist2edge (data_loader.py:494-517) against the oracle's new_data
+    nd = so.preprocess(opt, f)
+    d2e = engine.dist2edge(opt, fr0)
+    assert (d2e.cpu()[nd.valid] - nd.dist2edge).abs().max() < 1e-12
+
+
+def test_surfels_face_methods(tmp_path):
+    """Surfels(opt, models, inputs, data) + prepareStableIndexNSwapAllModel / update / fuseInputData / update_ed /
+    update_sfed_knn / evaluate through SuPer.forward, against driving engine.Tracker directly."""
+    from super_b200 import engine, synth
+    from super_b200.data_loader import InitNets
+    H, W, step = G.H, G.W, G.step
+    gt = {f"{t:06d}": np.array([[40, 30, 1], [80, 60, 1], [100, 20, 0]], dtype=np.int64) for t in range(1, 5)}
+    np.save(tmp_path / "gt.npy", {"gt": gt}, allow_pickle=True)
+    opt = so.default_opt(height=H, width=W, mesh_step_size=step, gpu=0, renderer="splat", depth_model=None,
+                         data_dir=str(tmp_path), tracking_gt_file="gt.npy", output_dir=str(tmp_path / "out"),
+                         model_name="m", save_sample_freq=2, renderer_rad=0.002)
+    models = InitNets(opt)
+    assert hasattr(models, "mesh_encoder") and hasattr(models, "renderer") and hasattr(models, "super")
+    trk = engine.Tracker(opt)
+    trk.enable_tracking(gt)
+    for t in (1, 2, 3, 4):
+        f = G.frame(t)
+        inputs = {"filename": [f["filename"]], "time": torch.tensor([f["time"]], dtype=torch.float64),
+                  ("color", 0): torch.from_numpy(f["color"])[None], ("depth", 0): torch.from_numpy(f["depth"])[None],
+                  "K": torch.from_numpy(f["K"])[None], "inv_K": torch.from_numpy(f["inv_K"])[None],
+                  "divterm": torch.tensor([f["divterm"]], dtype=torch.float64)}
+        beta = models.super(models, inputs)
+        b2 = trk.step(torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["color"]).cuda(), torch.from_numpy(f["K"]),
+                      torch.from_numpy(f["inv_K"]), f["time"], filename=f["filename"])
+        sf = models.super.sf
+        assert (beta is None) == (b2 is None)
+        if beta is not None:
+            assert torch.equal(beta, b2)
+        assert sf.sf_num == trk.num_surfels()
+        assert torch.equal(sf.points, trk.cur.points[: sf.sf_num])
+        assert sf.knn_indices.dtype == torch.int64 and sf.isStable.dtype == torch.bool
+        assert torch.equal(sf.track_id, trk.track_id)
+    # lazy render: (1,3,H,W) images of the current model
+    img = sf.renderImg
+    assert img.shape == (1, 3, H, W) and float(img.abs().sum()) > 0
+    assert sf.renderImg_conf_heat.shape == (1, 3, H, W)
+    # evaluate wrote the reference's scalars and the tracking results
+    out = sf.evaluate()
+    assert out is not None and os.path.exists(tmp_path / "out" / "m" / "tracking_rst.npy")
+    rst = np.load(tmp_path / "out" / "m" / "tracking_rst.npy", allow_pickle=True).tolist()
+    assert set(rst.keys()) == set(gt.keys()) and rst["000002"].shape == (3, 3)
+    assert out["reprojerr/pythonsuper_mean"] < 2.0
+    # update_ed / update_sfed_knn from the current state equal a fresh search by the oracle definitions
+    sf.update_ed()
+    sf.update_sfed_knn()
+    n = sf.sf_num
+    d_ref, i_ref = so.knn(sf.points.cpu(), sf.ED_nodes.points.cpu(), 4)
+    assert torch.equal(sf.knn_indices.cpu(), i_ref)
+    w_ref = so.softmax_exp_weights(d_ref, sf.ED_nodes.radii.cpu()[i_ref])
+    assert (sf.knn_w.cpu() - w_ref).abs().max() < 1e-12
+    # reset(): a second sequence on the same allocations gives the same frames
+    trk.reset()
+    for t in (1, 2):
+        f = G.frame(t)
+        b3 = trk.step(torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["color"]).cuda(), torch.from_numpy(f["K"]),
+                      torch.from_numpy(f["inv_K"]), f["time"], filename=f["filename"])
+    assert b3 is not None and n > 0
