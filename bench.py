@@ -128,6 +128,54 @@ def solver_report(trk, solve_ms):
             "achieved_gflops_band": float(n) * bw * bw / (ms * 1e-3) / 1e9, "bound": "latency (sequential pivot chain)"}
 
 
+OTHER_CONFIGS = {
+    # BASELINE.json configs other than the headline one: (H, W, mesh_step_size, option overrides, with_seg, data)
+    "c3a_lm_step16_640x480": (480, 640, 16, {}, False, "superv1"),
+    "c3b_adam_step16_640x480": (480, 640, 16, {"use_derived_gradient": False, "mesh_face": True, "optimizer": "Adam"}, False, "superv1"),
+    "c4_semantic_640x480": (480, 640, 32, {"use_derived_gradient": False, "mesh_face": True, "mesh_arap": False,
+                                           "sf_point_plane": False, "optimizer": "SGD", "method": "semantic-super",
+                                           "data": "superv2", "num_classes": 3, "sf_soft_seg_point_plane": True,
+                                           "sf_hard_seg_point_plane": False, "sf_bn_morph": True, "sf_bn_morph_weight": 0.1,
+                                           "hard_seg": False, "del_seg_classes": [], "disable_ssim_conf": True}, True, "superv2"),
+    "c5_lm_1280x1024": (1024, 1280, 32, {}, False, "superv1"),
+}
+
+
+def probe_config(name, dev, frames=8, warm=3):
+    """Frames/s of the device tracker on one of the other BASELINE configs (inputs resident in HBM, CUDA events around
+    the timed frames, L2 not flushed).  Parity of each at its own size: tests/test_gpu_sequences.py."""
+    from super_b200 import engine, synth
+    Hc, Wc, step, over, with_seg, data = OTHER_CONFIGS[name]
+    opt = make_opt()
+    opt.height, opt.width, opt.mesh_step_size = Hc, Wc, step
+    for k, v in over.items():
+        setattr(opt, k, v)
+    tex = synth.texture(Hc, Wc)
+    fr = [synth.frame_inputs(t, Hc, Wc, data=data, tex=tex, with_seg=with_seg, seg_speed=3.0 if with_seg else None)
+          for t in range(1, frames + warm + 2)]
+    dd = [torch.from_numpy(f["depth"]).to(dev) for f in fr]
+    seg = [torch.from_numpy(f["seg_conf"]).to(dev) for f in fr] if with_seg else [None] * len(fr)
+    dc = torch.from_numpy(fr[0]["color"]).to(dev)
+    K, iK = torch.from_numpy(fr[0]["K"]), torch.from_numpy(fr[0]["inv_K"])
+    trk = engine.Tracker(opt, device=dev)
+    for i in range(1 + warm):
+        trk.step(dd[i], dc, K, iK, fr[i]["time"], seg_scores=seg[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(1 + warm, 1 + warm + frames):
+        trk.step(dd[i], dc, K, iK, fr[i]["time"], seg_scores=seg[i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / frames
+    out = {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "ed_nodes": int(trk.ED.num), "surfels": trk.num_surfels(),
+           "frames_timed": frames, "solver": "LM" if opt.use_derived_gradient else opt.optimizer,
+           "half_bandwidth": None if trk.band is None else int(trk.band.bw)}
+    del trk
+    torch.cuda.empty_cache()
+    return out
+
+
 def reduce_over_ranks(total_ms, e2e_ms, info, world, device):
     """The only cross-rank step of the benchmark (replicas are independent sequences): MAX of the timed
     intervals over ranks and a gather of the per-rank summaries.  Backend-agnostic (NCCL on the GPUs, gloo in the
@@ -273,7 +321,7 @@ def run_cuda(args, rank, world, local_rank):
         "ms_per_step": total_ms / K, "ms_per_lm_iteration": (total_ms / K) / LM_ITERS,
         "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "configs_index": 1, "frames_timed": K, "surfels": N, "surfels_first_timed_frame": n_surf_first, "ed_nodes": int(trk.ED.num),
+        "config": {"workload": WORKLOAD, "configs_index": 1 if (H, W) == (480, 640) else 4, "frames_timed": K, "surfels": N, "surfels_first_timed_frame": n_surf_first, "ed_nodes": int(trk.ED.num),
                    "parallelism": f"{world} independent sequence replica(s), no data-path collective",
                    "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
@@ -294,6 +342,14 @@ def run_cuda(args, rank, world, local_rank):
     }
     if gathered:
         out["per_rank"] = gathered
+    if world == 1 and not args.no_configs:
+        # the other BASELINE configs, next to the headline (which stays on config 2): driver-visible frames/s
+        out["configs"] = {}
+        for name in OTHER_CONFIGS:
+            try:
+                out["configs"][name] = probe_config(name, dev)
+            except Exception as e:          # a probe must not take the headline line down
+                out["configs"][name] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(iters=args.cpu_iters)
     print(json.dumps(out), flush=True)
@@ -408,11 +464,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default, the headline): 640x480; c5: BASELINE config 5's 1280x1024 sequences, one per GPU")
     ap.add_argument("--cpu-iters", type=int, default=3)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c5":       # BASELINE config 5: 1280x1024 (~1.3 M surfels per sequence), one sequence per GPU
+        global H, W, METRIC, WORKLOAD
+        H, W = 1024, 1280
+        METRIC = "tracked frames/sec (ED warp+ICP+LM) at 1280x1024"
+        WORKLOAD = WORKLOAD.replace("640x480", "1280x1024")
     if args.impl == "reference":
         run_reference(args, rank)
         return
