@@ -301,9 +301,12 @@ add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* _
         }
     }
     if (!active) return;
+    // --hard_seg: a class with fewer than K nodes.  The reference asserts (utils/utils.py:236); padding the tuple with
+    // an unrelated node would bind the surfel to it with a weight of 0.15-0.25 and put duplicate ids into the node-set
+    // key, so such a pixel is simply not added.
+    if (bi[SB_KNN - 1] < 0) { add_flag[p] = 0; return; }
     bool any = false;
     for (int k = 0; k < SB_KNN; ++k) {
-        if (bi[k] < 0) { bi[k] = 0; bd[k] = 1e16; }      // class with fewer than K nodes (the reference asserts)
         bd[k] = __dsqrt_rn(bd[k]);
         any |= bd[k] <= ed_radii[bi[k]];       // nodes.py:501-502
         add_idx[4 * (size_t)p + k] = bi[k];

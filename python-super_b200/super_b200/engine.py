@@ -185,9 +185,12 @@ def dist2edge(opt, frame):
     from .utils.utils import pcd2depth
     v, u, _, _ = pcd2depth({("color", 0): torch.empty((1, 3, H, W), device="meta"), "K": _K44(frame.cam)},
                            frame.vmap[valid, :3].to(F64), round_coords=False)
-    q = torch.stack([u / W, v / H], dim=1).contiguous()
+    # divisors as device tensors: torch's CUDA tensor / python-scalar division multiplies by the reciprocal (1 ulp off the
+    # IEEE quotient the reference's CPU division gives)
+    Wd, Hd = torch.tensor(float(W), dtype=F64, device=dev), torch.tensor(float(H), dtype=F64, device=dev)
+    q = torch.stack([u / Wd, v / Hd], dim=1).contiguous()
     # the reference divides the INTEGER pixel coordinates of the edge points, i.e. in float32 (data_loader.py:507)
-    r = torch.stack([pts[:, 0].long() / W, pts[:, 1].long() / H], dim=1).to(F64).contiguous()
+    r = torch.stack([pts[:, 0].float() / Wd.float(), pts[:, 1].float() / Hd.float()], dim=1).to(F64).contiguous()
     rseg = torch.repeat_interleave(torch.arange(C, device=dev, dtype=I32), (off[1:] - off[:-1]).long())
     d, _ = ops.knn(q, r, 1, qseg=frame.seg[valid].contiguous(), rseg=rseg.contiguous())
     out[valid] = d[:, 0]
