@@ -121,7 +121,7 @@ def solver_report(trk, solve_ms):
     n, bw = trk.band.n, trk.band.bw
     ms = float(np.mean(solve_ms))
     variant = os.environ.get("SB_BAND_VARIANT", "4")
-    kern = ("band_from_fixed + band_reverse + band_chol3_dual + band_combine + band_chol3 + band_backsub4 kernels (fixed-point store -> f64 band, then sb_band_solve4_step: two-sided solve, LM step folded into the last kernel)"
+    kern = ("band_reverse (+ fixed-point store -> f64 band) + band_chol3_dual + band_combine + band_chol3 + band_backsub4 kernels (sb_band_solve4_step_fx: two-sided solve, LM step folded into the last kernel)"
             if variant == "4" else "band_chol3_kernel (sb_band_solve3)")
     return {"kernel": kern, "n": n, "half_bandwidth": bw, "ms_per_solve": ms,
             "solves_timed": len(solve_ms), "band_flops": float(n) * bw * bw, "dense_flops": float(n) ** 3 / 3.0,
@@ -231,7 +231,7 @@ def run_cuda(args, rank, world, local_rank):
     lib.LAUNCHES = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     # (begin, end) CUDA events on the launch stream around every J^T J pass and every linear solve of every timed frame, recorded inside sb_lm_frame (SbLMFrame.jtj_events / solve_events)
-    trk.event_sink = {"jtj": [], "solve": []}
+    trk.event_sink = {"jtj": [], "solve": [], "timeline": [], "timeline_frames": min(8, K)}
     trk.events_per_frame = (LM_ITERS, LM_ITERS)            # every J^T J pass (the first one of a frame is L2-cold) and every solve
     t_wall = time.perf_counter()
     for k in range(K):
@@ -255,6 +255,19 @@ def run_cuda(args, rank, world, local_rank):
             out.append(ms.value)
         return out
     jt_ms, solve_ms = ev_ms(trk.event_sink["jtj"]), ev_ms(trk.event_sink["solve"])
+    # live per-stage times of the LM loop (events after every stage of sb_lm_frame, first frames of the timed region)
+    names = ["lm_begin", "eval_decide", "gram", "scatter"]
+    for it in range(LM_ITERS):
+        names += ["solve"] + (["eval_decide", "gram", "scatter"] if it + 1 < LM_ITERS else ["loss_decide"])
+    stage_us = {}
+    for tev in trk.event_sink["timeline"]:
+        for i, nm in enumerate(names):
+            if i + 1 < len(tev):
+                stage_us.setdefault(nm, []).append(1e3 * ev_ms([(tev[i], tev[i + 1])])[0])
+        for e in tev:
+            lib.call("sb_event_destroy", e)
+    timeline = {k: {"launches_per_frame": len(v) // max(1, len(trk.event_sink["timeline"])), "us_mean": float(np.mean(v)),
+                    "us_per_frame": float(np.sum(v)) / max(1, len(trk.event_sink["timeline"]))} for k, v in stage_us.items()}
     for a, b in trk.event_sink["jtj"] + trk.event_sink["solve"]:
         lib.call("sb_event_destroy", a)
         lib.call("sb_event_destroy", b)
@@ -337,6 +350,7 @@ def run_cuda(args, rank, world, local_rank):
                      "algorithmic_bytes": b_pass, "launch_ms": jt_avg_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
         "solver": solver_report(trk, solve_ms),
+        "lm_timeline_live": timeline,
         "lm_trace_last_frame": {"loss": [float(x) for x in st["loss"]], "accept": [int(x) for x in st["accept"]]},
         "wall_s_timed_region": wall, "capacity_overflow": overflow, "tuple_order_redone": int(trk._order_redone),
     }

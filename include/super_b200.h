@@ -127,6 +127,10 @@ typedef struct SbLMFrame {
     int n_jtj_events;
     void* const* solve_events;  /* the same around the k-th linear solve (from_fixed + the five solver kernels) */
     int n_solve_events;
+    void* const* stage_events;  /* timeline: event 0 before the first launch, then one event after every stage of the frame,
+                                 * in issue order -- lm_begin, [eval, gram, scatter] and per iteration [solve, eval | loss,
+                                 * gram, scatter] -- for as many as the array covers */
+    int n_stage_events;
 } SbLMFrame;
 
 int sb_version(void);
@@ -173,6 +177,11 @@ int sb_warp_update(double* points, double* norms, const int* idx, const double* 
  * builds a COO Jacobian and calls torch.sparse.mm, /root/reference/super/loss.py:285-288,200-205). */
 int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, const int* node_pos,
                   int* block_bw, void* stream);
+
+/* The LM inputs of the surfels gathered into visiting order (row i <- row order[i] of points / knn_idx / knn_w): done once
+ * per frame, it makes every data-term pass of the frame coalesced (pass order = NULL with the gathered arrays). */
+int sb_gather_sorted(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
+                     const int* n_dev, double* out_points, int* out_idx, double* out_w, void* stream);
 
 /* Number of per-block partial sums sb_data_term_loss writes for a given capacity. */
 int sb_data_loss_blocks(int n_cap);
@@ -240,7 +249,7 @@ int sb_band_from_fixed(const long long* store, int n, int ldab, int fx_shift, in
 
 /* LM_Solver.LM, the whole loop of one frame: /root/reference/super/LM.py:81-122 (prepareCostTerm :53-79, Solver :38-51)
  * over DataLoss / ARAPLoss / RotLoss (/root/reference/super/loss.py:207-499), band path.  Enqueues
- * 4 + 9*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
+ * 2 + 8*iterations launches on `stream`; no host synchronisation.  On return (after the stream has run) f->beta holds the
  * result and the controller state the per-iteration trace (sb_lm_state_offsets).  A failed factorisation stops the
  * updates and leaves the last accepted beta (LM.py:99-103).  Bitwise reproducible. */
 /* CUDA events for timing launches inside sb_lm_frame on the stream they run on (bench.py's roofline) */
@@ -282,6 +291,13 @@ int sb_band_solve4(double* AB, int ldab, int n, int bw, double* g, const double*
 int sb_band_solve4_step(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
                         void* workspace, long long ws_bytes, int n_ctas, int* lm_failed, double* beta,
                         const int* pos_node, void* stream);
+/* sb_band_solve4_step with the system taken from one of two int64 fixed-point stores (AB | g; *sel names the current one,
+ * NULL = store 0): the conversion to the f64 work band AB / g rides in the solve's first kernel, which also clears the
+ * other store when zero_other != 0 (the frame loop's next assembly target). */
+int sb_band_solve4_step_fx(const long long* fx_store0, const long long* fx_store1, const int* sel, int fx_shift,
+                           int fx_gshift, int zero_other, double* AB, int ldab, int n, int bw, double* g, const double* u,
+                           double* dinv, int* info, void* workspace, long long ws_bytes, int n_ctas, int* lm_failed,
+                           double* beta, const int* pos_node, void* stream);
 int sb_band_max_bw(void);     /* widest half bandwidth the band solver takes */
 
 #ifdef SB_DEBUG_EXPORTS

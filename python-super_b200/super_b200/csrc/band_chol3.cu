@@ -1072,16 +1072,37 @@ struct TwoSided {
     int* flags; int nflags;             // the three instances' counters (one block), zeroed by band_reverse_kernel
 };
 
+// Source of the system when it arrives as one of two int64 fixed-point stores (AB | g, sb_lm_frame): the store the
+// device-resident selector names is converted on the fly -- this kernel then also writes the f64 work band the top
+// instance factors and clears the OTHER store for the next assembly (what band_from_fixed_kernel does as a launch of
+// its own: one launch and one gap less per LM iteration).
+struct FxSrc {
+    const long long* s0; const long long* s1; const int* sel; double inv_scale, inv_gscale; int zero_other;
+};
+
 // AB2 = the rows >= 32 m of the matrix with both index directions reversed (lower band storage again), its middle block
 // zeroed (the bottom instance accumulates only its Schur complement there); g2 likewise.
-__global__ void band_reverse_kernel(const double* __restrict__ AB, const double* __restrict__ g, double* __restrict__ AB2,
-                                    double* __restrict__ g2, TwoSided t) {
+__global__ void band_reverse_kernel(double* __restrict__ AB, double* __restrict__ g, double* __restrict__ AB2,
+                                    double* __restrict__ g2, TwoSided t, FxSrc fx) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = t.nB * t.ldab;
+    const long long n_ab = (long long)t.n * t.ldab;
+    const long long* src = nullptr;
+    if (fx.s0) {
+        const int sel = fx.sel ? *fx.sel : 0;
+        src = sel ? fx.s1 : fx.s0;
+        long long* oth = const_cast<long long*>(sel ? fx.s0 : fx.s1);
+        if (e < n_ab + t.n) {                                         // work copy of the whole system + clear the other store
+            const long long v = src[e];
+            if (e < n_ab) AB[e] = (double)v * fx.inv_scale;
+            else g[e - n_ab] = (double)v * fx.inv_gscale;
+            if (fx.zero_other) oth[e] = 0;
+        }
+    }
     if (e < t.nflags) t.flags[e] = 0;
     if (e < t.nB) {
         const int gi = t.n - 1 - e;                                   // original row
-        g2[e] = (gi >= t.m32 + t.Lm) ? g[gi] : 0.0;
+        g2[e] = (gi >= t.m32 + t.Lm) ? (src ? (double)src[n_ab + gi] * fx.inv_gscale : g[gi]) : 0.0;
     }
     if (e >= total) return;
     const int ip = e / t.ldab, dc = e - ip * t.ldab;                  // reversed row i', band column (j' - i' + bw)
@@ -1090,9 +1111,26 @@ __global__ void band_reverse_kernel(const double* __restrict__ AB, const double*
     if (jp >= 0 && dc <= t.bw) {
         const int gi = t.n - 1 - ip, gj = t.n - 1 - jp;               // original (row, col) with gi <= gj: stored at row gj
         const bool mid_i = gi < t.m32 + t.Lm, mid_j = gj < t.m32 + t.Lm;
-        if (!(mid_i && mid_j)) v = AB[(size_t)gj * t.ldab + (gi - gj + t.bw)];
+        if (!(mid_i && mid_j)) {
+            const size_t at = (size_t)gj * t.ldab + (gi - gj + t.bw);
+            v = src ? (double)src[at] * fx.inv_scale : AB[at];
+        }
     }
     AB2[e] = v;
+}
+
+// the conversion alone, for the systems that take the one-sided path
+__global__ void band_from_fixed3_kernel(FxSrc fx, long long n_ab, long long n_tot, double* __restrict__ AB,
+                                        double* __restrict__ g) {
+    const int sel = fx.sel ? *fx.sel : 0;
+    const long long* src = sel ? fx.s1 : fx.s0;
+    long long* oth = const_cast<long long*>(sel ? fx.s0 : fx.s1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tot; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = src[i];
+        if (i < n_ab) AB[i] = (double)v * fx.inv_scale;
+        else g[i - n_ab] = (double)v * fx.inv_gscale;
+        if (fx.zero_other) oth[i] = 0;
+    }
 }
 
 // middle system = the top instance's trailing block (original values + its complement) + the bottom instance's complement
@@ -1622,6 +1660,11 @@ long long sb_band3_prof_offset(int n, int bw) { return ws_bytes3(n, bw) - 1024; 
 
 int sb_band_max_bw(void) { return MAX_WB3 * NB; }
 
+int sb_band_solve4_step_fx(const long long* fx_store0, const long long* fx_store1, const int* sel, int fx_shift,
+                           int fx_gshift, int zero_other, double* AB, int ldab, int n, int bw, double* g, const double* u,
+                           double* dinv, int* info, void* workspace, long long ws_bytes, int n_ctas, int* lm_failed,
+                           double* beta, const int* pos_node, void* stream);
+
 int sb_band3_update_role(int n, int bw, int n_ctas) {
     const int NP = (n + NB - 1) / NB;
     int WB = (bw + NB - 1) / NB;
@@ -1714,10 +1757,17 @@ static int launch_step(const int* info, const double* x, int n, const StepArgs& 
 }
 
 static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const double* u, double* dinv, int* info,
-                       void* workspace, long long ws_bytes, int n_ctas, void* stream, StepArgs step) {
+                       void* workspace, long long ws_bytes, int n_ctas, void* stream, StepArgs step, FxSrc fx = FxSrc{}) {
     if (!AB || !g || !dinv || !info || !workspace || n <= 0 || bw < 0 || ldab < bw + 1) return SB_ERR_ARG;
     const int m = two_sided_m(n, bw);
     if (m == 0 || n_ctas < 8) {
+        if (fx.s0) {
+            const long long n_ab = (long long)n * ldab, n_tot = n_ab + n;
+            long long blocks = (n_tot + 255) / 256;
+            if (blocks > 1184) blocks = 1184;
+            band_from_fixed3_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(fx, n_ab, n_tot, AB, g);
+            SB_CHECK_LAUNCH();
+        }
         const int rc = sb_band_solve3(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream);
         return rc != SB_OK ? rc : launch_step(info, g, n, step, (cudaStream_t)stream);
     }
@@ -1757,7 +1807,10 @@ static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const dou
     if (!opt_in_smem(band_backsub2_kernel, smem_back, dc->smem_back2)) return SB_ERR_CUDA;
     // 1. reversed copy of the bottom part
     stamp4(0, st);
-    band_reverse_kernel<<<(t.nB * ldab + 255) / 256, 256, 0, st>>>(AB, g, AB2, g2, t);
+    {
+        const long long cover = fx.s0 ? (long long)n * ldab + n : (long long)t.nB * ldab;     // >= nB * ldab either way
+        band_reverse_kernel<<<(int)((cover + 255) / 256), 256, 0, st>>>(AB, g, AB2, g2, t, fx);
+    }
     SB_CHECK_LAUNCH();
     // 2. both ends at once
     stamp4(1, st);
@@ -1818,6 +1871,17 @@ int sb_band_solve4_step(double* AB, int ldab, int n, int bw, double* g, const do
                         const int* pos_node, void* stream) {
     if (!beta || !lm_failed) return SB_ERR_ARG;
     return solve4_impl(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream, StepArgs{lm_failed, beta, pos_node});
+}
+
+int sb_band_solve4_step_fx(const long long* fx_store0, const long long* fx_store1, const int* sel, int fx_shift,
+                           int fx_gshift, int zero_other, double* AB, int ldab, int n, int bw, double* g, const double* u,
+                           double* dinv, int* info, void* workspace, long long ws_bytes, int n_ctas, int* lm_failed,
+                           double* beta, const int* pos_node, void* stream) {
+    if (!fx_store0 || !fx_store1 || !beta || !lm_failed || fx_shift < 0 || fx_shift > 60 || fx_gshift < 0 || fx_gshift > 60)
+        return SB_ERR_ARG;
+    FxSrc fx{fx_store0, fx_store1, sel, ldexp(1.0, -fx_shift), ldexp(1.0, -fx_gshift), zero_other};
+    return solve4_impl(AB, ldab, n, bw, g, u, dinv, info, workspace, ws_bytes, n_ctas, stream,
+                       StepArgs{lm_failed, beta, pos_node}, fx);
 }
 
 #ifdef SB_DEBUG_EXPORTS

@@ -670,6 +670,21 @@ __global__ void tuple_keys_kernel(const int* __restrict__ knn_idx, int n_cap, co
     }
 }
 
+// the LM inputs of the surfels in visiting order: one gather per frame makes the ten evaluation passes coalesced
+__global__ void gather_sorted_kernel(const double* __restrict__ points, const int* __restrict__ knn_idx,
+                                     const double* __restrict__ knn_w, const int* __restrict__ order, int n_cap,
+                                     const int* n_dev, double* __restrict__ o_points, int* __restrict__ o_idx,
+                                     double* __restrict__ o_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_active(n_cap, n_dev)) return;
+    const int s = order[i];
+    o_points[3 * (size_t)i] = points[3 * (size_t)s];
+    o_points[3 * (size_t)i + 1] = points[3 * (size_t)s + 1];
+    o_points[3 * (size_t)i + 2] = points[3 * (size_t)s + 2];
+    reinterpret_cast<int4*>(o_idx)[i] = reinterpret_cast<const int4*>(knn_idx)[s];
+    reinterpret_cast<double4*>(o_w)[i] = reinterpret_cast<const double4*>(knn_w)[s];
+}
+
 DataArgs make_args(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
                    const int* n_dev, const double* ed_points, const double* beta, int J, const float* vmap,
                    const float* nmap, int H, int W, const double* intr, double lambda) {
@@ -745,6 +760,16 @@ int sb_data_term_jtj(const double* points, const int* knn_idx, const double* knn
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
     data_jtj_kernel<<<blocks, JTJ_WARPS * 32, smem, (cudaStream_t)stream>>>(a, M, loss_cur);
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+int sb_gather_sorted(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,
+                     const int* n_dev, double* out_points, int* out_idx, double* out_w, void* stream) {
+    if (!points || !knn_idx || !knn_w || !order || !out_points || !out_idx || !out_w) return SB_ERR_ARG;
+    if (n_cap <= 0) return SB_OK;
+    gather_sorted_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, knn_idx, knn_w, order, n_cap, n_dev,
+                                                                           out_points, out_idx, out_w);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
@@ -847,7 +872,7 @@ int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st) {
 
 // Gram pass over the rows of the last evaluation: J^T J and -J^T r into the store the decision made current (the
 // regularisers' terms are already there); returns at once on the device when the step was rejected.
-int launch_gram(const SbLMFrame* f, cudaStream_t st) {
+int launch_gram(const SbLMFrame* f, cudaStream_t st, int which) {
     MatView M;
     M.A = nullptr; M.g = nullptr;        // chosen in the kernel from the device-resident selector
     M.lda = f->ldab; M.bw = f->bw; M.node_pos = f->node_pos; M.overflow = f->band_overflow;
@@ -866,13 +891,17 @@ int launch_gram(const SbLMFrame* f, cudaStream_t st) {
     int blocks = (n_chunks + JTJ_WARPS - 1) / JTJ_WARPS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
-    jtj_gram_kernel<<<blocks, JTJ_WARPS * 32, smem, st>>>(f->n_cap, f->n_dev, M, ga);
-    SB_CHECK_LAUNCH();
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    jtj_scatter_kernel<<<8 * sms, 256, 0, st>>>(M, ga);
-    SB_CHECK_LAUNCH();
+    if (which & 1) {
+        jtj_gram_kernel<<<blocks, JTJ_WARPS * 32, smem, st>>>(f->n_cap, f->n_dev, M, ga);
+        SB_CHECK_LAUNCH();
+    }
+    if (which & 2) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        jtj_scatter_kernel<<<8 * sms, 256, 0, st>>>(M, ga);
+        SB_CHECK_LAUNCH();
+    }
     return SB_OK;
 }
 

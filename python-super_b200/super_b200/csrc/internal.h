@@ -7,6 +7,6 @@ namespace sbi {
 
 // data_term.cu: the two passes of the frame loop over the data term
 int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st);   // rows + keys + loss + LM decision (adopt: none)
-int launch_gram(const SbLMFrame* f, cudaStream_t st);                      // J^T J, -J^T r, ARAP / Rot into the current store
+int launch_gram(const SbLMFrame* f, cudaStream_t st, int which = 3);       // which: 1 = Gram records, 2 = scatter, 3 = both
 
 }  // namespace sbi

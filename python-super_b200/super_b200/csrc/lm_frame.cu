@@ -15,7 +15,7 @@
 //     input, so a copy is needed anyway) and clears the other store for the next assembly: no memset nodes, no side stream.
 //   * the data term runs as TWO launches: a high-occupancy evaluation pass that writes the Jacobian rows (and takes the
 //     LM decision in its last block) and a Gram pass that reads them back; after a reject the Gram pass returns at once.
-// One iteration = 9 launches: from_fixed, band_reverse, band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
+// One iteration = 8 launches: band_reverse (+ store -> band), band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
 // data_eval_decide (+ ARAP/Rot blocks + decision), jtj_gram (records), jtj_scatter.  No host synchronisation, no allocation.
 #include "common.cuh"
 #include "lm_state.cuh"
@@ -76,14 +76,28 @@ int sb_event_elapsed_ms(void* ev_begin, void* ev_end, float* ms) {
     return cudaEventElapsedTime(ms, (cudaEvent_t)ev_begin, (cudaEvent_t)ev_end) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
+// timeline event after a stage (SbLMFrame.stage_events)
+static int stamp(const SbLMFrame* f, int& next, cudaStream_t st) {
+    if (f->stage_events && next < f->n_stage_events &&
+        cudaEventRecord((cudaEvent_t)f->stage_events[next], st) != cudaSuccess)
+        return SB_ERR_CUDA;
+    ++next;
+    return SB_OK;
+}
+
 // k-th data-term pass of the frame: evaluation (+ decision) and Gram accumulation
-static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st) {
+static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st, int& ev) {
     const bool timed = f->jtj_events && 2 * k + 1 < f->n_jtj_events;
     if (timed && cudaEventRecord((cudaEvent_t)f->jtj_events[2 * k], st) != cudaSuccess) return SB_ERR_CUDA;
     int rc = sbi::launch_eval_decide(f, adopt, st);
     if (rc != SB_OK) return rc;
-    rc = sbi::launch_gram(f, st);
+    if (stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
+    rc = sbi::launch_gram(f, st, 1);
     if (rc != SB_OK) return rc;
+    if (stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
+    rc = sbi::launch_gram(f, st, 2);
+    if (rc != SB_OK) return rc;
+    if (stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
     if (timed && cudaEventRecord((cudaEvent_t)f->jtj_events[2 * k + 1], st) != cudaSuccess) return SB_ERR_CUDA;
     return SB_OK;
 }
@@ -109,26 +123,31 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
     if (cudaMemsetAsync(f->fx_store[1], 0, (size_t)n_tot * sizeof(long long), st) != cudaSuccess) return SB_ERR_CUDA;
     if (cudaMemsetAsync(f->info, 0, sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
     if (cudaMemsetAsync(f->rec_count, 0, sizeof(int), st) != cudaSuccess) return SB_ERR_CUDA;
+    int ev = 0;
+    if (stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
     int rc = sb_lm_begin(f->state, f->beta, f->best, f->J, f->u, f->v, f->minimal_loss, stream);
     if (rc != SB_OK) return rc;
-    rc = jtj_pass(f, 1, 0, st);
+    if (stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
+    rc = jtj_pass(f, 1, 0, st, ev);
     if (rc != SB_OK) return rc;
     for (int it = 0; it < f->iterations; ++it) {
         const bool timed = f->solve_events && 2 * it + 1 < f->n_solve_events;
         if (timed && cudaEventRecord((cudaEvent_t)f->solve_events[2 * it], st) != cudaSuccess) return SB_ERR_CUDA;
-        rc = from_fixed(f->fx_store[0], f->fx_store[1], state, f->n, f->ldab, f->fx_shift, f->fx_gshift, f->AB, f->g, 1, st);
-        if (rc != SB_OK) return rc;
-        rc = sb_band_solve4_step(f->AB, f->ldab, f->n, f->bw, f->g, &state->u, f->dinv, f->info, f->solver_ws,
-                                 f->solver_ws_bytes, f->n_ctas, &state->failed, f->beta, f->pos_node, stream);
+        // store -> f64 band rides in the solve's first kernel (band_reverse_kernel), which also clears the other store
+        rc = sb_band_solve4_step_fx(f->fx_store[0], f->fx_store[1], &state->sel, f->fx_shift, f->fx_gshift, 1, f->AB, f->ldab,
+                                    f->n, f->bw, f->g, &state->u, f->dinv, f->info, f->solver_ws, f->solver_ws_bytes,
+                                    f->n_ctas, &state->failed, f->beta, f->pos_node, stream);
         if (rc != SB_OK) return rc;
         if (timed && cudaEventRecord((cudaEvent_t)f->solve_events[2 * it + 1], st) != cudaSuccess) return SB_ERR_CUDA;
+        if (stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
         if (it + 1 < f->iterations) {
-            rc = jtj_pass(f, 0, it + 1, st);
+            rc = jtj_pass(f, 0, it + 1, st, ev);
         } else {      // after the last solve only the loss of the trial beta is needed
             rc = sb_data_term_loss_decide(f->points, f->knn_idx, f->knn_w, f->n_cap, f->n_dev, f->ed_points, f->beta, f->J,
                                           f->vmap, f->nmap, f->H, f->W, f->intr, f->lam_data, f->partials_loss,
                                           n_loss_blocks, f->state, f->ed_knn, f->lam_arap, f->lam_rot, f->use_arap,
                                           f->use_rot, f->beta, f->best, stream);
+            if (rc == SB_OK && stamp(f, ev, st) != SB_OK) return SB_ERR_CUDA;
         }
         if (rc != SB_OK) return rc;
     }

@@ -337,6 +337,7 @@ class Tracker:
                 rows = min(rows, self._n_exact + max(16384, 4 * max(0, self._last_growth)))
             self._order_rows = rows
             self._order = ops.tuple_order(self.cur.knn_idx[:rows], self.cur.n_dev, self.ED.node_pos, self.block_bw)
+            self._gather_sorted(rows)
         self._n_pinned.copy_(self.cur.n_dev, non_blocking=True)
         self._bw_pinned[0:1].copy_(self.block_bw, non_blocking=True)
         if self.band is not None:
@@ -344,6 +345,18 @@ class Tracker:
         self._bw_pinned[2:3].copy_(self.overflow, non_blocking=True)
         self._n_event = torch.cuda.Event()
         self._n_event.record()
+
+    def _gather_sorted(self, rows):
+        """The LM's view of the model in visiting order (points, node tuples, weights: final once the frame is compacted):
+        gathered once here, read coalesced by every data-term pass of the next frame."""
+        if getattr(self, "_sorted", None) is None:
+            self._sorted = NS(points=torch.empty((self.cap, 3), dtype=F64, device=self.dev),
+                              knn_idx=torch.empty((self.cap, 4), dtype=I32, device=self.dev),
+                              knn_w=torch.empty((self.cap, 4), dtype=F64, device=self.dev))
+        b, s = self.cur, self._sorted
+        call("sb_gather_sorted", ptr(b.points), ptr(b.knn_idx), ptr(b.knn_w), ptr(self._order), int(rows), ptr(b.n_dev),
+             ptr(s.points), ptr(s.knn_idx), ptr(s.knn_w), stream())
+        self._sorted_rows = int(rows)
 
     def _refresh_bound(self):
         if self._n_event is None:
@@ -373,6 +386,7 @@ class Tracker:
                 self._order = ops.tuple_order(self.cur.knn_idx[:n], self.cur.n_dev, self.ED.node_pos, self.block_bw)
                 self._order_rows = n
                 self._order_redone += 1
+                self._gather_sorted(n)
                 bwb = int(self.block_bw.item())
             self._plan_band(max(bwb, self.ED.block_bw_ed))
 
@@ -529,15 +543,23 @@ class Tracker:
             order = self._order
             if order is None:
                 order = ops.tuple_order(sfv.knn_indices, self.cur.n_dev, self.ED.node_pos, self.block_bw)
-            jev = sev = None
+            elif getattr(self, "_sorted", None) is not None and self._sorted_rows >= self.n_bound and self.band is not None:
+                # the frame loop reads the copies gathered into visiting order (coalesced); same values, same order
+                s, nb_ = self._sorted, self.n_bound
+                sfv = NS(points=s.points[:nb_], norms=sfv.norms, knn_indices=s.knn_idx[:nb_], knn_w=s.knn_w[:nb_], ED=self.ED)
+                order = None
+            jev = sev = tev = None
             if self.event_sink is not None:
                 jev, sev = self._new_events(2 * self.events_per_frame[0]), self._new_events(2 * self.events_per_frame[1])
                 self.event_sink["jtj"] += list(zip(jev[0::2], jev[1::2]))
                 self.event_sink["solve"] += list(zip(sev[0::2], sev[1::2]))
+                if "timeline" in self.event_sink and len(self.event_sink["timeline"]) < self.event_sink.get("timeline_frames", 0):
+                    tev = self._new_events(5 + 5 * int(opt.num_optimize_iterations))
+                    self.event_sink["timeline"].append(tev)
             beta, self.ws = lm.lm_solve(sfv, (frame.vmap, frame.nmap), frame.cam, opt, ws=self.ws, u=u, v=v,
                                         minimal_loss=minimal_loss, n_dev=self.cur.n_dev, order=order, band=self.band,
                                         cluster_size=self.cluster_size, jtj_events=jev, solve_events=sev,
-                                        row_capacity=self.cap)
+                                        row_capacity=self.cap, stage_events=tev)
         else:
             # autograd configuration of the reference (GraphFit, super.py:70-71): fused loss+gradient kernels
             seg = None

@@ -39,7 +39,8 @@ class SbLMFrame(ctypes.Structure):
                 ("fx_store", _P * 2), ("fx_shift", _I), ("fx_gshift", _I),
                 ("AB", _P), ("g", _P), ("band_overflow", _P), ("dinv", _P), ("info", _P),
                 ("solver_ws", _P), ("solver_ws_bytes", ctypes.c_longlong), ("n_ctas", _I),
-                ("jtj_events", _P), ("n_jtj_events", _I), ("solve_events", _P), ("n_solve_events", _I)]
+                ("jtj_events", _P), ("n_jtj_events", _I), ("solve_events", _P), ("n_solve_events", _I),
+                ("stage_events", _P), ("n_stage_events", _I)]
 
 
 class LMWorkspace:
@@ -76,7 +77,7 @@ def band_frame_ok(band, cluster_size):
 
 
 def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None, cluster_size=148,
-             jtj_events=None, solve_events=None, row_capacity=None):
+             jtj_events=None, solve_events=None, row_capacity=None, stage_events=None):
     """The whole LM loop of one frame in one C call (sb_lm_frame).  Same arguments and result as lm_solve.
     row_capacity: rows to size the Jacobian-row scratch for (the tracker passes its surfel capacity, so that the buffer
     is allocated once per sequence).
@@ -122,21 +123,22 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
     f.band_overflow, f.dinv, f.info = ptr(band.overflow), ptr(band.dinv), ptr(band.info)
     f.solver_ws, f.solver_ws_bytes, f.n_ctas = ptr(band.ws4), band.ws4.numel(), int(cluster_size)
     keep = []
-    for name, evs in (("jtj", jtj_events), ("solve", solve_events)):
+    for name, evs in (("jtj", jtj_events), ("solve", solve_events), ("stage", stage_events)):
         if evs:
             arr = (ctypes.c_void_p * len(evs))(*evs)
             keep.append(arr)
             setattr(f, name + "_events", ctypes.cast(arr, ctypes.c_void_p))
             setattr(f, "n_" + name + "_events", len(evs))
     call("sb_lm_frame", ctypes.byref(f), stream())
-    lib.LAUNCHES += 2 + 9 * f.iterations        # lm_begin, eval, Gram, scatter; per iteration from_fixed + 5 (solve) + eval + Gram + scatter | loss
+    lib.LAUNCHES += 2 + 8 * f.iterations        # lm_begin, eval, Gram, scatter; per iteration 5 (solve) + eval + Gram + scatter | loss
     band._dirty = False
     return ws.beta, ws
 
 
 
 def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None,
-             on_iter=None, band=None, cluster_size=16, jtj_events=None, solve_events=None, row_capacity=None):
+             on_iter=None, band=None, cluster_size=16, jtj_events=None, solve_events=None, row_capacity=None,
+             stage_events=None):
     """sf: object with points (N,3) f64, knn_indices (N,4) i32, knn_w (N,4) f64 and ED (points, knn_indices i32).
     maps: (vmap, nmap) dense float4 images of the new frame.  Returns beta (J,7) f64 (a view of the
     workspace) -- the same value LM_Solver.LM returns.
@@ -150,7 +152,7 @@ def lm_solve(sf, maps, cam, opt, ws=None, u=10.0, v=7.5, minimal_loss=1e10, orde
     if (on_iter is None and band_frame_ok(band, cluster_size) and bool(opt.sf_point_plane)
             and os.environ.get("SB_LM_STEPWISE", "0") != "1"):
         return lm_frame(sf, maps, cam, opt, ws, band, u, v, minimal_loss, order, n_dev, cluster_size, jtj_events,
-                        solve_events, row_capacity)
+                        solve_events, row_capacity, stage_events)
     n_cap = sf.points.shape[0]
     nb = ops.data_loss_blocks(n_cap)
     if ws.partials is None or ws.partials.numel() != nb:
