@@ -45,8 +45,23 @@ struct Eval {
 
 // Per-surfel evaluation.  Returns true when the surfel has a valid projective correspondence
 // (the reference's valid_pair & intrpl_valid, loss.py:229-246).  jrow: 28 doubles when GRAD.
-template <bool GRAD, bool CANON = false>
-__device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, double* jrow, int jstride) {
+// NS: the node data (ed_points | beta, 10 doubles per node: g[3], q[4], t[3]) is read from the shared-memory copy
+// `nodes_s` instead of global memory (the frame loop's evaluation pass: 80 node reads per surfel).
+//
+// Memory rounds per surfel (each a dependent L2/DRAM round trip at 20 warps per SM, which is what the pass' time is made
+// of -- ncu r2g/r2n: long-scoreboard stalls 6.6 per issue): (1) the surfel's own row, (2) the eight corner samples, all
+// issued together.  The reference's test of the ROUNDED pixel (valid_pair) needs no load of its own: round(x) is floor(x)
+// or ceil(x), so that pixel is one of the four corners -- if the corners are inside the image and valid so is the
+// rounded pixel, and if it is invalid or outside so is a corner; matched = corners inside & all four valid.
+__device__ __forceinline__ float4 ldg_f4_volatile(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <bool GRAD, bool CANON = false, bool NS = false>
+__device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, double* jrow, int jstride,
+                                            const double* nodes_s = nullptr) {
     const double* pp = a.points + 3 * (size_t)i;
     V3 p = v3(pp[0], pp[1], pp[2]);
     const int4 id4 = *reinterpret_cast<const int4*>(a.knn_idx + 4 * (size_t)i);
@@ -58,15 +73,25 @@ __device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, 
     V3 T = v3(0, 0, 0);
 #pragma unroll
     for (int k = 0; k < SB_KNN; ++k) {
-        const double* g = a.ed_points + 3 * ev.idx[k];
-        const double* b = a.beta + 7 * ev.idx[k];
-        V3 gk = v3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+        V3 gk;
+        double qw;
+        V3 qv, tk;
+        if (NS) {
+            const double* nd = nodes_s + 10 * ev.idx[k];
+            gk = v3(nd[0], nd[1], nd[2]);
+            qw = nd[3]; qv = v3(nd[4], nd[5], nd[6]); tk = v3(nd[7], nd[8], nd[9]);
+        } else {
+            const double* g = a.ed_points + 3 * ev.idx[k];
+            const double* b = a.beta + 7 * ev.idx[k];
+            gk = v3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+            qw = __ldg(b); qv = v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+            tk = v3(__ldg(b + 4), __ldg(b + 5), __ldg(b + 6));
+        }
         V3 cpk;
-        V3 tv = quat_rot_ref(v3(subr(p.x, gk.x), subr(p.y, gk.y), subr(p.z, gk.z)), __ldg(b),
-                             v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3)), cpk);
-        tv.x = addr(addr(tv.x, __ldg(b + 4)), gk.x);
-        tv.y = addr(addr(tv.y, __ldg(b + 5)), gk.y);
-        tv.z = addr(addr(tv.z, __ldg(b + 6)), gk.z);
+        V3 tv = quat_rot_ref(v3(subr(p.x, gk.x), subr(p.y, gk.y), subr(p.z, gk.z)), qw, qv, cpk);
+        tv.x = addr(addr(tv.x, tk.x), gk.x);
+        tv.y = addr(addr(tv.y, tk.y), gk.y);
+        tv.z = addr(addr(tv.z, tk.z), gk.z);
         if (k == 0) {
             T = v3(mulr(w[k], tv.x), mulr(w[k], tv.y), mulr(w[k], tv.z));
         } else {
@@ -79,38 +104,40 @@ __device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, 
     project_ref(T, a.cam, u, v);
     if (!(fabs(u) < 1e9 && fabs(v) < 1e9)) return false;
     const int H = a.cam.H, W = a.cam.W;
-    const long long P = (long long)H * W;
-    long long coords = round_ll(v) * W + round_ll(u);
-    if (coords < 0 || coords >= P) return false;
-    if (a.vmap[coords].w == 0.f) return false;
 
     double fv = floor(v), cv = ceil(v), fu = floor(u), cu = ceil(u);
     int iy[2] = {(int)fv, (int)cv}, ix[2] = {(int)fu, (int)cu};
     ev.flv = iy[0]; ev.cev = iy[1]; ev.flu = ix[0]; ev.ceu = ix[1];
     if (iy[0] < 0 || iy[1] >= H || ix[0] < 0 || ix[1] >= W) return false;
+    // all eight samples in flight at once; corner order (fl_v,fl_u),(fl_v,ce_u),(ce_v,fl_u),(ce_v,ce_u)
+    // (volatile: the compiler otherwise sinks the normal-map loads below the validity branch -- two rounds, not one)
+    float4 pv[4], nv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int pix = iy[c >> 1] * W + ix[c & 1];
+        pv[c] = ldg_f4_volatile(a.vmap + pix);
+        nv[c] = ldg_f4_volatile(a.nmap + pix);
+    }
+    if (pv[0].w == 0.f || pv[1].w == 0.f || pv[2].w == 0.f || pv[3].w == 0.f) return false;
     double dy[2] = {fv - v, cv - v}, dx[2] = {fu - u, cu - u};
     double wy[2] = {fmax(1.0 - fabs(dy[0]), 0.0), fmax(1.0 - fabs(dy[1]), 0.0)};
     double wx[2] = {fmax(1.0 - fabs(dx[0]), 0.0), fmax(1.0 - fabs(dx[1]), 0.0)};
     V3 o = v3(0, 0, 0), n = v3(0, 0, 0);
     V3 o_u = v3(0, 0, 0), o_v = v3(0, 0, 0), n_u = v3(0, 0, 0), n_v = v3(0, 0, 0);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {   // corner order (fl_v,fl_u),(fl_v,ce_u),(ce_v,fl_u),(ce_v,ce_u)
+    for (int c = 0; c < 4; ++c) {
         const int yi = c >> 1, xi = c & 1;
-        const int pix = iy[yi] * W + ix[xi];
-        const float4 pv = __ldg(a.vmap + pix);
-        if (pv.w == 0.f) return false;
-        const float4 nv = __ldg(a.nmap + pix);
         const double wgt_y = wy[yi], wgt_x = wx[xi];
         // reference: (U * w_y) * w_x, summed over corners in this order
-        o.x += ((double)pv.x * wgt_y) * wgt_x; o.y += ((double)pv.y * wgt_y) * wgt_x; o.z += ((double)pv.z * wgt_y) * wgt_x;
-        n.x += ((double)nv.x * wgt_y) * wgt_x; n.y += ((double)nv.y * wgt_y) * wgt_x; n.z += ((double)nv.z * wgt_y) * wgt_x;
+        o.x += ((double)pv[c].x * wgt_y) * wgt_x; o.y += ((double)pv[c].y * wgt_y) * wgt_x; o.z += ((double)pv[c].z * wgt_y) * wgt_x;
+        n.x += ((double)nv[c].x * wgt_y) * wgt_x; n.y += ((double)nv[c].y * wgt_y) * wgt_x; n.z += ((double)nv[c].z * wgt_y) * wgt_x;
         if (GRAD) {
             const double sx = dx[xi] >= 0.0 ? 1.0 : -1.0, sy = dy[yi] >= 0.0 ? 1.0 : -1.0;
             const double gu = wgt_y * sx, gv = wgt_x * sy;   // d/du, d/dv  (loss.py:147-150)
-            o_u.x += pv.x * gu; o_u.y += pv.y * gu; o_u.z += pv.z * gu;
-            o_v.x += pv.x * gv; o_v.y += pv.y * gv; o_v.z += pv.z * gv;
-            n_u.x += nv.x * gu; n_u.y += nv.y * gu; n_u.z += nv.z * gu;
-            n_v.x += nv.x * gv; n_v.y += nv.y * gv; n_v.z += nv.z * gv;
+            o_u.x += pv[c].x * gu; o_u.y += pv[c].y * gu; o_u.z += pv[c].z * gu;
+            o_v.x += pv[c].x * gv; o_v.y += pv[c].y * gv; o_v.z += pv[c].z * gv;
+            n_u.x += nv[c].x * gu; n_u.y += nv[c].y * gu; n_u.z += nv[c].z * gu;
+            n_v.x += nv[c].x * gv; n_v.y += nv[c].y * gv; n_v.z += nv[c].z * gv;
         }
     }
     V3 diff = v3(T.x - o.x, T.y - o.y, T.z - o.z);
@@ -125,14 +152,23 @@ __device__ __forceinline__ bool eval_surfel(const DataArgs& a, int i, Eval& ev, 
         av.x = n.x + cu_ * fxz;
         av.y = n.y + cv_ * fyz;
         av.z = n.z - (cu_ * fxz * T.x + cv_ * fyz * T.y) * iz;
+        if (NS) asm volatile("" ::: "memory");      // keep the node re-reads below the corner samples (registers)
 #pragma unroll
         for (int k = 0; k < SB_KNN; ++k) {
-            // node data re-read (L1 hits) instead of being kept live across the bilinear section
-            const double* g = a.ed_points + 3 * ev.idx[k];
-            const double* b = a.beta + 7 * ev.idx[k];
-            const V3 dk = v3(p.x - __ldg(g), p.y - __ldg(g + 1), p.z - __ldg(g + 2));
-            const double qwk = __ldg(b);
-            const V3 qvk = v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+            // node data re-read (shared memory / L1 hits) instead of being kept live across the bilinear section
+            V3 gk, qvk;
+            double qwk;
+            if (NS) {
+                const double* nd = nodes_s + 10 * ev.idx[k];
+                gk = v3(nd[0], nd[1], nd[2]);
+                qwk = nd[3]; qvk = v3(nd[4], nd[5], nd[6]);
+            } else {
+                const double* g = a.ed_points + 3 * ev.idx[k];
+                const double* b = a.beta + 7 * ev.idx[k];
+                gk = v3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+                qwk = __ldg(b); qvk = v3(__ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+            }
+            const V3 dk = v3(p.x - gk.x, p.y - gk.y, p.z - gk.z);
             const V3 cpk = cross3(qvk, dk);
             const double s = a.lambda * w[k];
             const double qd = dot3(qvk, dk), aq = dot3(av, qvk), ad = dot3(av, dk);
@@ -553,6 +589,9 @@ __global__ void __launch_bounds__(LOSS_BLOCK) data_loss_kernel(DataArgs a, doubl
 // ROWS: the evaluation pass of the frame loop -- slots of the visiting order instead of surfel ids, and the Jacobian row
 // of every slot is written out for the Gram pass (data_jtj_kernel<true>).
 struct DecideArgs { LMState* st; double* beta; double* best; int n; RegLossArgs rg; int flip_sel; int adopt; int* rec_count; };
+// (the regulariser blocks of the ROWS launch deliver their (arap, rot) loss sums behind the per-block data partials:
+//  partials[gridDim.x + 2 b], [.. + 1] for block b < reg_blocks -- the deciding block then adds reg_blocks pairs
+//  instead of re-evaluating 5 J residuals behind dependent loads)
 struct RowsOut { double* rows; unsigned long long* keys; int row_stride; };
 // The regularisers of the frame loop ride in the evaluation launch: its FIRST reg_blocks blocks assemble the ARAP / Rot
 // normal-equation terms at the pass' beta (one item per thread, ~5 k instructions of straight-line atomics: 20-30 us for
@@ -560,20 +599,35 @@ struct RowsOut { double* rows; unsigned long long* keys; int row_stride; };
 // into the store that is NOT current -- the one the Gram pass fills if the step is accepted; after a reject that store is
 // cleared again by band_from_fixed_kernel before it is next used.
 struct RegAsm { RegArgs reg; MatView M; double* store[2]; long long g_off; int reg_blocks; };
-__device__ __noinline__ void eval_reg_item(const RegArgs* reg, const MatView* M, int tid) {   // both in SHARED memory
+__device__ __noinline__ void eval_reg_item(const RegArgs* reg, const MatView* M, int tid, double* out) {   // all in SHARED memory
     double la, lr;
     reg_terms_item(*reg, tid, *M, true, la, lr);
+    out[0] = la; out[1] = lr;
 }
-constexpr int EVAL_BLOCK = 128;          // ROWS: 128 threads x 5 blocks per SM at <= 102 registers (20 warps, no spills)
-template <bool ROWS>
-__global__ void __launch_bounds__(ROWS ? EVAL_BLOCK : LOSS_BLOCK, ROWS ? 5 : 4)
+#ifndef EVAL_MINB
+#define EVAL_MINB 5
+#endif
+constexpr int EVAL_BLOCK = 128;          // ROWS: 128 threads x EVAL_MINB blocks per SM
+// NS: every surfel block first copies the node table (ed_points | beta -> 10 doubles per node) into shared memory; the
+// launcher chooses it when the table is small enough not to cost residency (C1: 266 nodes = 21 KB per block).
+constexpr int EVAL_NS_MAX_J = 400;
+template <bool ROWS, bool NS = false>
+__global__ void __launch_bounds__(ROWS ? EVAL_BLOCK : LOSS_BLOCK, ROWS ? EVAL_MINB : 4)
 data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d, RowsOut ro, RegAsm ra) {
     constexpr int BLOCK = ROWS ? EVAL_BLOCK : LOSS_BLOCK;
+    extern __shared__ double nodes_s[];
     __shared__ double red[BLOCK / 32];
     __shared__ bool s_last;
     const int n = n_active(a.n_cap, a.n_dev);
     double s = 0.0;
     const int rb = ROWS ? ra.reg_blocks : 0;
+    if (NS && (int)blockIdx.x >= rb) {
+        for (int e = threadIdx.x; e < 10 * a.J; e += BLOCK) {
+            const int j = e / 10, c = e - 10 * j;
+            nodes_s[e] = c < 3 ? __ldg(a.ed_points + 3 * j + c) : __ldg(a.beta + 7 * j + (c - 3));
+        }
+        __syncthreads();
+    }
     if (ROWS && (int)blockIdx.x < rb) {
         // arguments through shared memory: taking the address of a kernel parameter would move the whole parameter
         // block into local memory for every thread of the launch
@@ -585,21 +639,28 @@ data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d,
             s_M.A = ra.store[1 - d.st->sel];
             s_M.g = s_M.A + ra.g_off;
         }
+        __shared__ double s_lalr[BLOCK][2];
         __syncthreads();
-        eval_reg_item(&s_reg, &s_M, (int)(blockIdx.x * BLOCK + threadIdx.x));
+        eval_reg_item(&s_reg, &s_M, (int)(blockIdx.x * BLOCK + threadIdx.x), s_lalr[threadIdx.x]);
+        const double la = block_sum<BLOCK>(s_lalr[threadIdx.x][0], red);
+        const double lr = block_sum<BLOCK>(s_lalr[threadIdx.x][1], red);
+        if (threadIdx.x == 0) {
+            partials[gridDim.x + 2 * blockIdx.x] = la;
+            partials[gridDim.x + 2 * blockIdx.x + 1] = lr;
+        }
     }
     for (int i = ((int)blockIdx.x - rb) * BLOCK + threadIdx.x; i < n && (int)blockIdx.x >= rb;
          i += ((int)gridDim.x - rb) * BLOCK) {
         Eval ev;
         if (ROWS) {
             const int sid = a.order ? a.order[i] : i;
-            const bool ok = eval_surfel<true, true>(a, sid, ev, ro.rows + i, ro.row_stride);
+            const bool ok = eval_surfel<true, true, NS>(a, sid, ev, ro.rows + i, ro.row_stride, nodes_s);
             if (ok) {
                 ro.rows[(size_t)28 * ro.row_stride + i] = ev.r;
                 s += ev.r * ev.r;
             }
             ro.keys[i] = ok ? pack_key(ev.idx) : ~0ull;
-        } else if (eval_surfel<false>(a, i, ev, nullptr, 1)) {
+        } else if (eval_surfel<false, false, NS>(a, i, ev, nullptr, 1, nodes_s)) {
             s += ev.r * ev.r;
         }
     }
@@ -616,7 +677,7 @@ data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d,
     __threadfence();
     if (d.rec_count && threadIdx.x == 0) *d.rec_count = 0;       // Gram records of the pass that follows
     lm_decide_body<BLOCK>(d.st, partials, (int)gridDim.x, nullptr, d.beta, d.best, d.n, d.rg, d.flip_sel != 0,
-                          d.adopt != 0);
+                          d.adopt != 0, rb > 0 ? partials + gridDim.x : nullptr, rb);
 }
 
 // Per-surfel rows for parity tests and for the drop-in DataLoss.forward face.
@@ -826,17 +887,27 @@ int sb_data_term_rows(const double* points, const int* knn_idx, const double* kn
 namespace sbi {
 
 // resident blocks of the evaluation pass on the current device (one wave: the grid-stride loop balances the rest)
-static int eval_resident() {
-    static int resident[64] = {0};
+static int eval_resident(bool ns, size_t smem) {
+    static int resident[2][64] = {{0}};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-    if (resident[dev] == 0) {
+    if (resident[ns][dev] == 0) {
         int per_sm = 0, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_eval_decide_kernel<true>, EVAL_BLOCK, 0);
-        resident[dev] = (per_sm > 0 ? per_sm : 1) * sms;
+        if (ns) {
+            // the largest table the NS form is chosen for, so that the cached residency holds for every J below it
+            const size_t smem_max = (size_t)10 * EVAL_NS_MAX_J * sizeof(double);
+            if (cudaFuncSetAttribute(data_eval_decide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_max) != cudaSuccess)
+                return -1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_eval_decide_kernel<true, true>, EVAL_BLOCK, smem_max);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_eval_decide_kernel<true, false>, EVAL_BLOCK, 0);
+        }
+        resident[ns][dev] = (per_sm > 0 ? per_sm : 1) * sms;
     }
-    return resident[dev];
+    (void)smem;
+    return resident[ns][dev];
 }
 
 // evaluation pass at f->beta: rows + keys for the Gram pass, loss partials, LM decision in the last block.
@@ -859,13 +930,16 @@ int launch_eval_decide(const SbLMFrame* f, int adopt, cudaStream_t st) {
     const int reg_threads = (f->use_arap ? f->J * SB_KNN : 0) + (f->use_rot ? f->J : 0);
     ra.reg_blocks = (reg_threads + EVAL_BLOCK - 1) / EVAL_BLOCK;
     int blocks = (f->n_cap + EVAL_BLOCK - 1) / EVAL_BLOCK + ra.reg_blocks;
-    const int resident = eval_resident();
+    const bool ns = f->J <= EVAL_NS_MAX_J;
+    const size_t smem = ns ? (size_t)10 * f->J * sizeof(double) : 0;
+    const int resident = eval_resident(ns, smem);
     if (resident <= 0) return SB_ERR_CUDA;
     if (blocks > resident && resident > 2 * ra.reg_blocks) blocks = resident;     // one wave: regulariser + surfel blocks
-    if (blocks > f->n_partials_loss) blocks = f->n_partials_loss;
+    if (blocks + 2 * ra.reg_blocks > f->n_partials_loss) blocks = f->n_partials_loss - 2 * ra.reg_blocks;
     if (blocks <= ra.reg_blocks) return SB_ERR_WORKSPACE;
-    data_eval_decide_kernel<true><<<blocks, EVAL_BLOCK, 0, st>>>(a, f->partials_loss, d,
-                                                                RowsOut{f->rows, f->keys, f->row_stride}, ra);
+    const RowsOut ro{f->rows, f->keys, f->row_stride};
+    if (ns) data_eval_decide_kernel<true, true><<<blocks, EVAL_BLOCK, smem, st>>>(a, f->partials_loss, d, ro, ra);
+    else data_eval_decide_kernel<true, false><<<blocks, EVAL_BLOCK, 0, st>>>(a, f->partials_loss, d, ro, ra);
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

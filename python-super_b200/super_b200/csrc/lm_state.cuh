@@ -60,7 +60,7 @@ struct RegLossArgs {     // ed_points == nullptr: the ARAP / Rot losses come in 
 template <int BLOCK>
 __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partials, int n_partials, double* loss_arap_rot,
                                                double* beta, double* best, int n, RegLossArgs rg, bool flip_sel = false,
-                                               bool adopt = false) {
+                                               bool adopt = false, const double* reg_part = nullptr, int n_reg_part = 0) {
     if (adopt) {
         if (threadIdx.x == 0) { st->sel ^= 1; st->last_accept = 1; }
         return;
@@ -68,10 +68,30 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
     __shared__ double red[BLOCK / 32];
     __shared__ int s_accept;
     __shared__ double s_reg[2];
+    // This runs on ONE block behind everybody else: every dependent L2 round trip here is on the frame's critical path
+    // (r2o launch list: 11 us of the evaluation launch).  Loads are issued in batches, sums keep a fixed order.
     double s = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += BLOCK) s += __ldcg(partials + i);
+    {
+        constexpr int PER = 8;
+        for (int base = 0; base < n_partials; base += PER * BLOCK) {
+            double v[PER];
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int i = base + q * BLOCK + threadIdx.x;
+                v[q] = i < n_partials ? __ldcg(partials + i) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < PER; ++q) s += v[q];
+        }
+    }
     s = block_sum<BLOCK>(s, red);
-    if (rg.ed_points) {                      // the regularisers' losses of the stepped beta, in this launch
+    if (reg_part) {                          // per-block (arap, rot) sums delivered by the regulariser blocks of this launch
+        if (threadIdx.x == 0) {
+            double la = 0.0, lr = 0.0;
+            for (int b = 0; b < n_reg_part; ++b) { la += __ldcg(reg_part + 2 * b); lr += __ldcg(reg_part + 2 * b + 1); }
+            s_reg[0] = la; s_reg[1] = lr;
+        }
+    } else if (rg.ed_points) {               // the regularisers' losses of the stepped beta, in this launch
         double la = 0.0, lr = 0.0;
         if (rg.use_arap)
             for (int i = threadIdx.x; i < rg.J * SB_KNN; i += BLOCK) la += arap_loss_item(rg.ed_points, rg.ed_knn, beta, i, rg.lam_arap);
@@ -87,7 +107,8 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
             s_accept = -1;
             st->last_accept = 0;
         } else {
-            const double la = rg.ed_points ? s_reg[0] : loss_arap_rot[0], lr = rg.ed_points ? s_reg[1] : loss_arap_rot[1];
+            const bool own = reg_part || rg.ed_points;
+            const double la = own ? s_reg[0] : loss_arap_rot[0], lr = own ? s_reg[1] : loss_arap_rot[1];
             const double loss = s + la + lr;
             const bool acc = loss < st->minimal_loss;
             if (it < 64) {
@@ -110,9 +131,23 @@ __device__ __forceinline__ void lm_decide_body(LMState* st, const double* partia
     __syncthreads();
     const int acc = s_accept;
     if (acc < 0) return;
-    for (int i = threadIdx.x; i < n; i += BLOCK) {
-        if (acc) best[i] = beta[i];
-        else beta[i] = best[i];
+    {
+        const double* src = acc ? beta : best;
+        double* dst = acc ? best : beta;
+        constexpr int PER = 8;
+        for (int base = 0; base < n; base += PER * BLOCK) {
+            double v[PER];
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int i = base + q * BLOCK + threadIdx.x;
+                v[q] = i < n ? __ldcg(src + i) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int i = base + q * BLOCK + threadIdx.x;
+                if (i < n) dst[i] = v[q];
+            }
+        }
     }
 }
 
