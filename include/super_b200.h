@@ -178,6 +178,14 @@ int sb_warp_update(double* points, double* norms, const int* idx, const double* 
 int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* keys, const int* node_pos,
                   int* block_bw, void* stream);
 
+/* The sorted order itself in one call: keys with ceil(log2(J+1)) bits per node id and a stable LSD radix sort over just
+ * those 4*bits bits (5 passes at J = 266 instead of the 8 of a 64-bit key).  keys / keys_alt (n_cap u64), rows (n_cap i32)
+ * and temp (sb_tuple_order_temp_bytes) are scratch; order (n_cap i32) receives the visiting order. */
+long long sb_tuple_order_temp_bytes(int n_cap);
+int sb_tuple_order(const int* knn_idx, int n_cap, const int* n_dev, int J, const int* node_pos, int* block_bw,
+                   unsigned long long* keys, unsigned long long* keys_alt, int* rows, int* order, void* temp,
+                   long long temp_bytes, void* stream);
+
 /* The LM inputs of the surfels gathered into visiting order (row i <- row order[i] of points / knn_idx / knn_w): done once
  * per frame, it makes every data-term pass of the frame coalesced (pass order = NULL with the gathered arrays). */
 int sb_gather_sorted(const double* points, const int* knn_idx, const double* knn_w, const int* order, int n_cap,

@@ -52,6 +52,14 @@ struct Args3 {
     int debug;         // 1: U skips its tile work, 2: no back substitution, 4: cycle counters
 };
 
+// timing experiments / cycle counters exist only in the SB_DEBUG_EXPORTS build: in the product build every debug test is a
+// compile-time 0, so the counters, their registers and their code are gone (the pivot CTA's loop is instruction-fetch sensitive)
+#ifdef SB_DEBUG_EXPORTS
+#define DBGF(a) ((a).debug)
+#else
+#define DBGF(a) 0
+#endif
+
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -540,7 +548,7 @@ __device__ void role_P(const Args3& a, double* smem) {
     long long wacc[5] = {0, 0, 0, 0, 0};
     long long tsacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t0 = clock64(), t1;
-    const bool prof = (a.debug & 4) != 0;
+    const bool prof = (DBGF(a) & 4) != 0;
     // BAR.SYNC is issued "defer blocking": a clock read right behind it executes before the barrier completes.
     // The volatile shared load below cannot, and the clock read is made control-dependent on its value.
 #define PROF(slot) do { if (prof) { if (*(volatile double*)dinvs != 1.2345e300) t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; } } while (0)
@@ -630,11 +638,11 @@ __device__ void role_P(const Args3& a, double* smem) {
             long long q0 = 0, q1;
 #define IOPROF(slot) do { if (prof && lane == 0) { q1 = clock64(); ioacc[slot] += q1 - q0; q0 = q1; } } while (0)
             if (prof && lane == 0) q0 = clock64();
-            if (k >= 1 && it == 0 && !(a.debug & 8)) red_release(diag_done + (k - 1), 1);   // covers warp 1's stores (bar.sync above)
+            if (k >= 1 && it == 0 && !(DBGF(a) & 8)) red_release(diag_done + (k - 1), 1);   // covers warp 1's stores (bar.sync above)
             IOPROF(0);
             {   // NaN-arm the other column buffer for panel k+1 (its last reader finished before the barrier)
                 double* Ln = Lcol + ((k + 1) & 1) * T36;
-                if (!(a.debug & 32) && !tail) for (int e = it; e < T36; e += 96) Ln[e] = qnan;
+                if (!(DBGF(a) & 32) && !tail) for (int e = it; e < T36; e += 96) Ln[e] = qnan;
                 if (it < NB) dinvs[((k + 1) & 1) * NB + it] = qnan;
             }
             bar_sync(1, 224);                                              // L(k,k-1) is complete
@@ -645,7 +653,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                 if (iw == 2) {
                     bar_sync(3, 96);
                     IOPROF(2);
-                    if (lane == 0 && !(a.debug & 8)) red_release(rows_done + (k - 1), 1);
+                    if (lane == 0 && !(DBGF(a) & 8)) red_release(rows_done + (k - 1), 1);
                     IOPROF(3);
                 } else {
                     bar_arrive(3, 96);
@@ -762,7 +770,7 @@ __device__ void role_R(const Args3& a, double* smem) {
     double* ys = LinvS + T33;                  // NB
     double* Lrows = ys + NB;                   // 8 x T33
 
-    if (a.debug & 8) return;
+    if (DBGF(a) & 8) return;
     for (int i = tid; i < NP * NB; i += THREADS) s[i] = (i < n) ? __ldcg(a.g + i) : 0.0;
     for (int p = 0; p < NP && p < a.ke; ++p) {
         cta_wait(diag_done + p, 1);
@@ -781,7 +789,7 @@ __device__ void role_R(const Args3& a, double* smem) {
         }
         const int nrows = min(NP - 1, p + WB) - p;
         if (nrows > 0) {
-            if (a.debug & 1) __syncthreads(); else cta_wait(rows_done + p, nrows);    // also orders ys
+            if (DBGF(a) & 1) __syncthreads(); else cta_wait(rows_done + p, nrows);    // also orders ys
             for (int q0 = 0; q0 < nrows; q0 += 8) {
                 const int nq = min(8, nrows - q0);
                 for (int q = 0; q < nq; ++q)
@@ -805,8 +813,8 @@ __device__ void role_R(const Args3& a, double* smem) {
         }
     }
 
-    if ((a.debug & 4) && tid == 0) a.prof[10] = clock64();
-    if (a.debug & 2) {
+    if ((DBGF(a) & 4) && tid == 0) a.prof[10] = clock64();
+    if (DBGF(a) & 2) {
         for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
         return;
     }
@@ -817,7 +825,7 @@ __device__ void role_R(const Args3& a, double* smem) {
     }
     backsub(a, s, NP);
     for (int i = tid; i < n; i += THREADS) a.g[i] = s[i];
-    if ((a.debug & 4) && tid == 0) a.prof[11] = clock64();
+    if ((DBGF(a) & 4) && tid == 0) a.prof[11] = clock64();
 }
 
 // =====================================================================================================
@@ -838,7 +846,7 @@ __device__ void role_U(const Args3& a, double* smem) {
     double* LIs = Bs + T36;
     double* LJs = LIs + T36;
     const int fr = lane >> 2, fc = lane & 3;
-    const bool uprof = (a.debug & 4) && ui == 1;
+    const bool uprof = (DBGF(a) & 4) && ui == 1;
     long long ut[6] = {0, 0, 0, 0, 0, 0}, u0 = clock64(), u1;
 #define UPROF(slot) do { if (uprof) { if (*(volatile double*)LinvS != 1.2345e300) u1 = clock64(); ut[slot] += u1 - u0; u0 = u1; } } while (0)
 
@@ -849,7 +857,7 @@ __device__ void role_U(const Args3& a, double* smem) {
         int t = ((ui - p) % NU + NU) % NU;
         bool first = true;
         int rows_written = 0;
-        for (; t < ntiles && !(a.debug & 1); t += NU) {
+        for (; t < ntiles && !(DBGF(a) & 1); t += NU) {
             if (t == 0) continue;                                         // tile (p+1,p+1) belongs to P
             int ri = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
             while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
@@ -960,7 +968,7 @@ __device__ void role_U2(const Args3& a, double* smem) {
     for (int p = 0; p < NP && p < a.ke; ++p) {
         const int last = min(NP - 1, p + WB);
         const int nrows = last - p;
-        if (a.debug & 1) {          // timing experiments: no trailing work, but P still waits for the hot flag
+        if (DBGF(a) & 1) {          // timing experiments: no trailing work, but P still waits for the hot flag
             if (ui == 0 && tid == 0) red_release(a.flags + 3 * NP + p, 2);
             continue;
         }
@@ -1364,7 +1372,7 @@ __global__ void __launch_bounds__(THREADS, 1) band_backsub4_kernel(Args3 a0, Arg
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_poison;                                 // a poll of the chain timed out (time slicing, a debugger): report it
     if (tid == 0) s_poison = 0;
-    const bool prof = (a.debug & 1024) && top && rank == 0 && tid == 0;
+    const bool prof = (DBGF(a) & 1024) && top && rank == 0 && tid == 0;
     if (prof) { a.prof[56] = clock64(); for (int d = 0; d < BS4_MAXWB; ++d) a.prof[70 + d] = 0; }
     const int NP = a.NP, WB = a.WB, ke = a.ke, ke32 = NB * ke;
     double* xbuf = (double*)(smem_bs4 + L.xbuf);

@@ -13,6 +13,8 @@
 // 7x7 node-pair blocks, S[0:28,28] is J^T r and S[28,28] is sum r^2.  The accumulator is flushed with
 // one f64 atomic per entry only when the node tuple changes.  No 3 400-op ATen chain, no COO
 // Jacobian, no SpGEMM.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "lm_state.cuh"
 #include "reg_terms.cuh"
@@ -731,6 +733,46 @@ __global__ void tuple_keys_kernel(const int* __restrict__ knn_idx, int n_cap, co
     }
 }
 
+// The same key with `bits` bits per node id (J < 2^bits), 4*bits significant bits in all, and the row index next to it:
+// the radix sort behind it (sb_tuple_order) then needs ceil(4*bits/8) passes instead of the 8 of a 64-bit key.
+__global__ void tuple_keys_compact_kernel(const int* __restrict__ knn_idx, int n_cap, const int* n_dev, int bits,
+                                          unsigned long long* __restrict__ keys, int* __restrict__ rows,
+                                          const int* __restrict__ node_pos, int* __restrict__ block_bw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int span = 0;
+    if (i < n_cap) {
+        const int n = n_active(n_cap, n_dev);
+        rows[i] = i;
+        if (i >= n) {
+            keys[i] = (bits >= 16) ? ~0ull : ((1ull << (4 * bits)) - 1ull);     // an all-ones field is no node id
+        } else {
+            const int4 id = *reinterpret_cast<const int4*>(knn_idx + 4 * (size_t)i);
+            const int idx[4] = {id.x, id.y, id.z, id.w};
+            unsigned long long key = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int rank = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rank += (idx[j] < idx[k]) ? 1 : 0;
+                key |= (unsigned long long)(unsigned)idx[k] << (bits * (3 - rank));
+            }
+            keys[i] = key;
+            if (block_bw) {
+                int lo = 1 << 30, hi = -1;
+                for (int k = 0; k < 4; ++k) {
+                    const int p = node_pos ? node_pos[idx[k]] : idx[k];
+                    lo = min(lo, p); hi = max(hi, p);
+                }
+                span = hi - lo;
+            }
+        }
+    }
+    if (block_bw) {
+        span = __reduce_max_sync(0xffffffffu, span);
+        if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(block_bw, span);
+    }
+}
+
 // the LM inputs of the surfels in visiting order: one gather per frame makes the ten evaluation passes coalesced
 __global__ void gather_sorted_kernel(const double* __restrict__ points, const int* __restrict__ knn_idx,
                                      const double* __restrict__ knn_w, const int* __restrict__ order, int n_cap,
@@ -795,6 +837,35 @@ int sb_tuple_keys(const int* knn_idx, int n_cap, const int* n_dev, long long* ke
     tuple_keys_kernel<<<(n_cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(knn_idx, n_cap, n_dev, keys, node_pos,
                                                                            block_bw);
     SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+static int order_bits(int J) {
+    int b = 1;
+    while (b < 16 && (1 << b) <= J) ++b;       // J <= 2^b - 1: the all-ones field stays free for the sentinel
+    return b;
+}
+
+long long sb_tuple_order_temp_bytes(int n_cap) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int*)nullptr, (int*)nullptr, n_cap < 1 ? 1 : n_cap, 0, 64, (cudaStream_t)0);
+    return (long long)bytes;
+}
+
+int sb_tuple_order(const int* knn_idx, int n_cap, const int* n_dev, int J, const int* node_pos, int* block_bw,
+                   unsigned long long* keys, unsigned long long* keys_alt, int* rows, int* order, void* temp,
+                   long long temp_bytes, void* stream) {
+    if (!knn_idx || !keys || !keys_alt || !rows || !order || !temp || J <= 0 || J > 65535) return SB_ERR_ARG;
+    if (n_cap <= 0) return SB_OK;
+    if (temp_bytes < sb_tuple_order_temp_bytes(n_cap)) return SB_ERR_WORKSPACE;
+    const int bits = order_bits(J);
+    cudaStream_t st = (cudaStream_t)stream;
+    tuple_keys_compact_kernel<<<(n_cap + 255) / 256, 256, 0, st>>>(knn_idx, n_cap, n_dev, bits, keys, rows, node_pos, block_bw);
+    SB_CHECK_LAUNCH();
+    size_t tb = (size_t)temp_bytes;
+    if (cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_alt, rows, order, n_cap, 0, 4 * bits, st) != cudaSuccess)
+        return SB_ERR_CUDA;
     return SB_OK;
 }
 

@@ -97,7 +97,7 @@ def stream():
 
 
 # kernels of OURS launched per C-ABI call (library kernels such as the CUB scans are not counted)
-KERNELS_PER_CALL = {"sb_knn": 1, "sb_knn_class": 1, "sb_knn_weights": 1, "sb_reweight": 1, "sb_warp_update": 2, "sb_tuple_keys": 1,
+KERNELS_PER_CALL = {"sb_knn": 1, "sb_knn_class": 1, "sb_knn_weights": 1, "sb_reweight": 1, "sb_warp_update": 2, "sb_tuple_keys": 1, "sb_tuple_order": 1,
                     "sb_data_term_jtj": 1, "sb_data_term_loss": 1, "sb_data_term_loss_decide": 1, "sb_data_term_rows": 1, "sb_lm_begin": 1,
                     "sb_reg_terms": 1, "sb_lm_damp": 1, "sb_lm_step": 1, "sb_lm_decide": 1, "sb_lm_decide_reg": 1, "sb_preprocess": 2,
                     "sb_fuse": 6, "sb_compact": 2, "sb_band_solve3": 1, "sb_band_from_fixed": 1, "sb_band_solve4": 5, "sb_band_solve4_step": 5, "sb_band_solve4_step_fx": 5, "sb_gather_sorted": 1, "sb_graph_build": 1, "sb_gf_data": 1, "sb_gf_morph": 1, "sb_gf_reg": 1,

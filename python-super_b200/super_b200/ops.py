@@ -207,14 +207,29 @@ def data_term_loss_decide(points, knn_idx, knn_w, ed_points, ed_knn, beta, best,
          ptr(beta), ptr(best), stream())
 
 
-def tuple_order(knn_idx, n_dev=None, node_pos=None, block_bw=None):
+_ORDER_WS = {}
+
+
+def tuple_order(knn_idx, n_dev=None, node_pos=None, block_bw=None, J=None):
     """Surfel ids sorted by their (ordered) 4-tuple of ED nodes: the visiting order of the J^T J
     kernel, so that a warp's 32 surfels share their node blocks.  Rows beyond *n_dev sort last.
-    block_bw (1,) i32: atomically max-ed with the node-block half-bandwidth the tuples need."""
+    block_bw (1,) i32: atomically max-ed with the node-block half-bandwidth the tuples need.
+    J (number of ED nodes) bounds the key width: 4*ceil(log2(J+1)) bits are sorted (sb_tuple_order)."""
     n = knn_idx.shape[0]
-    keys = torch.empty(n, dtype=torch.int64, device=knn_idx.device)
-    call("sb_tuple_keys", ptr(knn_idx), n, ptr(n_dev), ptr(keys), ptr(node_pos), ptr(block_bw), stream())
-    return torch.sort(keys, stable=True)[1].to(I32)
+    dev = knn_idx.device
+    if J is None:
+        J = int(node_pos.shape[0]) if node_pos is not None else 65535
+    ws = _ORDER_WS.get(dev)
+    if ws is None or ws[0] < n:
+        cap = max(n, 1)
+        tb = int(lib.load().sb_tuple_order_temp_bytes(cap))
+        ws = (cap, torch.empty(cap, dtype=torch.int64, device=dev), torch.empty(cap, dtype=torch.int64, device=dev),
+              torch.empty(cap, dtype=I32, device=dev), torch.empty(max(tb, 8), dtype=torch.uint8, device=dev), tb)
+        _ORDER_WS[dev] = ws
+    order = torch.empty(n, dtype=I32, device=dev)
+    call("sb_tuple_order", ptr(knn_idx), n, ptr(n_dev), int(J), ptr(node_pos), ptr(block_bw), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]),
+         ptr(order), ptr(ws[4]), ws[5], stream())
+    return order
 
 
 # ---- LM regularisers / controller ----------------------------------------------------------------
