@@ -362,7 +362,19 @@ __device__ __forceinline__ void warp_tinv_trailing(const volatile double* Lcol, 
     }
 }
 
+// block row b (8 rows) of the shared inverse tile -> global tile (what U and R read)
+__device__ __forceinline__ void publish_inv_rows(const double* Ls, double* __restrict__ Lg, int b, int lane) {
+    const int c0 = 8 * b;
+    double r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = ((const volatile double*)Ls)[(c0 + i) * S36 + lane];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) __stcg(Lg + (c0 + i) * NB + lane, (r[i] == r[i]) ? r[i] : 0.0);
+}
+
 // Ls: shared inverse tile (stride S36; diagonal blocks NaN-armed, rest zero), Lg: global tile, Sc: 3 x 96 scratch.
+// Block rows 0..2 are published to Lg as they complete; the LAST one is left to the caller (publish_inv_rows(.., 3, ..)
+// behind the next top-of-panel barrier): its 8 loads + 8 stores sat on the pivot chain's panel-to-panel path.
 __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const volatile double* dinvs, double* Ls,
                                                   double* __restrict__ Lg, double* __restrict__ Sc, int lane,
                                                   bool& failed, long long* wacc = nullptr, long long* ts = nullptr,
@@ -444,14 +456,8 @@ __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const vola
             __syncwarp();
             WPROF(3);
         }
-        // block row b of the inverse is final: publish it
-        {
-            double r[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = ((const volatile double*)Ls)[(c0 + i) * S36 + lane];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) __stcg(Lg + (c0 + i) * NB + lane, (r[i] == r[i]) ? r[i] : 0.0);
-        }
+        // block row b of the inverse is final: publish it (the last one: see above)
+        if (b < 3) publish_inv_rows(Ls, Lg, b, lane);
         WPROF(4);
         if (ts) ts[b] += clock64() - tbase;
     }
@@ -540,6 +546,12 @@ __device__ void role_P(const Args3& a, double* smem) {
     for (int e = tid; e < T36; e += THREADS) Lcol[e] = qnan;
     if (tid < NB) dinvs[tid] = qnan;
     for (int e = tid; e < T36; e += THREADS) Xbuf[e] = 0.0;
+    // inverse tiles: zero once (upper blocks and pad columns never change; lower blocks are overwritten whole every panel),
+    // diagonal blocks NaN-armed per panel by the inverse builder itself before it arrives at the panel's barrier
+    for (int e = tid; e < 2 * T36; e += THREADS) {
+        const int r = (e % T36) / S36, c = (e % T36) % S36;
+        Linv[e] = (e < T36 && c < NB && (r >> 3) == (c >> 3)) ? qnan : 0.0;
+    }
 
     bool linv_failed = false, tinv_failed = false;
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
@@ -548,11 +560,13 @@ __device__ void role_P(const Args3& a, double* smem) {
     long long wacc[5] = {0, 0, 0, 0, 0};
     long long tsacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t0 = clock64(), t1;
+    long long arrive_acc = 0, tA_prev = 0;
     const bool prof = (DBGF(a) & 4) != 0;
     // BAR.SYNC is issued "defer blocking": a clock read right behind it executes before the barrier completes.
     // The volatile shared load below cannot, and the clock read is made control-dependent on its value.
 #define PROF(slot) do { if (prof) { if (*(volatile double*)dinvs != 1.2345e300) t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; } } while (0)
     if (prof && tid == 0) { a.prof[8] = clock64(); for (int q = 16; q < 24; ++q) a.prof[q] = 0; }
+    if (warp == 1) bar_arrive(7, THREADS);                 // panel 0's barrier (covers the initialisation above)
     // partial mode (KE < NP): one more, reduced, step k = KE forms L(KE,KE-1) and the un-damped D(KE,KE) and writes them back
     for (int k = 0; k < NP && k <= KE; ++k) {
         const bool tail = (k == KE);
@@ -563,19 +577,16 @@ __device__ void role_P(const Args3& a, double* smem) {
         double* Lc = Lcol + (k & 1) * T36;
         double* dv = dinvs + (k & 1) * NB;
         PROF(0);
-        __syncthreads();                                   // staged tiles + previous inverse are in shared memory
+        if (prof && k >= 1) arrive_acc += clock64() - tA_prev;
+        // top-of-panel barrier: staged tiles + previous inverse are in shared memory.  The inverse builder only ARRIVES (at the
+        // end of its previous panel, the moment the inverse tile is complete in shared memory): it publishes the tile's last
+        // block row and raises diag_done while the other seven warps are already in this panel's products.
+        if (warp != 1) bar_sync(7, THREADS);
         PROF(1);
         const long long tA = t0;
+        tA_prev = tA;
         if (cw >= 0) {
             // ---- L(k,k-1) = A(k,k-1) L(k-1,k-1)^-T, then D = A(k,k) - L(k,k-1) L(k,k-1)^T (+ u on the diagonal) ----
-            if (cw == 3 && !tail) {   // warp "T": NaN-arm the diagonal blocks of this panel's inverse tile
-                double* Ls = Linv + (k & 1) * T36;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int e = q * 32 + lane, bb = e >> 6, r = (e >> 3) & 7, c = e & 7;
-                    Ls[(8 * bb + r) * S36 + 8 * bb + c] = qnan;
-                }
-            }
             if (k >= 1) trsm_strip(X, Lp, Lx, cw, 0xfu, lane);
             bar_sync(2, 128);
             bar_arrive(1, 224);                            // I/O warps may store L(k,k-1)
@@ -622,23 +633,33 @@ __device__ void role_P(const Args3& a, double* smem) {
             if (!tail) {   // zero the inverse tile while the products of this panel run, then build it behind the Cholesky
                 long long w0 = prof ? clock64() : 0;
                 double* Ls = Linv + (k & 1) * T36;
-                for (int e = lane; e < T36; e += 32) {
-                    const int r = e / S36, c = e - r * S36;
-                    if ((r >> 3) != (c >> 3) || c >= NB) Ls[e] = 0.0;          // the diagonal blocks are NaN-armed by warp "T"
-                }
-                __syncwarp();
                 warp_linv_blocked(Lc, dv, Ls, a.LI + (size_t)k * T32, Sc, lane, linv_failed, prof ? wacc : nullptr,
                                   prof ? tsacc : nullptr, tA);
                 if (prof) w1acc += clock64() - w0;
             }
             if (!tail && NB * k + lane < n) a.dinv[NB * k + lane] = dv[lane];
             if (linv_failed && lane == 0) *a.info = 1;
+            if (k + 1 < NP && k + 1 <= KE) {
+                double* Ln = Linv + ((k + 1) & 1) * T36;                // next panel's tile: its last reader was this panel's product
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int e = q * 32 + lane, bb = e >> 6, r = (e >> 3) & 7, c = e & 7;
+                    Ln[(8 * bb + r) * S36 + 8 * bb + c] = qnan;
+                }
+                // the next panel may start: its inverse operand is in shared memory.  After a failure nothing paces this
+                // warp any more (every wait returns at once), so it then WAITS at the barrier like the others.
+                if (linv_failed) bar_sync(7, THREADS); else bar_arrive(7, THREADS);
+            }
+            if (!tail) {   // last block row of the inverse -> global, then the flag U and R wait for (covers dinv too)
+                publish_inv_rows(Linv + (k & 1) * T36, a.LI + (size_t)k * T32, 3, lane);
+                __syncwarp();
+                if (lane == 0 && !(DBGF(a) & 8)) red_release(diag_done + k, 1);
+            }
         } else {
             // ---- I/O warps ----
             long long q0 = 0, q1;
 #define IOPROF(slot) do { if (prof && lane == 0) { q1 = clock64(); ioacc[slot] += q1 - q0; q0 = q1; } } while (0)
             if (prof && lane == 0) q0 = clock64();
-            if (k >= 1 && it == 0 && !(DBGF(a) & 8)) red_release(diag_done + (k - 1), 1);   // covers warp 1's stores (bar.sync above)
             IOPROF(0);
             {   // NaN-arm the other column buffer for panel k+1 (its last reader finished before the barrier)
                 double* Ln = Lcol + ((k + 1) & 1) * T36;
@@ -673,7 +694,6 @@ __device__ void role_P(const Args3& a, double* smem) {
         }
     }
     __syncthreads();
-    if (tid == 0 && KE >= NP) red_release(diag_done + (NP - 1), 1);      // partial mode: the reduced step released KE-1
     if (prof && tid == 0) {
         a.prof[9] = clock64();
         for (int q = 0; q < 5; ++q) a.prof[q] = tacc[q];
@@ -681,8 +701,8 @@ __device__ void role_P(const Args3& a, double* smem) {
     if (prof && iw >= 0 && lane == 0) for (int q = 0; q < 6; ++q) a.prof[12 + 6 * iw + q] = ioacc[q];
     if (prof && warp == 1 && lane == 0) { a.prof[30] = w1acc; for (int q = 0; q < 5; ++q) a.prof[3 + 0 * q + 0] += 0; }
     if (prof && warp == 1 && lane == 0) for (int q = 0; q < 5; ++q) a.prof[31 + q] = wacc[q];
-    if (prof && lane == 0 && (warp == 0 || warp == 5 || warp == 1))
-        for (int q = 0; q < 4; ++q) a.prof[36 + 4 * (warp == 0 ? 0 : warp == 5 ? 1 : 2) + q] = tsacc[q];
+    if (prof && lane == 0 && warp == 1) for (int q = 0; q < 4; ++q) a.prof[44 + q] = tsacc[q];
+    if (prof && lane == 0) a.prof[36 + warp] = arrive_acc;      // arrival at the top-of-panel barrier, since the previous one
     if (prof && tid == 0) for (int q = 4; q < 7; ++q) a.prof[44 + q] = tsacc[q];
 #undef PROF
 #undef IOPROF

@@ -69,6 +69,8 @@ if variant == 4 and os.environ.get("PROFP", "0") == "1":
     print("  top instance, P role, cycles per eliminated panel (m = %d):" % m, {nm: int(v) // m for nm, v in zip(names, prof[:6])},
           "| P total", int(prof[9] - prof[8]), "=", int(prof[9] - prof[8]) // m, "per panel",
           "\n   io warps [release diag, arm+wait Lx, store Lx, release rows, spin upd, stage]:", [[int(v) // m for v in prof[12 + 6 * w:18 + 6 * w]] for w in range(3)],
+          "\n   warp 1 (inverse builder) total", int(prof[30]) // m, "[wait cols<b, S products, wait T_b, M products, publish]", [int(v) // m for v in prof[31:36]],
+          "\n   since panel top, per block b: warp 0 ts", [int(v) // m for v in prof[36:40]], "warp 5", [int(v) // m for v in prof[40:44]], "warp 1 (row b published)", [int(v) // m for v in prof[44:48]],
           "\n   potrf parts [load, chain+T, dmma update]", [int(v) // m for v in prof[48:51]],
           "\n   U (rank 3) per panel [wait upd(p-1), operand loads, wait diag(p), Linv load + products + stores, signal, idle]:", [int(v) // m for v in prof[52:58]])
     l.sb_band3_debug(0)
