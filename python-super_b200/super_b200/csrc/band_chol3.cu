@@ -41,7 +41,8 @@ struct Args3 {
     double* AB; int ldab, n, bw;
     double* g; const double* u; double* dinv; int* info;
     double* LB;      // L tiles below the diagonal, tile (I, d = I-J in 1..WB) at ((I*WB + d-1) * 1024), row-major 32x32
-    double* LI;      // L(k,k)^-1, tile k at k*1024, row-major
+    double* LI;      // L(k,k)^-1, tile k at k*1024, row-major; NaN-armed before the launch: the update CTAs take it BY VALUE
+    double* HM;      // hot-tile mailbox, NaN-armed: tiles (p+2,p+1) | (p+2,p+2) after panel p's update at (2p | 2p+1)*1024, row-major
     int* flags;      // diag_done[NP] | rows_done[NP] | upd_done[NP] | hot_done[NP]
     int NP, WB;
     int ke;            // panels to eliminate: NP = full solve; < NP = partial factorisation (two-sided solve), the trailing
@@ -146,6 +147,45 @@ __device__ __forceinline__ void load_ab_tiles2(const Args3& a, int I0, int J0, d
         }
     }
 }
+// The pivot CTA's two tiles of the next panel from the hot-tile mailbox (NaN-armed, written by the owners of the tiles'
+// last update): same thread mapping and in-band predicate as above, every load in flight at once, re-polled until no
+// in-band value is NaN.
+template <int NT>
+__device__ __forceinline__ void load_hot_tiles2(const Args3& a, const double* __restrict__ H0, const double* __restrict__ H1,
+                                                int I0, int J0, double* __restrict__ T0, int s0, int I1, int J1,
+                                                double* __restrict__ T1, int s1, int t) {
+    constexpr int RSTEP = NT / 32, PER = (NB + RSTEP - 1) / RSTEP;
+    const int c = t & 31, r0 = t >> 5;
+    const int d0 = NB * (I0 - J0) + r0 - c, d1 = NB * (I1 - J1) + r0 - c;
+    const int i0 = NB * I0 + r0, i1 = NB * I1 + r0;
+    double v0[PER], v1[PER];
+    int polls = 0;
+    bool again;
+    do {
+        again = false;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int dr = q * RSTEP;
+            const bool ok0 = (r0 + dr < NB) && (i0 + dr < a.n) && (d0 + dr >= 0) && (d0 + dr <= a.bw);
+            const bool ok1 = (r0 + dr < NB) && (i1 + dr < a.n) && (d1 + dr >= 0) && (d1 + dr <= a.bw);
+            v0[q] = ok0 ? __ldcg(H0 + (r0 + dr) * NB + c) : 0.0;
+            v1[q] = ok1 ? __ldcg(H1 + (r0 + dr) * NB + c) : 0.0;
+            again = again || (v0[q] != v0[q]) || (v1[q] != v1[q]);
+        }
+        if (again && (++polls & 63) == 0) {
+            if (*(volatile int*)a.info != 0) again = false;
+            else if (polls > (1 << 16)) { *a.info = 1; again = false; }
+        }
+    } while (again);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int r = r0 + q * RSTEP;
+        if (r < NB) {
+            T0[r * s0 + c] = v0[q];
+            T1[r * s1 + c] = v1[q];
+        }
+    }
+}
 // contiguous row-major 32x32 global tile -> shared with stride
 __device__ __forceinline__ void load_g_tile(const double* __restrict__ G, double* __restrict__ T, int stride, int t,
                                             int nt) {
@@ -156,6 +196,35 @@ __device__ __forceinline__ void load_g_tile(const double* __restrict__ G, double
             const int e = base + q * nt + t;
             v[q] = (e < T32) ? __ldcg(G + e) : 0.0;
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = base + q * nt + t;
+            if (e < T32) T[(e >> 5) * stride + (e & 31)] = v[q];
+        }
+    }
+}
+// The same from a NaN-armed tile another CTA is writing: a value is its own ready flag (8-byte stores are single
+// transactions), so no flag, no fence and no second round trip.  Gives up when a failure has been flagged (the data may then
+// be NaN for good) or after ~2^16 polls, which flags the failure itself.
+__device__ __forceinline__ void load_g_tile_polled(const double* __restrict__ G, double* __restrict__ T, int stride, int t,
+                                                   int nt, int* info) {
+    for (int base = 0; base < T32; base += 4 * nt) {
+        double v[4];
+        int polls = 0;
+        bool again;
+        do {
+            again = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = base + q * nt + t;
+                v[q] = (e < T32) ? __ldcg(G + e) : 0.0;
+                again = again || (v[q] != v[q]);
+            }
+            if (again && (++polls & 63) == 0) {
+                if (*(volatile int*)info != 0) again = false;
+                else if (polls > (1 << 16)) { *info = 1; again = false; }
+            }
+        } while (again);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int e = base + q * nt + t;
@@ -252,6 +321,7 @@ __device__ __forceinline__ bool warp_potrf_blocked(double* __restrict__ D, doubl
 #pragma unroll
         for (int j = 0; j < 8; ++j) p[j] = D[lane * S33 + c0 + j];
         double x[8];                                                                 // column jc of T_b = L_bb^-1
+        double myinv = 0.0;
         long long q0 = 0, q1;
         if (ts) { if (p[7] + d[7][7] != 1.2345e300) q0 = clock64(); ts[4] += q0 - tbase; tbase = q0; }
 #pragma unroll
@@ -276,9 +346,14 @@ __device__ __forceinline__ bool warp_potrf_blocked(double* __restrict__ D, doubl
             p[c] *= inv;                                                             // l_rc of my own row
 #pragma unroll
             for (int j = c + 1; j < 8; ++j) p[j] = fma(-p[c], d[j][c], p[j]);
-            Lcol[(c0 + c) * S36 + lane] = p[c];
-            if (lane == c) dinvs[c0 + c] = inv;
+            if (lane == c) myinv = inv;
         }
+        // The block's 8 columns and pivots leave the registers only now: every reader (inverse builder, helpers, the L(k+1,k)
+        // pre-phase) waits for whole blocks, and a shared-memory store inside the loop above can stall the in-order chain
+        // behind the other warps' shared-memory traffic.  dinvs[c0+7] and T_b(7,7) are the ready flags: columns first.
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Lcol[(c0 + c) * S36 + lane] = p[c];
+        if (lane < 8) dinvs[c0 + lane] = myinv;
         if (lane < 8) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) Ls[(c0 + i) * S36 + c0 + lane] = bad ? 0.0 : x[i];   // (7,7) last: the block's ready flag
@@ -375,10 +450,11 @@ __device__ __forceinline__ void publish_inv_rows(const double* Ls, double* __res
 // Ls: shared inverse tile (stride S36; diagonal blocks NaN-armed, rest zero), Lg: global tile, Sc: 3 x 96 scratch.
 // Block rows 0..2 are published to Lg as they complete; the LAST one is left to the caller (publish_inv_rows(.., 3, ..)
 // behind the next top-of-panel barrier): its 8 loads + 8 stores sat on the pivot chain's panel-to-panel path.
+template <typename OnLast>
 __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const volatile double* dinvs, double* Ls,
                                                   double* __restrict__ Lg, double* __restrict__ Sc, int lane,
-                                                  bool& failed, long long* wacc = nullptr, long long* ts = nullptr,
-                                                  long long tbase = 0) {
+                                                  bool& failed, volatile int* rowflag, int tag, OnLast on_last,
+                                                  long long* wacc = nullptr, long long* ts = nullptr, long long tbase = 0) {
     const int fr = lane >> 2, fc = lane & 3;
     constexpr int SS = 12;
     long long w0 = wacc ? clock64() : 0, w1;
@@ -428,6 +504,7 @@ __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const vola
             WPROF(1);
         }
         wait_value(Ls + (c0 + 7) * S36 + c0 + 7);      // T_b is complete (warp "T")
+        if (b == 3) on_last();                         // the Cholesky of this panel is complete: what the pivot CTA itself needs exists
         WPROF(2);
         if (b >= 1) {
             // M_bj = -T_b S_bj, the three products interleaved
@@ -456,7 +533,10 @@ __device__ __forceinline__ void warp_linv_blocked(const double* Lcol, const vola
             __syncwarp();
             WPROF(3);
         }
-        // block row b of the inverse is final: publish it (the last one: see above)
+        // block row b of the inverse is final in shared memory (flag for the pivot CTA's own products): publish it (the last
+        // one: see above)
+        __threadfence_block();
+        if (lane == 0) rowflag[b] = tag;
         if (b < 3) publish_inv_rows(Ls, Lg, b, lane);
         WPROF(4);
         if (ts) ts[b] += clock64() - tbase;
@@ -523,7 +603,6 @@ __device__ void role_P(const Args3& a, double* smem) {
     int* diag_done = a.flags;
     int* rows_done = a.flags + NP;
     int* upd_done = a.flags + 2 * NP;
-    int* hot_done = a.flags + 3 * NP;      // the two tiles P stages next, signalled by their owners as soon as they are done
     const int NU = a.ncta - 2;
     const int KE = a.ke;
     const int hot_expected = (WB >= 2) ? 2 : 0;
@@ -539,8 +618,10 @@ __device__ void role_P(const Args3& a, double* smem) {
     double* Sc = dinvs + 2 * NB;           // 3 x 96 scratch of the inverse builder
 
     const int cw = (warp == 0) ? 0 : (warp == 2) ? 1 : (warp == 3) ? 2 : (warp == 5) ? 3 : -1;   // compute rank
-    const int iw = (warp == 4) ? 0 : (warp == 6) ? 1 : (warp == 7) ? 2 : -1;                     // I/O rank
-    const int it = iw * 32 + lane;                                                               // I/O thread id (0..95)
+    const int cr = (warp == 6) ? 0 : (cw >= 1) ? cw : -1;      // row block of the L(k,k-1) products (not warp 0: it is on the chain; not warp 4: same scheduler)
+    const int iw = (warp == 4) ? 0 : (warp == 7) ? 1 : -1;                                       // I/O rank
+    const int it = iw * 32 + lane;                                                               // I/O thread id (0..63)
+    double a3[2] = {0.0, 0.0}, pre0[2] = {0.0, 0.0}, dold[2] = {0.0, 0.0};   // carried from a panel's pre-phase to its final step
 
     load_ab_tile(a, 0, 0, Dbuf, S33, tid, THREADS);
     for (int e = tid; e < T36; e += THREADS) Lcol[e] = qnan;
@@ -561,13 +642,78 @@ __device__ void role_P(const Args3& a, double* smem) {
     long long tsacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t0 = clock64(), t1;
     long long arrive_acc = 0, tA_prev = 0;
+    __shared__ int linv_row_ready[4];      // panel index + 1 once block row b of that panel's inverse is complete in shared memory
+    if (tid < 4) linv_row_ready[tid] = 0;
+    __shared__ long long pe_smem[2];       // profiling: clock at the end of the last Cholesky
     const bool prof = (DBGF(a) & 4) != 0;
     // BAR.SYNC is issued "defer blocking": a clock read right behind it executes before the barrier completes.
     // The volatile shared load below cannot, and the clock read is made control-dependent on its value.
 #define PROF(slot) do { if (prof) { if (*(volatile double*)dinvs != 1.2345e300) t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; } } while (0)
     if (prof && tid == 0) { a.prof[8] = clock64(); for (int q = 16; q < 24; ++q) a.prof[q] = 0; }
-    if (warp == 1) bar_arrive(7, THREADS);                 // panel 0's barrier (covers the initialisation above)
-    // partial mode (KE < NP): one more, reduced, step k = KE forms L(KE,KE-1) and the un-damped D(KE,KE) and writes them back
+    // partial mode (KE < NP): one more, reduced, step k = KE forms L(KE,KE-1) and the un-damped D(KE,KE) and writes them back.
+    // The pivot chain and the inverse builder run their OWN loops over the panels (everything between the warps goes through
+    // named barriers and values in shared memory): the chain's code is a few KB that stay in the instruction cache, instead of
+    // one body of ~50 KB that every warp jumps through.
+    if (warp == 0) {
+        for (int k = 0; k < NP && k <= KE; ++k) {
+            const bool tail = (k == KE);
+            double* D = Dbuf + (k & 1) * T33;
+            PROF(0);
+            bar_sync(7, THREADS);                          // this panel's operands are in shared memory (see the barrier below)
+            PROF(1);
+            if (prof && lane == 0) pe_smem[1] = clock64();
+            const long long tA = t0;
+            bar_sync(9, 160);                              // block column 0 of D is final
+            PROF(2);
+            PROF(3);
+            if (tail) {
+                bar_sync(10, 128);
+                for (int e = lane; e < T32; e += 128) {    // this warp's quarter of the Schur complement, back to the band storage
+                    const int r = e >> 5, c = e & 31, i = NB * k + r, j = NB * k + c;
+                    if (c <= r && in_band(a, i, j)) __stcg(ab_at(a, i, j), D[r * S33 + c]);
+                }
+            } else {
+                if (warp_potrf_blocked(D, Lcol + (k & 1) * T36, dinvs + (k & 1) * NB, Linv + (k & 1) * T36, lane,
+                                       prof ? tsacc : nullptr, tA))
+                    *a.info = 1;
+                if (prof && lane == 0) pe_smem[0] = clock64();
+                PROF(4);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- L(k,k)^-1 behind the Cholesky, into shared memory (its diagonal blocks feed the next panel's products) and global
+        // memory (U, R).  The moment the Cholesky is complete it arms the next panel's tile and ARRIVES at that panel's
+        // barrier; the last block row's products, its publication and the flag follow off the panel-to-panel path. ----
+        bar_arrive(7, THREADS);                            // panel 0's barrier (covers the initialisation above)
+        for (int k = 0; k < NP && k < KE; ++k) {
+            double* Lc = Lcol + (k & 1) * T36;
+            double* dv = dinvs + (k & 1) * NB;
+            double* Ls = Linv + (k & 1) * T36;
+            const long long w0 = prof ? clock64() : 0;
+            auto on_last = [&]() {
+                if (NB * k + lane < n) a.dinv[NB * k + lane] = dv[lane];
+                if (k + 1 < NP && k + 1 <= KE) {
+                    double* Ln = Linv + ((k + 1) & 1) * T36;            // next panel's tile: its last reader was this panel's final step
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int e = q * 32 + lane, bb = e >> 6, r = (e >> 3) & 7, c = e & 7;
+                        Ln[(8 * bb + r) * S36 + 8 * bb + c] = qnan;
+                    }
+                    if (prof) arrive_acc += clock64() - *(volatile long long*)pe_smem;
+                    // After a failure nothing paces this warp any more (every wait returns at once): it then WAITS at the barrier
+                    if (linv_failed) bar_sync(7, THREADS); else bar_arrive(7, THREADS);
+                }
+            };
+            warp_linv_blocked(Lc, dv, Ls, a.LI + (size_t)k * T32, Sc, lane, linv_failed, linv_row_ready, k + 1, on_last,
+                              prof ? wacc : nullptr, prof ? tsacc : nullptr, w0);
+            if (prof) w1acc += clock64() - w0;
+            if (linv_failed && lane == 0) *a.info = 1;
+            // last block row of the inverse -> global, then the flag R waits for (covers dinv too; U takes the tile by value)
+            publish_inv_rows(Ls, a.LI + (size_t)k * T32, 3, lane);
+            __syncwarp();
+            if (lane == 0 && !(DBGF(a) & 8)) red_release(diag_done + k, 1);
+        }
+    } else {
     for (int k = 0; k < NP && k <= KE; ++k) {
         const bool tail = (k == KE);
         double* D = Dbuf + (k & 1) * T33;
@@ -576,132 +722,177 @@ __device__ void role_P(const Args3& a, double* smem) {
         const double* Lp = Linv + ((k + 1) & 1) * T36;     // L(k-1,k-1)^-1
         double* Lc = Lcol + (k & 1) * T36;
         double* dv = dinvs + (k & 1) * NB;
-        PROF(0);
-        if (prof && k >= 1) arrive_acc += clock64() - tA_prev;
         // top-of-panel barrier: staged tiles + previous inverse are in shared memory.  The inverse builder only ARRIVES (at the
         // end of its previous panel, the moment the inverse tile is complete in shared memory): it publishes the tile's last
         // block row and raises diag_done while the other seven warps are already in this panel's products.
-        if (warp != 1) bar_sync(7, THREADS);
-        PROF(1);
-        const long long tA = t0;
-        tA_prev = tA;
-        if (cw >= 0) {
-            // ---- L(k,k-1) = A(k,k-1) L(k-1,k-1)^-T, then D = A(k,k) - L(k,k-1) L(k,k-1)^T (+ u on the diagonal) ----
-            if (k >= 1) trsm_strip(X, Lp, Lx, cw, 0xfu, lane);
-            bar_sync(2, 128);
-            bar_arrive(1, 224);                            // I/O warps may store L(k,k-1)
-            PROF(2);
-            // D -= L(k,k-1) L(k,k-1)^T (+ damping): only block column 0 is needed before the pivot chain can start, so the
-            // four warps do (cw,0) first; the other six lower blocks follow on the helper warps behind the chain
-            syrk_blocks(Lx, D, k >= 1, cw, 0, -1, -1, k, n, u, lane, !tail);
-            bar_sync(2, 128);
-            PROF(3);
-            if (tail) {
-                // Schur complement of the first non-eliminated panel: the other six blocks, then back to the band storage
-                if (cw >= 1) syrk_blocks(Lx, D, k >= 1, cw, 1, (cw == 1) ? 2 : 3, (cw == 3) ? 3 : 2, k, n, u, lane, false);
-                bar_sync(2, 128);
-                for (int e = cw * 32 + lane; e < T32; e += 128) {
-                    const int r = e >> 5, c = e & 31, i = NB * k + r, j = NB * k + c;
-                    if (c <= r && in_band(a, i, j)) __stcg(ab_at(a, i, j), D[r * S33 + c]);
-                }
-            } else if (warp == 0) {
-                if (warp_potrf_blocked(D, Lc, dv, Linv + (k & 1) * T36, lane, prof ? tsacc : nullptr, tA)) *a.info = 1;
-                PROF(4);
+        // Compute warps (cr >= 0) have done everything of this panel's L(k,k-1) and D(k) that does not need the last 8 columns
+        // of L(k-1,k-1) during the previous panel (PRE-PHASE below), and only arrive here.
+        if (k == 0 || cr < 0) bar_sync(7, THREADS); else bar_arrive(7, THREADS);
+        if (cr >= 0) {
+            // ---- FINAL STEP of L(k,k-1) = A(k,k-1) L(k-1,k-1)^-T and of block column 0 of D = A(k,k) - L L^T (+ u) ----
+            // Forward-substitution form by 8-column blocks: Y_t = (X_t - sum_{s<t} Y_s L_ts^T) T_t^T with T_t = L_tt^-1 straight
+            // from the Cholesky warp.  W_3 = X_3 - sum_{s<3} Y_s L_3s^T (operand registers a3) and the products over columns
+            // 0..23 (pre0) were formed while the chain was still on block 3: two DMMAs, one exchange, two DMMAs remain.
+            const int fr = lane >> 2, fc = lane & 3, rb = cr;
+            double v0, v1;
+            if (k >= 1) {
+                const volatile double* T = Lp;
+                int spins = 0;
+                double dq = T[31 * S36 + 31];
+                while (dq != dq && ++spins < (1 << 20)) dq = T[31 * S36 + 31];
+                asm volatile("" ::: "memory");
+                double y0 = 0.0, y1 = 0.0;
+                dmma884(y0, y1, a3[0], T[(24 + fr) * S36 + 24 + fc]);
+                dmma884(y0, y1, a3[1], T[(24 + fr) * S36 + 28 + fc]);
+                *reinterpret_cast<double2*>(Lx + (8 * rb + fr) * S36 + 24 + 2 * fc) = make_double2(y0, y1);
+                bar_sync(2, 128);                          // Y_3 of all four row blocks
+                bar_arrive(1, 192);                        // I/O warps may store L(k,k-1)
+                double c0 = 0.0, c1 = 0.0;
+                dmma884(c0, c1, Lx[(8 * rb + fr) * S36 + 24 + fc], Lx[fr * S36 + 24 + fc]);
+                dmma884(c0, c1, Lx[(8 * rb + fr) * S36 + 28 + fc], Lx[fr * S36 + 28 + fc]);
+                v0 = dold[0] - (pre0[0] + c0);
+                v1 = dold[1] - (pre0[1] + c1);
             } else {
-                // helper h = cw owns blocks (h,1) [syrk only] and (2,2) | (3,2) | (3,3): rest of the syrk, then the
-                // non-urgent part of the Cholesky's trailing updates (block columns right of the next one).
-                // One barrier id per phase: a helper may reach its next arrive before warp 0 has consumed the previous one.
-                const int oi = (cw == 1) ? 2 : 3, oj = (cw == 3) ? 3 : 2;
-                syrk_blocks(Lx, D, k >= 1, cw, 1, oi, oj, k, n, u, lane);
+                bar_arrive(1, 192);
+                v0 = D[(8 * rb + fr) * S33 + 2 * fc];
+                v1 = D[(8 * rb + fr) * S33 + 2 * fc + 1];
+            }
+            {
+                const int i = 8 * rb + fr, j = 2 * fc, gi = NB * k + i;
+                if (!tail && i == j) v0 = (gi < n) ? v0 + u : 1.0;
+                if (!tail && i == j + 1) v1 = (gi < n) ? v1 + u : 1.0;
+                D[i * S33 + j] = v0;
+                D[i * S33 + j + 1] = v1;
+            }
+            bar_arrive(9, 160);                            // block column 0 of D is final: the pivot chain may start
+        }
+        if (cw >= 1) {
+            // helper h = cw owns blocks (h,1) [syrk only] and (2,2) | (3,2) | (3,3): rest of the syrk, then the
+            // non-urgent part of the Cholesky's trailing updates (block columns right of the next one).
+            // One barrier id per phase: a helper may reach its next arrive before warp 0 has consumed the previous one.
+            const int oi = (cw == 1) ? 2 : 3, oj = (cw == 3) ? 3 : 2;
+            syrk_blocks(Lx, D, k >= 1, cw, 1, oi, oj, k, n, u, lane, !tail);
+            if (tail) {
+                bar_sync(10, 128);
+            } else {
                 bar_arrive(4, 128);                                   // phase 0: warp 0 may update block column 1
                 helper_trailing(D, Lc, dv, 0, oi, oj, lane, true);
                 bar_arrive(5, 128);                                   // phase 1: ... block column 2
                 helper_trailing(D, Lc, dv, 1, oi, oj, lane, cw == 3);
                 bar_arrive(6, 128);                                   // phase 2: ... block (3,3)
-                // idle from here on: help the I/O warps stage the next panel's tiles (six warps, 12 loads per thread)
-                if (k + 1 < NP) {
-                    if (k >= 1 && NU > 0) {
-                        if (lane == 0) spin_until(hot_done + (k - 1), hot_expected);
-                        __syncwarp();
-                    }
-                    load_ab_tiles2<192>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
-                                        Xbuf + ((k + 1) & 1) * T36, S36, (2 + cw) * 32 + lane);
-                }
-            }
-        } else if (warp == 1) {
-            // ---- L(k,k)^-1 behind the Cholesky; publish to shared (next panel's product) and global (U, R) ----
-            if (!tail) {   // zero the inverse tile while the products of this panel run, then build it behind the Cholesky
-                long long w0 = prof ? clock64() : 0;
-                double* Ls = Linv + (k & 1) * T36;
-                warp_linv_blocked(Lc, dv, Ls, a.LI + (size_t)k * T32, Sc, lane, linv_failed, prof ? wacc : nullptr,
-                                  prof ? tsacc : nullptr, tA);
-                if (prof) w1acc += clock64() - w0;
-            }
-            if (!tail && NB * k + lane < n) a.dinv[NB * k + lane] = dv[lane];
-            if (linv_failed && lane == 0) *a.info = 1;
-            if (k + 1 < NP && k + 1 <= KE) {
-                double* Ln = Linv + ((k + 1) & 1) * T36;                // next panel's tile: its last reader was this panel's product
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int e = q * 32 + lane, bb = e >> 6, r = (e >> 3) & 7, c = e & 7;
-                    Ln[(8 * bb + r) * S36 + 8 * bb + c] = qnan;
-                }
-                // the next panel may start: its inverse operand is in shared memory.  After a failure nothing paces this
-                // warp any more (every wait returns at once), so it then WAITS at the barrier like the others.
-                if (linv_failed) bar_sync(7, THREADS); else bar_arrive(7, THREADS);
-            }
-            if (!tail) {   // last block row of the inverse -> global, then the flag U and R wait for (covers dinv too)
-                publish_inv_rows(Linv + (k & 1) * T36, a.LI + (size_t)k * T32, 3, lane);
-                __syncwarp();
-                if (lane == 0 && !(DBGF(a) & 8)) red_release(diag_done + k, 1);
-            }
-        } else {
-            // ---- I/O warps ----
-            long long q0 = 0, q1;
-#define IOPROF(slot) do { if (prof && lane == 0) { q1 = clock64(); ioacc[slot] += q1 - q0; q0 = q1; } } while (0)
-            if (prof && lane == 0) q0 = clock64();
-            IOPROF(0);
-            {   // NaN-arm the other column buffer for panel k+1 (its last reader finished before the barrier)
-                double* Ln = Lcol + ((k + 1) & 1) * T36;
-                if (!(DBGF(a) & 32) && !tail) for (int e = it; e < T36; e += 96) Ln[e] = qnan;
-                if (it < NB) dinvs[((k + 1) & 1) * NB + it] = qnan;
-            }
-            bar_sync(1, 224);                                              // L(k,k-1) is complete
-            if (prof && lane == 0 && *(volatile double*)Lx == 1.2345e300) q0 = 0;
-            IOPROF(1);
-            if (k >= 1 && WB >= 1) {
-                store_g_tile(lb_tile(a, k, 1), Lx, S36, it, 96);
-                if (iw == 2) {
-                    bar_sync(3, 96);
-                    IOPROF(2);
-                    if (lane == 0 && !(DBGF(a) & 8)) red_release(rows_done + (k - 1), 1);
-                    IOPROF(3);
-                } else {
-                    bar_arrive(3, 96);
-                    IOPROF(2);
-                }
-            }
-            if (k + 1 < NP && !tail) {
-                if (k >= 1 && NU > 0) {
-                    if (lane == 0) spin_until(hot_done + (k - 1), hot_expected);
-                    __syncwarp();
-                    IOPROF(4);
-                }
-                load_ab_tiles2<192>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k,
-                                    Xbuf + ((k + 1) & 1) * T36, S36, it);      // threads 0..95; the helper warps are 96..191
-                IOPROF(5);
             }
         }
+        if (tail && cw >= 1) {
+            // Schur complement of the first non-eliminated panel goes back to the band storage
+            for (int e = cw * 32 + lane; e < T32; e += 128) {
+                const int r = e >> 5, c = e & 31, i = NB * k + r, j = NB * k + c;
+                if (c <= r && in_band(a, i, j)) __stcg(ab_at(a, i, j), D[r * S33 + c]);
+            }
+        }
+        const bool has_next = (k + 1 < NP && !tail);
+        if (iw >= 0) {
+            // ---- I/O warps (4 and 7): NaN-arm the other column buffer for panel k+1 (its last reader finished before the
+            // barrier), store L(k,k-1), raise rows_done ----
+            double* Ln = Lcol + ((k + 1) & 1) * T36;
+            if (!(DBGF(a) & 32) && !tail) for (int e = it; e < T36; e += 64) Ln[e] = qnan;
+            if (it < NB) dinvs[((k + 1) & 1) * NB + it] = qnan;
+            bar_sync(1, 192);                                              // L(k,k-1) is complete
+            if (k >= 1 && WB >= 1) {
+                store_g_tile(lb_tile(a, k, 1), Lx, S36, it, 64);
+                if (iw == 1) {
+                    bar_sync(3, 64);
+                    if (lane == 0 && !(DBGF(a) & 8)) red_release(rows_done + (k - 1), 1);
+                } else {
+                    bar_arrive(3, 64);
+                }
+            }
+        }
+        if (has_next) {
+            // ---- staging of panel k+1's two tiles by three warps (22 loads per thread, all in flight at once) ----
+            if (cr <= 0) {      // warps 4, 7 and 6: the helpers are still behind the Cholesky's block columns
+                const int lt = (cr == 0 ? 2 : iw) * 32 + lane;
+                if (prof && warp == 7) tsacc[0] += clock64() - *(volatile long long*)(pe_smem + 1);
+                if (k >= 1 && NU > 0 && hot_expected == 2)      // both tiles' last update was panel k-1's: by value from their owners
+                    load_hot_tiles2<96>(a, a.HM + (size_t)(2 * (k - 1) + 1) * T32, a.HM + (size_t)(2 * (k - 1)) * T32, k + 1, k + 1,
+                                        Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k, Xbuf + ((k + 1) & 1) * T36, S36, lt);
+                else
+                    load_ab_tiles2<96>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k, Xbuf + ((k + 1) & 1) * T36, S36, lt);
+            }
+            if (prof && warp == 7) tsacc[1] += clock64() - *(volatile long long*)(pe_smem + 1);
+            if (cr < 0) {
+                bar_arrive(8, 192);
+            } else {
+                // ---- PRE-PHASE of panel k+1 (see the final step above), behind the Cholesky of panel k ----
+                bar_sync(8, 192);
+                if (prof && warp == 3) tsacc[1] += clock64() - *(volatile long long*)(pe_smem + 1);
+                const int fr = lane >> 2, fc = lane & 3, rb = cr;
+                const double* Xn = Xbuf + ((k + 1) & 1) * T36;
+                const double* Dn = Dbuf + ((k + 1) & 1) * T33;
+                double* Lxn = Lxbuf + ((k + 1) & 1) * T36;
+                const volatile double* T = Linv + (k & 1) * T36;      // T_t in the diagonal blocks (this panel's Cholesky writes them)
+                const volatile double* Lk = Lc;                        // L(k,k) by columns
+                double acc[4][2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double2 x2 = *reinterpret_cast<const double2*>(Xn + (8 * rb + fr) * S36 + 8 * t + 2 * fc);
+                    acc[t][0] = x2.x; acc[t][1] = x2.y;
+                }
+                dold[0] = Dn[(8 * rb + fr) * S33 + 2 * fc];
+                dold[1] = Dn[(8 * rb + fr) * S33 + 2 * fc + 1];
+                // block 0 needs no conversion: W_0 = X_0, operands straight from the staged tile
+                double w0 = Xn[(8 * rb + fr) * S36 + fc], w1 = Xn[(8 * rb + fr) * S36 + 4 + fc];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    int spins = 0;
+                    double dq = T[(8 * t + 7) * S36 + 8 * t + 7];
+                    while (dq != dq && ++spins < (1 << 20)) dq = T[(8 * t + 7) * S36 + 8 * t + 7];
+                    asm volatile("" ::: "memory");
+                    if (prof && warp == 3 && t == 1) tsacc[0] += clock64() - *(volatile long long*)(pe_smem + 1);
+                    if (prof && warp == 3 && t == 2) tsacc[3] += clock64() - *(volatile long long*)(pe_smem + 1);
+                    if (t > 0) {   // W_t: accumulator layout -> operand layout through this warp's own rows of the L(k+1,k) tile
+                        *reinterpret_cast<double2*>(Lxn + (8 * rb + fr) * S36 + 8 * t + 2 * fc) = make_double2(acc[t][0], acc[t][1]);
+                        __syncwarp();
+                        w0 = Lxn[(8 * rb + fr) * S36 + 8 * t + fc]; w1 = Lxn[(8 * rb + fr) * S36 + 8 * t + 4 + fc];
+                        __syncwarp();
+                    }
+                    double y0 = 0.0, y1 = 0.0;
+                    dmma884(y0, y1, w0, T[(8 * t + fr) * S36 + 8 * t + fc]);
+                    dmma884(y0, y1, w1, T[(8 * t + fr) * S36 + 8 * t + 4 + fc]);
+                    *reinterpret_cast<double2*>(Lxn + (8 * rb + fr) * S36 + 8 * t + 2 * fc) = make_double2(y0, y1);
+                    __syncwarp();
+                    const double ya = -Lxn[(8 * rb + fr) * S36 + 8 * t + fc], yb = -Lxn[(8 * rb + fr) * S36 + 8 * t + 4 + fc];
+                    // the NEXT block's accumulator first: it is the one the chain of the substitution waits for
+#pragma unroll
+                    for (int uu = t + 1; uu < 4; ++uu) {
+                        dmma884(acc[uu][0], acc[uu][1], ya, Lk[(8 * t + fc) * S36 + 8 * uu + fr]);
+                        dmma884(acc[uu][0], acc[uu][1], yb, Lk[(8 * t + 4 + fc) * S36 + 8 * uu + fr]);
+                    }
+                }
+                if (prof && warp == 3) tsacc[2] += clock64() - *(volatile long long*)(pe_smem + 1);
+                // W_3 as operand registers
+                *reinterpret_cast<double2*>(Lxn + (8 * rb + fr) * S36 + 24 + 2 * fc) = make_double2(acc[3][0], acc[3][1]);
+                __syncwarp();
+                a3[0] = Lxn[(8 * rb + fr) * S36 + 24 + fc];
+                a3[1] = Lxn[(8 * rb + fr) * S36 + 28 + fc];
+                bar_sync(2, 128);                          // Y_0..2 of all four row blocks
+                pre0[0] = pre0[1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 6; ++ks)
+                    dmma884(pre0[0], pre0[1], Lxn[(8 * rb + fr) * S36 + 4 * ks + fc], Lxn[fr * S36 + 4 * ks + fc]);
+            }
+        }
+    }
     }
     __syncthreads();
     if (prof && tid == 0) {
         a.prof[9] = clock64();
         for (int q = 0; q < 5; ++q) a.prof[q] = tacc[q];
     }
-    if (prof && iw >= 0 && lane == 0) for (int q = 0; q < 6; ++q) a.prof[12 + 6 * iw + q] = ioacc[q];
     if (prof && warp == 1 && lane == 0) { a.prof[30] = w1acc; for (int q = 0; q < 5; ++q) a.prof[3 + 0 * q + 0] += 0; }
     if (prof && warp == 1 && lane == 0) for (int q = 0; q < 5; ++q) a.prof[31 + q] = wacc[q];
     if (prof && lane == 0 && warp == 1) for (int q = 0; q < 4; ++q) a.prof[44 + q] = tsacc[q];
+    if (prof && lane == 0 && warp == 3) for (int q = 0; q < 4; ++q) a.prof[58 + q] = tsacc[q];
+    if (prof && lane == 0 && warp == 7) for (int q = 0; q < 2; ++q) a.prof[6 + q] = tsacc[q];
     if (prof && lane == 0) a.prof[36 + warp] = arrive_acc;      // arrival at the top-of-panel barrier, since the previous one
     if (prof && tid == 0) for (int q = 4; q < 7; ++q) a.prof[44 + q] = tsacc[q];
 #undef PROF
@@ -904,9 +1095,8 @@ __device__ void role_U(const Args3& a, double* smem) {
             }
             if (first) {
                 UPROF(1);
-                cta_wait(diag_done + p, 1);
+                load_g_tile_polled(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS, a.info);   // no flag: the tile is NaN until written
                 UPROF(2);
-                load_g_tile(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS);
                 first = false;
             }
             __syncthreads();
@@ -929,21 +1119,20 @@ __device__ void role_U(const Args3& a, double* smem) {
                     if (!skip0) dmma884(acc[0][0], acc[0][1], af, Lb[(8 * bj0 + fr) * S36 + 4 * ks + fc]);
                     if (!skip1) dmma884(acc[1][0], acc[1][1], af, Lb[(8 * (bj0 + 1) + fr) * S36 + 4 * ks + fc]);
                 }
+                // (p+2,p+1), (p+2,p+2) are what P stages for panel p+2: they also go, by value, into its mailbox
+                double* hm = (t == 1 || t == 2) ? a.HM + (size_t)(2 * p + (t - 1)) * T32 : nullptr;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (q == 0 ? skip0 : skip1) continue;
                     const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * (bj0 + q) + 2 * fc;
-                    if (in_band(a, i, j)) __stcg(ab_at(a, i, j), oldv[q][0] - acc[q][0]);
-                    if (in_band(a, i, j + 1)) __stcg(ab_at(a, i, j + 1), oldv[q][1] - acc[q][1]);
+                    const double w0 = oldv[q][0] - acc[q][0], w1 = oldv[q][1] - acc[q][1];
+                    if (in_band(a, i, j)) { __stcg(ab_at(a, i, j), w0); if (hm) __stcg(hm + (8 * bi + fr) * NB + 8 * (bj0 + q) + 2 * fc, w0); }
+                    if (in_band(a, i, j + 1)) { __stcg(ab_at(a, i, j + 1), w1); if (hm) __stcg(hm + (8 * bi + fr) * NB + 8 * (bj0 + q) + 2 * fc + 1, w1); }
                 }
             }
             if (diag) {
                 store_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
                 ++rows_written;
-            }
-            if (t == 1 || t == 2) {     // (p+2,p+1), (p+2,p+2): what P stages for panel p+2 -- do not make it wait for the stragglers
-                __syncthreads();
-                if (tid == 0) red_release(a.flags + 3 * NP + p, 1);
             }
         }
         __syncthreads();
@@ -988,10 +1177,6 @@ __device__ void role_U2(const Args3& a, double* smem) {
     for (int p = 0; p < NP && p < a.ke; ++p) {
         const int last = min(NP - 1, p + WB);
         const int nrows = last - p;
-        if (DBGF(a) & 1) {          // timing experiments: no trailing work, but P still waits for the hot flag
-            if (ui == 0 && tid == 0) red_release(a.flags + 3 * NP + p, 2);
-            continue;
-        }
         // ---- my work of this panel: rows (phase 1) and tiles (phase 2, packed I<<16|J, sorted by J then I) ----
         __syncthreads();
         if (tid == 0) { n1 = 0; n2 = 0; }
@@ -1022,8 +1207,7 @@ __device__ void role_U2(const Args3& a, double* smem) {
         const int m1 = n1, m2 = n2;
         // ---- phase 1 ----
         if (m1 > 0) {
-            cta_wait(diag_done + p, 1);
-            load_g_tile(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS);
+            load_g_tile_polled(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS, a.info);
             for (int x = 0; x < m1; ++x) {
                 const int I = lst1[x];
                 __syncthreads();
@@ -1064,16 +1248,15 @@ __device__ void role_U2(const Args3& a, double* smem) {
                     if (!skip0) dmma884(acc[0][0], acc[0][1], af, Lb[(8 * bj0 + fr) * S36 + 4 * ks + fc]);
                     if (!skip1) dmma884(acc[1][0], acc[1][1], af, Lb[(8 * (bj0 + 1) + fr) * S36 + 4 * ks + fc]);
                 }
+                // what P stages for panel p+2 also goes, by value, into its mailbox
+                double* hm = (I == p + 2 && (J == p + 1 || J == p + 2)) ? a.HM + (size_t)(2 * p + (J - p - 1)) * T32 : nullptr;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (q == 0 ? skip0 : skip1) continue;
                     const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * (bj0 + q) + 2 * fc;
-                    if (in_band(a, i, j)) __stcg(ab_at(a, i, j), oldv[q][0] - acc[q][0]);
-                    if (in_band(a, i, j + 1)) __stcg(ab_at(a, i, j + 1), oldv[q][1] - acc[q][1]);
-                }
-                if (I == p + 2 && (J == p + 1 || J == p + 2)) {   // what P stages for panel p+2
-                    __syncthreads();
-                    if (tid == 0) red_release(a.flags + 3 * NP + p, 1);
+                    const double w0 = oldv[q][0] - acc[q][0], w1 = oldv[q][1] - acc[q][1];
+                    if (in_band(a, i, j)) { __stcg(ab_at(a, i, j), w0); if (hm) __stcg(hm + (8 * bi + fr) * NB + 8 * (bj0 + q) + 2 * fc, w0); }
+                    if (in_band(a, i, j + 1)) { __stcg(ab_at(a, i, j + 1), w1); if (hm) __stcg(hm + (8 * bi + fr) * NB + 8 * (bj0 + q) + 2 * fc + 1, w1); }
                 }
             }
         }
@@ -1098,6 +1281,7 @@ __device__ __forceinline__ void run_roles(const Args3& a, double* smem) {
 struct TwoSided {
     int n, bw, ldab, m32, Lm, nB;       // rows: total, half bandwidth, band row length, 32*m, middle, bottom instance (= n - 32 m)
     int* flags; int nflags;             // the three instances' counters (one block), zeroed by band_reverse_kernel
+    double* arm[3]; int narm[3];        // the three instances' inverse tiles + hot-tile mailboxes, NaN-armed by band_reverse_kernel
 };
 
 // Source of the system when it arrives as one of two int64 fixed-point stores (AB | g, sb_lm_frame): the store the
@@ -1128,6 +1312,13 @@ __global__ void band_reverse_kernel(double* __restrict__ AB, double* __restrict_
         }
     }
     if (e < t.nflags) t.flags[e] = 0;
+    {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        const int stride = gridDim.x * blockDim.x;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            for (int x = e; x < t.narm[q]; x += stride) t.arm[q][x] = qnan;
+    }
     if (e < t.nB) {
         const int gi = t.n - 1 - e;                                   // original row
         g2[e] = (gi >= t.m32 + t.Lm) ? (src ? (double)src[n_ab + gi] * fx.inv_gscale : g[gi]) : 0.0;
@@ -1636,7 +1827,7 @@ size_t smem_bytes3(int n) {
 
 long long ws_bytes3(int n, int bw) {
     const long long NP = (n + NB - 1) / NB, WB = (bw + NB - 1) / NB;
-    return (NP * (WB > 0 ? WB : 1) + NP) * (long long)T32 * (long long)sizeof(double) + ((4 * NP * (long long)sizeof(int) + 255) & ~255LL) + 256 + 1024;
+    return (NP * (WB > 0 ? WB : 1) + 3 * NP) * (long long)T32 * (long long)sizeof(double) + ((4 * NP * (long long)sizeof(int) + 255) & ~255LL) + 256 + 1024;
 }
 
 #ifdef SB_DEBUG_EXPORTS
@@ -1725,12 +1916,16 @@ int sb_band_solve3(double* AB, int ldab, int n, int bw, double* g, const double*
     const long long tiles = (long long)a.NP * (a.WB > 0 ? a.WB : 1);
     a.LB = (double*)workspace;
     a.LI = a.LB + tiles * T32;
-    a.flags = (int*)(a.LI + (long long)a.NP * T32);
+    a.HM = a.LI + (long long)a.NP * T32;
+    a.flags = (int*)(a.HM + 2LL * a.NP * T32);
     a.two_phase = (a.WB * (a.WB + 1) / 2 - 1 > n_ctas - 2 || (g_debug3 & 64)) ? 1 : 0;
     a.ke = a.NP; a.rank0 = 0; a.ncta = n_ctas;
     a.prof = (long long*)((char*)workspace + ws_bytes3(n, bw) - 1024);
     a.debug = g_debug3;
     if (cudaMemsetAsync(a.flags, 0, 4 * (size_t)a.NP * sizeof(int), (cudaStream_t)stream) != cudaSuccess)
+        return SB_ERR_CUDA;
+    // the inverse tiles and the hot-tile mailbox are taken by value: all-ones bytes are a NaN
+    if (cudaMemsetAsync(a.LI, 0xff, 3 * (size_t)a.NP * T32 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
         return SB_ERR_CUDA;
     void* kargs[] = {(void*)&a};
     if (cudaLaunchCooperativeKernel((const void*)band_chol3_kernel, dim3(n_ctas), dim3(THREADS), kargs, smem,
@@ -1751,7 +1946,8 @@ static void fill_args3(Args3& a, double* AB, int ldab, int n, int bw, double* g,
     const long long tiles = (long long)a.NP * (a.WB > 0 ? a.WB : 1);
     a.LB = (double*)ws;
     a.LI = a.LB + tiles * T32;
-    a.flags = (int*)(a.LI + (long long)a.NP * T32);
+    a.HM = a.LI + (long long)a.NP * T32;
+    a.flags = (int*)(a.HM + 2LL * a.NP * T32);
     a.two_phase = (a.WB * (a.WB + 1) / 2 - 1 > ncta - 2 || (g_debug3 & 64)) ? 1 : 0;
     a.ke = ke < 0 ? a.NP : ke; a.rank0 = rank0; a.ncta = ncta;
     a.prof = (long long*)((char*)ws + ws_bytes3(n, bw) - 1024);
@@ -1827,6 +2023,9 @@ static int solve4_impl(double* AB, int ldab, int n, int bw, double* g, const dou
     fill_args3(aM, ABm, ldab, t.Lm, bwm, gm, u, dinvM, info, wsM, -1, 0, cM);
     aA.flags = flags4; aB.flags = aA.flags + 4 * aA.NP; aM.flags = aB.flags + 4 * aB.NP;
     t.flags = flags4; t.nflags = 4 * (aA.NP + aB.NP + aM.NP);
+    t.arm[0] = aA.LI; t.narm[0] = 3 * aA.NP * T32;
+    t.arm[1] = aB.LI; t.narm[1] = 3 * aB.NP * T32;
+    t.arm[2] = aM.LI; t.narm[2] = 3 * aM.NP * T32;
     size_t smem = smem_bytes3(nA);
     if (smem_bytes3(t.Lm) > smem) smem = smem_bytes3(t.Lm);
     if (!opt_in_smem(band_chol3_dual_kernel, smem, dc->smem_dual)) return SB_ERR_CUDA;
