@@ -1,25 +1,25 @@
-// Banded Cholesky solve v3 of (A + u I) x = g -- the LM step solve, replacing
+// Banded Cholesky solve of (A + u I) x = g -- the LM step solve, replacing
 // torch.linalg.cholesky + cholesky_solve   /root/reference/super/LM.py:38-51,97-100.
 //
-// What v2 (band_chol2.cu) measured on B200 (profiles/r1b_band_probe.md): the pivot-chain CTA alone needs
-// 11 k cycles per 32-column panel (one-warp triangular solve 2.8 k, scalar syrk 1.7 k, one-warp Cholesky
-// 6.2 k), the update CTAs need 19 k (two redundant one-warp triangular solves per tile) and the
-// back substitution 192 us.  v3 keeps the role split (the factorisation is a chain of n pivots, everything
-// else has slack) and removes those costs:
+// The factorisation is a chain of n pivots; everything else has slack.  Roles on a cooperative grid (launched cooperatively
+// only for the co-residency guarantee: there is no grid-wide barrier, every spin is bounded):
 //
-//   * every 32x32 triangular solve is a tensor-core product with the explicit inverse of the diagonal
-//     factor: while warp 0 of the pivot CTA factors block k column by column, warp 1 builds L(k,k)^-1 row by
-//     row behind it (the columns travel through a NaN-initialised shared buffer: a value is its own
-//     "ready" flag).  P publishes only L(k,k)^-1; nobody needs L(k,k).
-//   * P: L(k,k-1) = A(k,k-1) Linv^T and D -= L L^T are FP64 DMMA products on four warps; three I/O warps
-//     publish flags, store L(k,k-1) and stage the next panel's tiles behind the Cholesky.
-//   * U: one tile per CTA and panel, three DMMA products (two "triangular solves", one update).
-//   * R: forward substitution y_p = Linv s_p behind P, then -- on the same CTA, no grid barrier -- a
-//     push-style back substitution x_k = Linv^T s_k, s_j -= L(k,j)^T x_k with register-prefetched tiles.
+//   * P, one CTA: the pivot chain.  Warp 0 factors the 32x32 diagonal block (replicated 8x8 blocks in registers, no
+//     shuffle or shared round trip on the chain) in its own loop over the panels; warp 1 builds L(k,k)^-1 behind it (for
+//     U and R) and only ARRIVES at the next panel's barrier; four compute warps form L(k+1,k) = A(k+1,k) L(k,k)^-T by
+//     forward substitution in 8-column blocks BEHIND the Cholesky (pre-phase: blocks 0..2, W_3, the products over
+//     columns 0..23 of D -= L L^T), so that after the last pivot two DMMAs, one exchange and two DMMAs remain (final
+//     step); two I/O warps store L(k+1,k), raise rows_done and -- with warp 6 -- stage the next panel's two tiles.
+//   * U: one trailing tile per CTA and panel, three DMMA products (two "triangular solves" recomputed from the unfactored
+//     tiles with the explicit inverse, one update).  U2 (wide bands): fixed tile owners, L(I,p) formed once per row.
+//   * R: forward substitution y_p = Linv s_p behind P, then -- on the same CTA -- a push-style back substitution.
 //
-// Synchronisation: release/acquire counters in global memory (diag_done | rows_done | upd_done per panel),
-// zeroed by a memset node in front of the launch.  The grid is launched cooperatively only for the
-// co-residency guarantee (spinning CTAs); there is no grid-wide barrier.  Every spin is bounded and traps.
+// Hand-over: inside the pivot CTA by value through NaN-armed shared buffers and named barriers; P -> U (inverse tiles, LI)
+// and U -> P (the two tiles whose last update was the previous panel's: HM) BY VALUE through NaN-armed global tiles -- a
+// value is its own ready flag, so neither a fence nor a flag nor a second L2 round trip sits on that path; R and the
+// per-panel barrier among the update CTAs use release/acquire counters (diag_done | rows_done | upd_done per panel).
+// The two-sided solve (sb_band_solve4*) runs two such pipelines from both ends of the band at once, then the middle block.
+// Measurements behind every choice: DESIGN.md section 5, profiles/r1_microbench.md, profiles/r2s_chol_probe.md.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -636,7 +636,6 @@ __device__ void role_P(const Args3& a, double* smem) {
 
     bool linv_failed = false, tinv_failed = false;
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
-    long long ioacc[6] = {0, 0, 0, 0, 0, 0};
     long long w1acc = 0;
     long long wacc[5] = {0, 0, 0, 0, 0};
     long long tsacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -888,7 +887,7 @@ __device__ void role_P(const Args3& a, double* smem) {
         a.prof[9] = clock64();
         for (int q = 0; q < 5; ++q) a.prof[q] = tacc[q];
     }
-    if (prof && warp == 1 && lane == 0) { a.prof[30] = w1acc; for (int q = 0; q < 5; ++q) a.prof[3 + 0 * q + 0] += 0; }
+    if (prof && warp == 1 && lane == 0) a.prof[30] = w1acc;
     if (prof && warp == 1 && lane == 0) for (int q = 0; q < 5; ++q) a.prof[31 + q] = wacc[q];
     if (prof && lane == 0 && warp == 1) for (int q = 0; q < 4; ++q) a.prof[44 + q] = tsacc[q];
     if (prof && lane == 0 && warp == 3) for (int q = 0; q < 4; ++q) a.prof[58 + q] = tsacc[q];

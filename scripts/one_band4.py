@@ -65,12 +65,13 @@ if variant == 4 and os.environ.get("PROFP", "0") == "1":
         band.AB.copy_(ABd); band.g.copy_(rd); ops.band_solve(band, None, 148, variant=4)
     torch.cuda.synchronize()
     prof = band.ws4[off: off + 512].view(torch.int64).cpu().numpy()
-    names = ["potrf-end->top", "wait BAR_A", "trsm", "syrk", "potrf", "io wait upd"]
-    print("  top instance, P role, cycles per eliminated panel (m = %d):" % m, {nm: int(v) // m for nm, v in zip(names, prof[:6])},
+    names = ["Cholesky end -> barrier 7 reached", "wait at barrier 7", "wait for block column 0 of D (final step)", "-", "Cholesky"]
+    print("  top instance, pivot CTA, cycles per eliminated panel (m = %d):" % m, {nm: int(v) // m for nm, v in zip(names, prof[:5])},
           "| R forward substitution done at", int(prof[10] - prof[8]), "after P's start | P total", int(prof[9] - prof[8]), "=", int(prof[9] - prof[8]) // m, "per panel",
-          "\n   io warps [release diag, arm+wait Lx, store Lx, release rows, spin upd, stage]:", [[int(v) // m for v in prof[12 + 6 * w:18 + 6 * w]] for w in range(3)],
-          "\n   warp 1 (inverse builder) total", int(prof[30]) // m, "[wait cols<b, S products, wait T_b, M products, publish]", [int(v) // m for v in prof[31:36]],
-          "\n   since panel top, per block b: warp 0 ts", [int(v) // m for v in prof[36:40]], "warp 5", [int(v) // m for v in prof[40:44]], "warp 1 (row b published)", [int(v) // m for v in prof[44:48]],
-          "\n   potrf parts [load, chain+T, dmma update]", [int(v) // m for v in prof[48:51]], "warp 3 since panel top [T_1 seen, at bar 8, t-loop end, T_2 seen]", [int(v) // m for v in prof[58:62]], "warp 7 [stage begin, staged]", [int(v) // m for v in prof[6:8]],
-          "\n   U (rank 3) per panel [wait upd(p-1), operand loads, wait diag(p), Linv load + products + stores, signal, idle]:", [int(v) // m for v in prof[52:58]])
+          "\n   Cholesky parts [replica loads (block 0 since the panel's barrier), chain + T_b, urgent trailing DMMA + barrier]", [int(v) // m for v in prof[48:51]],
+          "\n   inverse builder: total", int(prof[30]) // m, "[wait cols<b, S products, wait T_b, M products, publish]", [int(v) // m for v in prof[31:36]],
+          "| barrier-7 arrival after the Cholesky end", int(prof[37]) // m, "| row b published since its own loop top", [int(v) // m for v in prof[44:48]],
+          "\n   compute warp 3 since the panel's barrier [T_1 seen, arrived at the staging barrier, substitution loop done, T_2 seen]", [int(v) // m for v in prof[58:62]],
+          "| I/O warp 7 [staging begins, staged]", [int(v) // m for v in prof[6:8]],
+          "\n   U (rank 3; it owns a tile in few panels, so its waits are mostly idle time) [wait upd(p-1), operand loads, inverse tile by value, products + stores, signal, idle]:", [int(v) // m for v in prof[52:58]])
     l.sb_band3_debug(0)
