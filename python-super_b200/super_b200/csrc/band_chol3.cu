@@ -61,6 +61,15 @@ struct Args3 {
 #define DBGF(a) 0
 #endif
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// hot-path study (debug build): sums of %globaltimer at five events of the panels 1..ke-2, prof[64..68] (+ counts at [69..73])
+#define GSTAMP(a, slot, p_) do { if ((DBGF(a) & 4) && (p_) >= 1 && (p_) <= (a).ke - 2) { \
+    atomicAdd((unsigned long long*)(a).prof + 64 + (slot), gtime_ns()); atomicAdd((unsigned long long*)(a).prof + 69 + (slot), 1ull); } } while (0)
+
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -676,6 +685,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                                        prof ? tsacc : nullptr, tA))
                     *a.info = 1;
                 if (prof && lane == 0) pe_smem[0] = clock64();
+                if (lane == 0) GSTAMP(a, 0, k);
                 PROF(4);
             }
         }
@@ -726,6 +736,10 @@ __device__ void role_P(const Args3& a, double* smem) {
         // block row and raises diag_done while the other seven warps are already in this panel's products.
         // Compute warps (cr >= 0) have done everything of this panel's L(k,k-1) and D(k) that does not need the last 8 columns
         // of L(k-1,k-1) during the previous panel (PRE-PHASE below), and only arrive here.
+        if (prof && k >= 2) {      // arrivals AFTER the last Cholesky's end: how many, how late in all
+            const long long dt = clock64() - *(volatile long long*)pe_smem;
+            if (dt < 4000) { arrive_acc += dt; tA_prev += 1; }
+        }
         if (k == 0 || cr < 0) bar_sync(7, THREADS); else bar_arrive(7, THREADS);
         if (cr >= 0) {
             // ---- FINAL STEP of L(k,k-1) = A(k,k-1) L(k-1,k-1)^-T and of block column 0 of D = A(k,k) - L L^T (+ u) ----
@@ -818,6 +832,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                     load_ab_tiles2<96>(a, k + 1, k + 1, Dbuf + ((k + 1) & 1) * T33, S33, k + 1, k, Xbuf + ((k + 1) & 1) * T36, S36, lt);
             }
             if (prof && warp == 7) tsacc[1] += clock64() - *(volatile long long*)(pe_smem + 1);
+            if (warp == 7 && lane == 0) GSTAMP(a, 4, k - 1);
             if (cr < 0) {
                 bar_arrive(8, 192);
             } else {
@@ -892,7 +907,7 @@ __device__ void role_P(const Args3& a, double* smem) {
     if (prof && lane == 0 && warp == 1) for (int q = 0; q < 4; ++q) a.prof[44 + q] = tsacc[q];
     if (prof && lane == 0 && warp == 3) for (int q = 0; q < 4; ++q) a.prof[58 + q] = tsacc[q];
     if (prof && lane == 0 && warp == 7) for (int q = 0; q < 2; ++q) a.prof[6 + q] = tsacc[q];
-    if (prof && lane == 0) a.prof[36 + warp] = arrive_acc;      // arrival at the top-of-panel barrier, since the previous one
+    if (prof && lane == 0) a.prof[36 + warp] = (warp == 1) ? arrive_acc : (tA_prev << 32) | arrive_acc;
     if (prof && tid == 0) for (int q = 4; q < 7; ++q) a.prof[44 + q] = tsacc[q];
 #undef PROF
 #undef IOPROF
@@ -1094,8 +1109,10 @@ __device__ void role_U(const Args3& a, double* smem) {
             }
             if (first) {
                 UPROF(1);
+                if (t == 1 && tid == 0) GSTAMP(a, 1, p);
                 load_g_tile_polled(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS, a.info);   // no flag: the tile is NaN until written
                 UPROF(2);
+                if (t == 1 && tid == 0) GSTAMP(a, 2, p);
                 first = false;
             }
             __syncthreads();
@@ -1129,6 +1146,7 @@ __device__ void role_U(const Args3& a, double* smem) {
                     if (in_band(a, i, j + 1)) { __stcg(ab_at(a, i, j + 1), w1); if (hm) __stcg(hm + (8 * bi + fr) * NB + 8 * (bj0 + q) + 2 * fc + 1, w1); }
                 }
             }
+            if (t == 1 && tid == 0) GSTAMP(a, 3, p);
             if (diag) {
                 store_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
                 ++rows_written;

@@ -549,7 +549,10 @@ class Tracker:
                 sfv = NS(points=s.points[:nb_], norms=sfv.norms, knn_indices=s.knn_idx[:nb_], knn_w=s.knn_w[:nb_], ED=self.ED)
                 order = None
             jev = sev = tev = None
-            if self.event_sink is not None:
+            if self.event_sink is not None and self.event_sink.get("frames_left", 1 << 30) > 0:
+                # per-pass / per-solve events only on the first frames of the timed region: an event record costs ~1 us of
+                # stream time, forty of them per frame would sit inside the number they are meant to explain
+                self.event_sink["frames_left"] = self.event_sink.get("frames_left", 1 << 30) - 1
                 jev, sev = self._new_events(2 * self.events_per_frame[0]), self._new_events(2 * self.events_per_frame[1])
                 self.event_sink["jtj"] += list(zip(jev[0::2], jev[1::2]))
                 self.event_sink["solve"] += list(zip(sev[0::2], sev[1::2]))

@@ -64,13 +64,15 @@ if variant == 4 and os.environ.get("PROFP", "0") == "1":
     for _ in range(3):
         band.AB.copy_(ABd); band.g.copy_(rd); ops.band_solve(band, None, 148, variant=4)
     torch.cuda.synchronize()
-    prof = band.ws4[off: off + 512].view(torch.int64).cpu().numpy()
+    prof = band.ws4[off: off + 1024].view(torch.int64).cpu().numpy()
+    gs = prof[64:69].astype(np.float64) / np.maximum(prof[69:74], 1)
+    print("  hot path (globaltimer, ns after the Cholesky end of panel p; counts", prof[69:74].tolist(), "): U owner of (p+2,p+1) starts polling the inverse %.0f | has it %.0f | tile in the mailbox %.0f | pivot CTA has staged it %.0f" % tuple(gs[1:5] - gs[0]))
     names = ["Cholesky end -> barrier 7 reached", "wait at barrier 7", "wait for block column 0 of D (final step)", "-", "Cholesky"]
     print("  top instance, pivot CTA, cycles per eliminated panel (m = %d):" % m, {nm: int(v) // m for nm, v in zip(names, prof[:5])},
           "| R forward substitution done at", int(prof[10] - prof[8]), "after P's start | P total", int(prof[9] - prof[8]), "=", int(prof[9] - prof[8]) // m, "per panel",
           "\n   Cholesky parts [replica loads (block 0 since the panel's barrier), chain + T_b, urgent trailing DMMA + barrier]", [int(v) // m for v in prof[48:51]],
           "\n   inverse builder: total", int(prof[30]) // m, "[wait cols<b, S products, wait T_b, M products, publish]", [int(v) // m for v in prof[31:36]],
-          "| barrier-7 arrival after the Cholesky end", int(prof[37]) // m, "| row b published since its own loop top", [int(v) // m for v in prof[44:48]],
+          "| inverse builder's barrier-7 arrival after the Cholesky end", int(prof[37]) // m, "| warps 2..7: (panels in which they reached barrier 7 AFTER the Cholesky's end, mean delay)", [(int(v) >> 32, (int(v) & 0xffffffff) // max(1, int(v) >> 32)) for v in prof[38:44]], "| row b published since its own loop top", [int(v) // m for v in prof[44:48]],
           "\n   compute warp 3 since the panel's barrier [T_1 seen, arrived at the staging barrier, substitution loop done, T_2 seen]", [int(v) // m for v in prof[58:62]],
           "| I/O warp 7 [staging begins, staged]", [int(v) // m for v in prof[6:8]],
           "\n   U (rank 3; it owns a tile in few panels, so its waits are mostly idle time) [wait upd(p-1), operand loads, inverse tile by value, products + stores, signal, idle]:", [int(v) // m for v in prof[52:58]])
