@@ -1082,6 +1082,47 @@ __device__ void role_U(const Args3& a, double* smem) {
         int t = ((ui - p) % NU + NU) % NU;
         bool first = true;
         int rows_written = 0;
+        // The off-diagonal tile P stages next, (p+2,p+1), sits on the solve's critical loop (inverse -> this update -> P's
+        // staging -> P's products), and a whole tile is 288 DMMAs on a role that is DMMA-issue-bound.  When update CTAs are idle
+        // in this panel, four of them take one 8-row block of it each (the tile's own CTA + three idle ones): 20 + 80 + 32
+        // DMMAs instead of 288.
+        const bool split = (ntiles >= 3) && (ntiles + 3 <= NU) && !(DBGF(a) & 1);
+        const int part = !split ? -1 : (t == 1) ? 0 : (t >= ntiles && t < ntiles + 3) ? t - ntiles + 1 : -1;
+        if (part >= 0) {
+            const int I = p + 2, J = p + 1, rb = part;
+            if (p >= 1) cta_wait(upd_done + (p - 1), NU);
+            else __syncthreads();
+            load_ab_tiles2<THREADS>(a, I, p, As, S36, J, p, Bs, S36, tid);
+            double oldv[2] = {0.0, 0.0};
+            if (warp < 4) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = NB * I + 8 * rb + fr, j = NB * J + 8 * warp + 2 * fc + e;
+                    oldv[e] = in_band(a, i, j) ? __ldcg(ab_at(a, i, j)) : 0.0;
+                }
+            }
+            if (part == 0 && tid == 0) GSTAMP(a, 1, p);
+            load_g_tile_polled(a.LI + (size_t)p * T32, LinvS, S36, tid, THREADS, a.info);
+            if (part == 0 && tid == 0) GSTAMP(a, 2, p);
+            first = false;
+            __syncthreads();
+            if (warp < 4) trsm_strip(As, LinvS, LIs, rb, 1u << warp, lane);     // L(I,p), my 8 rows: one block column per warp
+            else trsm_strip(Bs, LinvS, LJs, warp - 4, 0xfu, lane);              // L(J,p), all of it
+            __syncthreads();
+            if (warp < 4) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    dmma884(c0, c1, LIs[(8 * rb + fr) * S36 + 4 * ks + fc], LJs[(8 * warp + fr) * S36 + 4 * ks + fc]);
+                double* hm = a.HM + (size_t)(2 * p) * T32;
+                const int i = NB * I + 8 * rb + fr, j = NB * J + 8 * warp + 2 * fc;
+                const double w0 = oldv[0] - c0, w1 = oldv[1] - c1;
+                if (in_band(a, i, j)) { __stcg(ab_at(a, i, j), w0); __stcg(hm + (8 * rb + fr) * NB + 8 * warp + 2 * fc, w0); }
+                if (in_band(a, i, j + 1)) { __stcg(ab_at(a, i, j + 1), w1); __stcg(hm + (8 * rb + fr) * NB + 8 * warp + 2 * fc + 1, w1); }
+            }
+            if (part == 0 && tid == 0) GSTAMP(a, 3, p);
+            t = ntiles;                                                   // nothing else for this CTA in this panel
+        }
         for (; t < ntiles && !(DBGF(a) & 1); t += NU) {
             if (t == 0) continue;                                         // tile (p+1,p+1) belongs to P
             int ri = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
