@@ -231,7 +231,7 @@ def run_cuda(args, rank, world, local_rank):
     lib.LAUNCHES = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     # (begin, end) CUDA events on the launch stream around every J^T J pass and every linear solve of every timed frame, recorded inside sb_lm_frame (SbLMFrame.jtj_events / solve_events)
-    trk.event_sink = {"jtj": [], "solve": [], "timeline": [], "timeline_frames": min(8, K), "frames_left": min(16, K)}
+    trk.event_sink = {"jtj": [], "solve": [], "timeline": [], "timeline_frames": min(8, K), "frames_left": min(8, K)}
     trk.events_per_frame = (LM_ITERS, LM_ITERS)            # every J^T J pass (the first one of a frame is L2-cold) and every solve
     t_wall = time.perf_counter()
     for k in range(K):

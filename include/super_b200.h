@@ -131,9 +131,18 @@ typedef struct SbLMFrame {
                                  * in issue order -- lm_begin, [eval, gram, scatter] and per iteration [solve, eval | loss,
                                  * gram, scatter] -- for as many as the array covers */
     int n_stage_events;
+    void** graph_cache;         /* host: address of a caller-owned opaque handle (initially NULL) or NULL.  With a handle and no
+                                 * event arrays, the frame's launch sequence is stream-captured (on a private stream), the
+                                 * caller's instantiated graph is updated in place (cudaGraphExecUpdate: same topology every
+                                 * frame, only parameters change) and launched on `stream`: the ~85 dependent launches of a
+                                 * frame then follow each other ~2.5 us closer than stream launches do.  The first call with a
+                                 * fresh handle launches directly.  Free the handle with sb_lm_graph_destroy. */
 } SbLMFrame;
 
 int sb_version(void);
+
+/* Releases what sb_lm_frame keeps behind SbLMFrame.graph_cache (graph exec + capture stream); *cache becomes NULL. */
+int sb_lm_graph_destroy(void** cache);
 
 /* ---- kNN / weights / warp -------------------------------------------------------------------- */
 

@@ -1017,8 +1017,23 @@ __device__ void role_R(const Args3& a, double* smem) {
             if (DBGF(a) & 1) __syncthreads(); else cta_wait(rows_done + p, nrows);    // also orders ys
             for (int q0 = 0; q0 < nrows; q0 += 8) {
                 const int nq = min(8, nrows - q0);
-                for (int q = 0; q < nq; ++q)
-                    load_g_tile(lb_tile(a, p + 1 + q0 + q, q0 + q + 1), Lrows + (size_t)q * T33, S33, tid, THREADS);
+                {   // the batch's tiles with EVERY load in flight before the first shared store (one L2 round trip per batch
+                    // instead of one per tile: this role's lag behind the pivot chain is the kernel's tail)
+                    double v[8][4];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double* G = lb_tile(a, p + 1 + q0 + min(q, nq - 1), q0 + min(q, nq - 1) + 1);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) v[q][x] = (q < nq) ? __ldcg(G + x * THREADS + tid) : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const int e = x * THREADS + tid;
+                            if (q < nq) Lrows[(size_t)q * T33 + (e >> 5) * S33 + (e & 31)] = v[q][x];
+                        }
+                }
                 __syncthreads();
                 const int q = tid >> 5;
                 if (q < nq) {                  // s_i -= L(i, panel p) . y_p

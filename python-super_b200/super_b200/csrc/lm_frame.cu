@@ -102,7 +102,7 @@ static int jtj_pass(const SbLMFrame* f, int adopt, int k, cudaStream_t st, int& 
     return SB_OK;
 }
 
-int sb_lm_frame(const SbLMFrame* f, void* stream) {
+static int lm_frame_launches(const SbLMFrame* f, void* stream) {
     if (!f || !f->points || !f->knn_idx || !f->knn_w || !f->ed_points || !f->ed_knn || !f->vmap || !f->nmap) return SB_ERR_ARG;
     if (!f->state || !f->beta || !f->best || !f->partials_loss || !f->rows || !f->keys || f->row_stride < f->n_cap ||
         (f->row_stride & 31))
@@ -152,6 +152,67 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
         if (rc != SB_OK) return rc;
     }
     return SB_OK;
+}
+
+// what sb_lm_frame keeps for a caller between frames (SbLMFrame.graph_cache)
+struct LMGraphCache {
+    cudaStream_t capture_stream;
+    cudaGraphExec_t exec;
+    int warmed;
+};
+
+int sb_lm_graph_destroy(void** cache) {
+    if (!cache) return SB_ERR_ARG;
+    LMGraphCache* gc = (LMGraphCache*)*cache;
+    if (gc) {
+        if (gc->exec) cudaGraphExecDestroy(gc->exec);
+        if (gc->capture_stream) cudaStreamDestroy(gc->capture_stream);
+        delete gc;
+        *cache = nullptr;
+    }
+    return SB_OK;
+}
+
+int sb_lm_frame(const SbLMFrame* f, void* stream) {
+    if (!f) return SB_ERR_ARG;
+    const bool events = f->jtj_events || f->solve_events || f->stage_events;
+    if (!f->graph_cache || events) return lm_frame_launches(f, stream);
+    LMGraphCache* gc = (LMGraphCache*)*f->graph_cache;
+    if (!gc) {
+        gc = new LMGraphCache{nullptr, nullptr, 0};
+        if (cudaStreamCreateWithFlags(&gc->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { delete gc; return SB_ERR_CUDA; }
+        *f->graph_cache = gc;
+    }
+    if (!gc->warmed) {            // first frame: direct launches (per-device launch configuration gets cached outside a capture)
+        gc->warmed = 1;
+        return lm_frame_launches(f, stream);
+    }
+    // Capture this frame's sequence (argument checks included: nothing is launched), update the instantiated graph in place
+    // -- the topology is the same every frame, only kernel parameters and grids change -- and launch it on the caller's stream.
+    if (cudaStreamBeginCapture(gc->capture_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) return SB_ERR_CUDA;
+    const int rc = lm_frame_launches(f, (void*)gc->capture_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(gc->capture_stream, &graph);
+    if (rc != SB_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc != SB_OK ? rc : SB_ERR_CUDA;
+    }
+    if (gc->exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(gc->exec, graph, &info) != cudaSuccess) {      // topology changed (other iteration count, ...)
+            cudaGetLastError();
+            cudaGraphExecDestroy(gc->exec);
+            gc->exec = nullptr;
+        }
+    }
+    if (!gc->exec && cudaGraphInstantiate(&gc->exec, graph, 0) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return SB_ERR_CUDA;
+    }
+    cudaGraphDestroy(graph);
+    return cudaGraphLaunch(gc->exec, (cudaStream_t)stream) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
 }  // extern "C"

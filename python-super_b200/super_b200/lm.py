@@ -40,7 +40,7 @@ class SbLMFrame(ctypes.Structure):
                 ("AB", _P), ("g", _P), ("band_overflow", _P), ("dinv", _P), ("info", _P),
                 ("solver_ws", _P), ("solver_ws_bytes", ctypes.c_longlong), ("n_ctas", _I),
                 ("jtj_events", _P), ("n_jtj_events", _I), ("solve_events", _P), ("n_solve_events", _I),
-                ("stage_events", _P), ("n_stage_events", _I)]
+                ("stage_events", _P), ("n_stage_events", _I), ("graph_cache", _P)]
 
 
 class LMWorkspace:
@@ -57,6 +57,14 @@ class LMWorkspace:
         self.state = ops.LMState(device)
         self.partials = None
         self.rows = self.keys = None        # Jacobian rows (29, stride) + node-set keys of the frame loop's evaluation pass
+        self.graph_handle = ctypes.c_void_p(0)   # sb_lm_frame's instantiated CUDA graph of the frame loop (SbLMFrame.graph_cache)
+
+    def __del__(self):
+        try:
+            if self.graph_handle:
+                lib.load().sb_lm_graph_destroy(ctypes.byref(self.graph_handle))
+        except Exception:
+            pass
 
     @property
     def A(self):
@@ -129,6 +137,8 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
             keep.append(arr)
             setattr(f, name + "_events", ctypes.cast(arr, ctypes.c_void_p))
             setattr(f, "n_" + name + "_events", len(evs))
+    if not keep and os.environ.get("SB_LM_GRAPH", "1") != "0":
+        f.graph_cache = ctypes.cast(ctypes.pointer(ws.graph_handle), ctypes.c_void_p)
     call("sb_lm_frame", ctypes.byref(f), stream())
     lib.LAUNCHES += 2 + 8 * f.iterations        # lm_begin, eval, Gram, scatter; per iteration 5 (solve) + eval + Gram + scatter | loss
     band._dirty = False
