@@ -263,6 +263,7 @@ add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* _
                int* __restrict__ add_flag, int* __restrict__ add_idx, double* __restrict__ add_dist,
                const int* __restrict__ ed_seg) {
     __shared__ double tile[ADD_TILE * 3];
+    __shared__ float box[(ADD_TILE / 8) * 6];          // per group of 8 consecutive nodes: lo xyz, hi xyz (outward-rounded floats)
     const int P = fr.H * fr.W;
     const int p = blockIdx.x * ADD_BLOCK + threadIdx.x;
     const bool active = p < P && add_flag[p] != 0;
@@ -278,25 +279,61 @@ add_knn_kernel(SbFrame fr, const double* __restrict__ ed_points, const double* _
         qx = pv.x; qy = pv.y; qz = pv.z;
         if (by_class) qc = fr.seg[p];
     }
+    // (d2, index) lexicographic insertion: the result is the K smallest by (distance, index) whatever the visiting order,
+    // i.e. ties -> lower index, exactly what the index-order scan with a strict comparison gave
+    auto visit = [&](int j, int jg) {
+        const double dx = subr(qx, tile[3 * j]), dy = subr(qy, tile[3 * j + 1]), dz = subr(qz, tile[3 * j + 2]);
+        const double d2 = addr(addr(mulr(dx, dx), mulr(dy, dy)), mulr(dz, dz));
+        if (d2 < bd[SB_KNN - 1] || (d2 == bd[SB_KNN - 1] && jg < bi[SB_KNN - 1])) {
+            bd[SB_KNN - 1] = d2; bi[SB_KNN - 1] = jg;
+#pragma unroll
+            for (int k = SB_KNN - 1; k > 0; --k)
+                if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1])) {
+                    const double td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                    const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+                }
+        }
+    };
     for (int t0 = 0; t0 < J; t0 += ADD_TILE) {
         const int cnt = min(ADD_TILE, J - t0);
+        const int ng = (cnt + 7) >> 3;
         __syncthreads();
         for (int e = threadIdx.x; e < cnt * 3; e += ADD_BLOCK) tile[e] = ed_points[(size_t)t0 * 3 + e];
         __syncthreads();
-        if (active) {
-            for (int j = 0; j < cnt; ++j) {
-                if (by_class && ed_seg[t0 + j] != qc) continue;
-                const double dx = subr(qx, tile[3 * j]), dy = subr(qy, tile[3 * j + 1]), dz = subr(qz, tile[3 * j + 2]);
-                const double d2 = addr(addr(mulr(dx, dx), mulr(dy, dy)), mulr(dz, dz));
-                if (d2 < bd[SB_KNN - 1]) {
-                    bd[SB_KNN - 1] = d2; bi[SB_KNN - 1] = t0 + j;
-#pragma unroll
-                    for (int k = SB_KNN - 1; k > 0; --k)
-                        if (bd[k] < bd[k - 1]) {
-                            const double td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-                            const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
-                        }
+        // Bounding boxes of groups of 8 consecutive nodes (neighbours on the node grid).  A group whose box is farther from
+        // the pixel than its current K-th neighbour cannot contribute: the brute-force scan over all J nodes (the kernel was
+        // FP64-issue-bound on it) becomes ~1/4 of the distance evaluations, with the same result.
+        for (int g = threadIdx.x; g < ng; g += ADD_BLOCK) {
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int j = 8 * g; j < min(cnt, 8 * g + 8); ++j)
+                for (int c = 0; c < 3; ++c) {
+                    lo[c] = fminf(lo[c], __double2float_rd(tile[3 * j + c]));
+                    hi[c] = fmaxf(hi[c], __double2float_ru(tile[3 * j + c]));
                 }
+            for (int c = 0; c < 3; ++c) { box[6 * g + c] = lo[c]; box[6 * g + 3 + c] = hi[c]; }
+        }
+        __syncthreads();
+        if (active) {
+            // lower bound of the squared distance to a group's box, rounded DOWN (float, then a relative margin)
+            auto lower = [&](int g) {
+                const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
+                const float ex = fmaxf(0.f, fmaxf(box[6 * g] - fx, fx - box[6 * g + 3]));
+                const float ey = fmaxf(0.f, fmaxf(box[6 * g + 1] - fy, fy - box[6 * g + 4]));
+                const float ez = fmaxf(0.f, fmaxf(box[6 * g + 2] - fz, fz - box[6 * g + 5]));
+                return (double)((ex * ex + ey * ey + ez * ez) * 0.9999f);
+            };
+            int g0 = 0;                            // the group that most likely holds the nearest node goes first
+            float best = INFINITY;
+            for (int g = 0; g < ng; ++g) {
+                const float lb = (float)lower(g);
+                if (lb < best) { best = lb; g0 = g; }
+            }
+            for (int j = 8 * g0; j < min(cnt, 8 * g0 + 8); ++j)
+                if (!(by_class && ed_seg[t0 + j] != qc)) visit(j, t0 + j);
+            for (int g = 0; g < ng; ++g) {
+                if (g == g0 || lower(g) > bd[SB_KNN - 1]) continue;
+                for (int j = 8 * g; j < min(cnt, 8 * g + 8); ++j)
+                    if (!(by_class && ed_seg[t0 + j] != qc)) visit(j, t0 + j);
             }
         }
     }
