@@ -144,6 +144,15 @@ int sb_version(void);
 /* Releases what sb_lm_frame keeps behind SbLMFrame.graph_cache (graph exec + capture stream); *cache becomes NULL. */
 int sb_lm_graph_destroy(void** cache);
 
+/* The same mechanism for any fixed sequence of calls of this library (the per-frame tail: warp/update, fusion, compaction,
+ * visiting order): between _begin and _end pass *use_stream to the calls instead of `stream`; _end replays what was captured
+ * as one graph on `stream` (updated in place from frame to frame).  The first use of a handle runs directly.  Only calls of
+ * this library (and nothing that synchronises) may be issued in between; abort_scope != 0 drops the capture. */
+int sb_graph_scope_begin(void** cache, void* stream, void** use_stream);
+int sb_graph_scope_end(void** cache, void* stream, int abort_scope);
+/* device-to-device copy of n ints on the stream (a memcpy node inside a scope) */
+int sb_copy_i32(int* dst, const int* src, int n, void* stream);
+
 /* ---- kNN / weights / warp -------------------------------------------------------------------- */
 
 /* find_knn -> pytorch3d knn_points: /root/reference/utils/utils.py:212-220.  K nearest rows of `ref`

@@ -159,6 +159,7 @@ struct LMGraphCache {
     cudaStream_t capture_stream;
     cudaGraphExec_t exec;
     int warmed;
+    int capturing;      // sb_graph_scope_begin .. _end
 };
 
 int sb_lm_graph_destroy(void** cache) {
@@ -173,13 +174,75 @@ int sb_lm_graph_destroy(void** cache) {
     return SB_OK;
 }
 
+// capture ended: update the caller's instantiated graph in place (or instantiate it) and launch it on `stream`
+static int graph_update_and_launch(LMGraphCache* gc, cudaGraph_t graph, cudaStream_t stream) {
+    if (gc->exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(gc->exec, graph, &info) != cudaSuccess) {      // topology changed
+            cudaGetLastError();
+            cudaGraphExecDestroy(gc->exec);
+            gc->exec = nullptr;
+        }
+    }
+    if (!gc->exec && cudaGraphInstantiate(&gc->exec, graph, 0) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return SB_ERR_CUDA;
+    }
+    cudaGraphDestroy(graph);
+    return cudaGraphLaunch(gc->exec, stream) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int sb_graph_scope_begin(void** cache, void* stream, void** use_stream) {
+    if (!cache || !use_stream) return SB_ERR_ARG;
+    LMGraphCache* gc = (LMGraphCache*)*cache;
+    if (!gc) {
+        gc = new LMGraphCache{nullptr, nullptr, 0, 0};
+        if (cudaStreamCreateWithFlags(&gc->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { delete gc; return SB_ERR_CUDA; }
+        *cache = gc;
+    }
+    if (gc->capturing) return SB_ERR_ARG;
+    if (!gc->warmed) {            // first use: the scope's calls go straight to the caller's stream
+        *use_stream = stream;
+        return SB_OK;
+    }
+    if (cudaStreamBeginCapture(gc->capture_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) return SB_ERR_CUDA;
+    gc->capturing = 1;
+    *use_stream = (void*)gc->capture_stream;
+    return SB_OK;
+}
+
+int sb_graph_scope_end(void** cache, void* stream, int abort_scope) {
+    if (!cache || !*cache) return SB_ERR_ARG;
+    LMGraphCache* gc = (LMGraphCache*)*cache;
+    if (!gc->capturing) {         // the direct first use
+        gc->warmed = 1;
+        return SB_OK;
+    }
+    gc->capturing = 0;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(gc->capture_stream, &graph);
+    if (abort_scope || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return abort_scope ? SB_OK : SB_ERR_CUDA;
+    }
+    return graph_update_and_launch(gc, graph, (cudaStream_t)stream);
+}
+
+int sb_copy_i32(int* dst, const int* src, int n, void* stream) {
+    if (!dst || !src || n <= 0) return SB_ERR_ARG;
+    return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess
+               ? SB_OK : SB_ERR_CUDA;
+}
+
 int sb_lm_frame(const SbLMFrame* f, void* stream) {
     if (!f) return SB_ERR_ARG;
     const bool events = f->jtj_events || f->solve_events || f->stage_events;
     if (!f->graph_cache || events) return lm_frame_launches(f, stream);
     LMGraphCache* gc = (LMGraphCache*)*f->graph_cache;
     if (!gc) {
-        gc = new LMGraphCache{nullptr, nullptr, 0};
+        gc = new LMGraphCache{nullptr, nullptr, 0, 0};
         if (cudaStreamCreateWithFlags(&gc->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { delete gc; return SB_ERR_CUDA; }
         *f->graph_cache = gc;
     }
@@ -198,21 +261,7 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
         cudaGetLastError();
         return rc != SB_OK ? rc : SB_ERR_CUDA;
     }
-    if (gc->exec) {
-        cudaGraphExecUpdateResultInfo info;
-        if (cudaGraphExecUpdate(gc->exec, graph, &info) != cudaSuccess) {      // topology changed (other iteration count, ...)
-            cudaGetLastError();
-            cudaGraphExecDestroy(gc->exec);
-            gc->exec = nullptr;
-        }
-    }
-    if (!gc->exec && cudaGraphInstantiate(&gc->exec, graph, 0) != cudaSuccess) {
-        cudaGraphDestroy(graph);
-        cudaGetLastError();
-        return SB_ERR_CUDA;
-    }
-    cudaGraphDestroy(graph);
-    return cudaGraphLaunch(gc->exec, (cudaStream_t)stream) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+    return graph_update_and_launch(gc, graph, (cudaStream_t)stream);
 }
 
 }  // extern "C"

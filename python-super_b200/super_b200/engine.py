@@ -327,6 +327,10 @@ class Tracker:
     # sort are not sized for a loose upper bound) and a band that is exactly as wide as the pattern (the solve
     # is 60 % of the frame and scales with bw^2: 255 us at bw 300 against 312 us with a 25 % safety margin).
     def _publish_count(self):
+        self._order_and_gather()
+        self._handover()
+
+    def _order_and_gather(self):
         self._order = None
         if self.ED is not None and self.ED.node_pos is not None and getattr(self.opt, "use_derived_gradient", True):
             # The host's bound at this point is (rows at frame start + H W); the frame really adds a few thousand rows.
@@ -338,6 +342,8 @@ class Tracker:
             self._order_rows = rows
             self._order = ops.tuple_order(self.cur.knn_idx[:rows], self.cur.n_dev, self.ED.node_pos, self.block_bw)
             self._gather_sorted(rows)
+
+    def _handover(self):
         self._n_pinned.copy_(self.cur.n_dev, non_blocking=True)
         self._bw_pinned[0:1].copy_(self.block_bw, non_blocking=True)
         if self.band is not None:
@@ -600,16 +606,32 @@ class Tracker:
         call("sb_fuse", self.cur.ref(), frame.ref(), ptr(self.ED.points), ptr(self.ED.radii), self.ED.num,
              ctypes.byref(pr), ptr(self.track_id), 0 if self.track_id is None else self.track_id.numel(),
              ptr(self.n_tmp), ptr(self.overflow), ptr(self.fuse_ws), self.fuse_ws.numel(), stream())
-        self.cur.n_dev.copy_(self.n_tmp)
+        call("sb_copy_i32", ptr(self.cur.n_dev), ptr(self.n_tmp), 1, stream())
         self.n_bound = min(self.cap, self.n_bound + self.P)
         self.time = frame.time
 
     def track(self, frame, filename=None):
         """SuPer.fusion (/root/reference/super/super.py:66-83): solve -> update -> fuse -> compact."""
         beta = self.solve(frame)
-        self.apply(beta)
-        self.fuse(frame)
-        self.finish_frame(frame, filename)
+        # The frame's tail -- warp/update, fusion, compaction, the next frame's visiting order and its gathered copies: ~25
+        # dependent launches of this library and nothing else -- is replayed as ONE CUDA graph (lib.graph_scope), like the LM
+        # loop inside sb_lm_frame.  Not with tracked points (their bookkeeping allocates) or the autograd deformation.
+        scoped = (getattr(self, "_finished_once", False) and getattr(self, "gt", None) is None and beta is not None
+                  and beta.shape[0] == self.ED.num and getattr(self.opt, "use_derived_gradient", True)
+                  and getattr(self, "_sorted", None) is not None and os.environ.get("SB_TAIL_GRAPH", "1") != "0")
+        if not scoped:
+            self.apply(beta)
+            self.fuse(frame)
+            self.finish_frame(frame, filename)
+            return beta
+        if getattr(self, "_tail_graph", None) is None:
+            self._tail_graph = ctypes.c_void_p(0)
+        with lib.graph_scope(self._tail_graph):
+            self.apply(beta)
+            self.fuse(frame)
+            self._compact(frame)
+            self._order_and_gather()
+        self._handover()
         return beta
 
     def enable_tracking(self, gt):

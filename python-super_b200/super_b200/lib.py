@@ -92,8 +92,44 @@ def ptr(t):
     return t.data_ptr()
 
 
+_SCOPE_STREAM = None      # inside graph_scope(): the capture stream every call of the scope is issued on
+
+
 def stream():
+    if _SCOPE_STREAM is not None:
+        return _SCOPE_STREAM
     return torch.cuda.current_stream().cuda_stream
+
+
+class graph_scope:
+    """with graph_scope(handle): ...C-ABI calls only...  -- the calls are stream-captured and replayed as ONE CUDA graph on
+    the current stream (sb_graph_scope_begin/_end; handle = ctypes.c_void_p owned by the caller).  No torch device work, no
+    synchronisation inside.  handle None: plain execution."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __enter__(self):
+        global _SCOPE_STREAM
+        if self.handle is None:
+            return self
+        self.real = torch.cuda.current_stream().cuda_stream
+        use = ctypes.c_void_p()
+        rc = load().sb_graph_scope_begin(ctypes.byref(self.handle), self.real, ctypes.byref(use))
+        if rc != 0:
+            raise SuperB200Error(f"sb_graph_scope_begin failed: {_ERR.get(rc, rc)}")
+        _SCOPE_STREAM = use.value or 0
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global _SCOPE_STREAM
+        if self.handle is None:
+            return False
+        _SCOPE_STREAM = None
+        rc = load().sb_graph_scope_end(ctypes.byref(self.handle), self.real, 1 if et is not None else 0)
+        if rc != 0 and et is None:
+            raise SuperB200Error(f"sb_graph_scope_end failed: {_ERR.get(rc, rc)}")
+        return False
 
 
 # kernels of OURS launched per C-ABI call (library kernels such as the CUB scans are not counted)
