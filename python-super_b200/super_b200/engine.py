@@ -11,6 +11,7 @@ super_b200/super/ expose exact-size views of them.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from types import SimpleNamespace as NS
@@ -328,7 +329,10 @@ class Tracker:
     # is 60 % of the frame and scales with bw^2: 255 us at bw 300 against 312 us with a 25 % safety margin).
     def _publish_count(self):
         self._order_and_gather()
-        self._handover()
+        if getattr(self, "_defer_handover", False):
+            self._handover_pending = True      # inside tail_scope: after the captured launches have been issued
+        else:
+            self._handover()
 
     def _order_and_gather(self):
         self._order = None
@@ -613,26 +617,35 @@ class Tracker:
     def track(self, frame, filename=None):
         """SuPer.fusion (/root/reference/super/super.py:66-83): solve -> update -> fuse -> compact."""
         beta = self.solve(frame)
-        # The frame's tail -- warp/update, fusion, compaction, the next frame's visiting order and its gathered copies: ~25
-        # dependent launches of this library and nothing else -- is replayed as ONE CUDA graph (lib.graph_scope), like the LM
-        # loop inside sb_lm_frame.  Not with tracked points (their bookkeeping allocates) or the autograd deformation.
+        with self.tail_scope(beta):
+            self.apply(beta)
+            self.fuse(frame)
+            self.finish_frame(frame, filename)
+        return beta
+
+    @contextlib.contextmanager
+    def tail_scope(self, beta):
+        """The frame's tail -- warp/update, fusion, compaction, the next frame's visiting order and its gathered copies: ~25
+        dependent launches of this library and nothing else -- replayed as ONE CUDA graph (lib.graph_scope), like the LM loop
+        inside sb_lm_frame.  apply / fuse / finish_frame (Surfels.update / fuseInputData / prepareStableIndexNSwapAllModel)
+        are called inside it; the hand-over of the row count to the host (pinned copies, torch) follows the graph's launch.
+        Plain execution with tracked points (their bookkeeping allocates), the autograd deformation and on the first frames."""
         scoped = (getattr(self, "_finished_once", False) and getattr(self, "gt", None) is None and beta is not None
                   and beta.shape[0] == self.ED.num and getattr(self.opt, "use_derived_gradient", True)
                   and getattr(self, "_sorted", None) is not None and os.environ.get("SB_TAIL_GRAPH", "1") != "0")
         if not scoped:
-            self.apply(beta)
-            self.fuse(frame)
-            self.finish_frame(frame, filename)
-            return beta
+            yield
+            return
         if getattr(self, "_tail_graph", None) is None:
             self._tail_graph = ctypes.c_void_p(0)
-        with lib.graph_scope(self._tail_graph):
-            self.apply(beta)
-            self.fuse(frame)
-            self._compact(frame)
-            self._order_and_gather()
-        self._handover()
-        return beta
+        self._defer_handover, self._handover_pending = True, False
+        try:
+            with lib.graph_scope(self._tail_graph):
+                yield
+        finally:
+            self._defer_handover = False
+        if self._handover_pending:
+            self._handover()
 
     def enable_tracking(self, gt):
         """--tracking_gt_file: gt = {"%06d": (T,3) int array [x, y, valid]} (utils/utils.py:383-391).  Tracked surfel ids

@@ -74,10 +74,13 @@ class SuPer(torch.nn.Module):
             deform_param = self.graph_fit(inputs, self.sf, sfdata, models)
             if deform_param is not None:
                 deform_param = deform_param.detach()
-        self.sf.update(deform_param)
         if self.opt.phase == "test":
-            self.sf.fuseInputData(inputs, sfdata)                # fuse the input data into the reference model
-            self.sf.prepareStableIndexNSwapAllModel(inputs, sfdata)
+            with self.sf.tail_scope(deform_param):               # the three stages' launches replayed as one CUDA graph
+                self.sf.update(deform_param)
+                self.sf.fuseInputData(inputs, sfdata)            # fuse the input data into the reference model
+                self.sf.prepareStableIndexNSwapAllModel(inputs, sfdata)
             if int(self.sf.time) % int(getattr(self.opt, "save_sample_freq", 10)) == 0:
                 self.sf.evaluate()
+        else:
+            self.sf.update(deform_param)
         return deform_param
