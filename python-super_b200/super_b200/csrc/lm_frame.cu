@@ -17,6 +17,8 @@
 //     LM decision in its last block) and a Gram pass that reads them back; after a reject the Gram pass returns at once.
 // One iteration = 8 launches: band_reverse (+ store -> band), band_chol3_dual, band_combine, band_chol3, band_backsub4 (+ step),
 // data_eval_decide (+ ARAP/Rot blocks + decision), jtj_gram (records), jtj_scatter.  No host synchronisation, no allocation.
+#include <cstring>
+
 #include "common.cuh"
 #include "lm_state.cuh"
 #include "internal.h"
@@ -160,13 +162,28 @@ struct LMGraphCache {
     cudaGraphExec_t exec;
     int warmed;
     int capturing;      // sb_graph_scope_begin .. _end
+    // sb_lm_frame: instantiated graphs by the argument block they were captured for (frames alternate between two input
+    // buffers and the row bound is quantised by the caller, so the block repeats: a hit is one cudaGraphLaunch)
+    static constexpr int SLOTS = 4;
+    SbLMFrame key[SLOTS];
+    cudaGraphExec_t slot_exec[SLOTS];
+    unsigned long long last_use[SLOTS], clock;
 };
+
+static LMGraphCache* new_cache() {
+    LMGraphCache* gc = new LMGraphCache();
+    gc->capture_stream = nullptr; gc->exec = nullptr; gc->warmed = 0; gc->capturing = 0; gc->clock = 0;
+    for (int i = 0; i < LMGraphCache::SLOTS; ++i) { gc->slot_exec[i] = nullptr; gc->last_use[i] = 0; memset(&gc->key[i], 0, sizeof(SbLMFrame)); }
+    return gc;
+}
 
 int sb_lm_graph_destroy(void** cache) {
     if (!cache) return SB_ERR_ARG;
     LMGraphCache* gc = (LMGraphCache*)*cache;
     if (gc) {
         if (gc->exec) cudaGraphExecDestroy(gc->exec);
+        for (int i = 0; i < LMGraphCache::SLOTS; ++i)
+            if (gc->slot_exec[i]) cudaGraphExecDestroy(gc->slot_exec[i]);
         if (gc->capture_stream) cudaStreamDestroy(gc->capture_stream);
         delete gc;
         *cache = nullptr;
@@ -197,7 +214,7 @@ int sb_graph_scope_begin(void** cache, void* stream, void** use_stream) {
     if (!cache || !use_stream) return SB_ERR_ARG;
     LMGraphCache* gc = (LMGraphCache*)*cache;
     if (!gc) {
-        gc = new LMGraphCache{nullptr, nullptr, 0, 0};
+        gc = new_cache();
         if (cudaStreamCreateWithFlags(&gc->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { delete gc; return SB_ERR_CUDA; }
         *cache = gc;
     }
@@ -242,7 +259,7 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
     if (!f->graph_cache || events) return lm_frame_launches(f, stream);
     LMGraphCache* gc = (LMGraphCache*)*f->graph_cache;
     if (!gc) {
-        gc = new LMGraphCache{nullptr, nullptr, 0, 0};
+        gc = new_cache();
         if (cudaStreamCreateWithFlags(&gc->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { delete gc; return SB_ERR_CUDA; }
         *f->graph_cache = gc;
     }
@@ -250,8 +267,24 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
         gc->warmed = 1;
         return lm_frame_launches(f, stream);
     }
-    // Capture this frame's sequence (argument checks included: nothing is launched), update the instantiated graph in place
-    // -- the topology is the same every frame, only kernel parameters and grids change -- and launch it on the caller's stream.
+    // The argument block this frame's graph depends on (host-side values and device addresses; what the kernels read through
+    // those addresses -- beta, the LM state, the row count -- is not part of a graph)
+    SbLMFrame key;
+    memset(&key, 0, sizeof(key));
+    memcpy(&key, f, sizeof(SbLMFrame));
+    key.graph_cache = nullptr;
+    int hit = -1, lru = 0;
+    for (int i = 0; i < LMGraphCache::SLOTS; ++i) {
+        if (gc->slot_exec[i] && memcmp(&gc->key[i], &key, sizeof(SbLMFrame)) == 0) hit = i;
+        if (gc->last_use[i] < gc->last_use[lru]) lru = i;
+    }
+    if (hit >= 0) {
+        gc->last_use[hit] = ++gc->clock;
+        return cudaGraphLaunch(gc->slot_exec[hit], (cudaStream_t)stream) == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+    }
+    // Miss: capture this frame's sequence (argument checks included: nothing is launched), update the least recently used
+    // instantiated graph in place -- the topology is the same every frame, only kernel parameters and grids change -- and
+    // launch it on the caller's stream.
     if (cudaStreamBeginCapture(gc->capture_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) return SB_ERR_CUDA;
     const int rc = lm_frame_launches(f, (void*)gc->capture_stream);
     cudaGraph_t graph = nullptr;
@@ -261,7 +294,14 @@ int sb_lm_frame(const SbLMFrame* f, void* stream) {
         cudaGetLastError();
         return rc != SB_OK ? rc : SB_ERR_CUDA;
     }
-    return graph_update_and_launch(gc, graph, (cudaStream_t)stream);
+    cudaGraphExec_t keep = gc->exec;
+    gc->exec = gc->slot_exec[lru];
+    const int lrc = graph_update_and_launch(gc, graph, (cudaStream_t)stream);
+    gc->slot_exec[lru] = gc->exec;
+    gc->exec = keep;
+    if (lrc == SB_OK) { gc->key[lru] = key; gc->last_use[lru] = ++gc->clock; }
+    else gc->last_use[lru] = 0;
+    return lrc;
 }
 
 }  // extern "C"

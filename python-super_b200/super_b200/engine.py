@@ -555,7 +555,12 @@ class Tracker:
                 order = ops.tuple_order(sfv.knn_indices, self.cur.n_dev, self.ED.node_pos, self.block_bw)
             elif getattr(self, "_sorted", None) is not None and self._sorted_rows >= self.n_bound and self.band is not None:
                 # the frame loop reads the copies gathered into visiting order (coalesced); same values, same order
-                s, nb_ = self._sorted, self.n_bound
+                # Row bound handed to the frame loop: rounded up to 16 k rows (the kernels stop at the device-side count; rows
+                # behind it are never read), so that sb_lm_frame's argument block repeats from frame to frame and its
+                # instantiated graph is simply launched again instead of being re-captured and updated (~90 us of host time
+                # during which the device has nothing to do: the host has just waited for the previous frame)
+                s = self._sorted
+                nb_ = min(self.cap, -(-self.n_bound // 16384) * 16384)
                 sfv = NS(points=s.points[:nb_], norms=sfv.norms, knn_indices=s.knn_idx[:nb_], knn_w=s.knn_w[:nb_], ED=self.ED)
                 order = None
             jev = sev = tev = None
