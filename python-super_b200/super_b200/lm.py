@@ -84,6 +84,30 @@ def band_frame_ok(band, cluster_size):
     return band is not None and cluster_size >= 8 and bool(lib.load().sb_band3_fits(band.n, band.bw))
 
 
+def _build_frame_struct(sf, ed, J, n_cap, n_dev, order, vmap, nmap, cam, opt, ws, band, u, v, minimal_loss, cluster_size):
+    f = SbLMFrame()
+    f.points, f.knn_idx, f.knn_w, f.order = ptr(sf.points), ptr(sf.knn_indices), ptr(sf.knn_w), ptr(order)
+    f.n_cap, f.n_dev = n_cap, ptr(n_dev)
+    f.ed_points, f.ed_knn, f.J = ptr(ed.points), ptr(ed.knn_indices), J
+    f.vmap, f.nmap, f.H, f.W = ptr(vmap), ptr(nmap), cam.H, cam.W
+    f.intr = (ctypes.c_double * 4)(cam.fx, cam.fy, cam.cx, cam.cy)
+    f.lam_data, f.lam_arap, f.lam_rot = opt.sf_point_plane_weight, opt.mesh_arap_weight, opt.mesh_rot_weight
+    f.use_arap, f.use_rot = int(bool(opt.mesh_arap)), int(bool(opt.mesh_rot))
+    f.iterations, f.u, f.v, f.minimal_loss = int(opt.num_optimize_iterations), u, v, minimal_loss
+    f.state, f.beta, f.best = ptr(ws.state.buf), ptr(ws.beta), ptr(ws.best)
+    f.partials_loss, f.n_partials_loss = ptr(ws.partials_frame), ws.partials_frame.numel()
+    f.rows, f.keys, f.row_stride = ptr(ws.rows), ptr(ws.keys), ws.keys.numel()
+    f.rec_vals, f.rec_keys, f.rec_count, f.rec_cap = ptr(ws.rec_vals), ptr(ws.rec_keys), ptr(ws.rec_count), ws.rec_cap
+    f.n, f.bw, f.ldab = band.n, band.bw, band.ldab
+    f.node_pos, f.pos_node = ptr(band.node_pos), ptr(band.pos_node)
+    f.fx_store = (ctypes.c_void_p * 2)(ptr(band.fx[0]), ptr(band.fx[1]))
+    f.fx_shift, f.fx_gshift = band.fx_shift, band.fx_gshift
+    f.AB, f.g = ptr(band._AB), ptr(band._g)
+    f.band_overflow, f.dinv, f.info = ptr(band.overflow), ptr(band.dinv), ptr(band.info)
+    f.solver_ws, f.solver_ws_bytes, f.n_ctas = ptr(band.ws4), band.ws4.numel(), int(cluster_size)
+    return f
+
+
 def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, order=None, n_dev=None, cluster_size=148,
              jtj_events=None, solve_events=None, row_capacity=None, stage_events=None):
     """The whole LM loop of one frame in one C call (sb_lm_frame).  Same arguments and result as lm_solve.
@@ -110,26 +134,20 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
     if getattr(band, "ws4", None) is None:
         band.ws4 = torch.zeros(int(l.sb_band4_workspace_bytes(band.n, band.bw, band.ldab)), dtype=torch.uint8, device=dev)
     vmap, nmap = maps
-    f = SbLMFrame()
-    f.points, f.knn_idx, f.knn_w, f.order = ptr(sf.points), ptr(sf.knn_indices), ptr(sf.knn_w), ptr(order)
-    f.n_cap, f.n_dev = n_cap, ptr(n_dev)
-    f.ed_points, f.ed_knn, f.J = ptr(ed.points), ptr(ed.knn_indices), J
-    f.vmap, f.nmap, f.H, f.W = ptr(vmap), ptr(nmap), cam.H, cam.W
-    f.intr = (ctypes.c_double * 4)(cam.fx, cam.fy, cam.cx, cam.cy)
-    f.lam_data, f.lam_arap, f.lam_rot = opt.sf_point_plane_weight, opt.mesh_arap_weight, opt.mesh_rot_weight
-    f.use_arap, f.use_rot = int(bool(opt.mesh_arap)), int(bool(opt.mesh_rot))
-    f.iterations, f.u, f.v, f.minimal_loss = int(opt.num_optimize_iterations), u, v, minimal_loss
-    f.state, f.beta, f.best = ptr(ws.state.buf), ptr(ws.beta), ptr(ws.best)
-    f.partials_loss, f.n_partials_loss = ptr(ws.partials_frame), ws.partials_frame.numel()
-    f.rows, f.keys, f.row_stride = ptr(ws.rows), ptr(ws.keys), ws.keys.numel()
-    f.rec_vals, f.rec_keys, f.rec_count, f.rec_cap = ptr(ws.rec_vals), ptr(ws.rec_keys), ptr(ws.rec_count), ws.rec_cap
-    f.n, f.bw, f.ldab = band.n, band.bw, band.ldab
-    f.node_pos, f.pos_node = ptr(band.node_pos), ptr(band.pos_node)
-    f.fx_store = (ctypes.c_void_p * 2)(ptr(band.fx[0]), ptr(band.fx[1]))
-    f.fx_shift, f.fx_gshift = band.fx_shift, band.fx_gshift
-    f.AB, f.g = ptr(band._AB), ptr(band._g)
-    f.band_overflow, f.dinv, f.info = ptr(band.overflow), ptr(band.dinv), ptr(band.info)
-    f.solver_ws, f.solver_ws_bytes, f.n_ctas = ptr(band.ws4), band.ws4.numel(), int(cluster_size)
+    # the argument block only depends on persistent buffers and a few scalars: built once per distinct combination (the two
+    # input buffers alternate), reused afterwards -- the host has just waited for the previous frame when it gets here, so
+    # everything in front of the launch is time the device spends idle
+    ck = (ptr(sf.points), ptr(sf.knn_indices), ptr(sf.knn_w), ptr(order), n_cap, ptr(n_dev), ptr(ed.points), ptr(ed.knn_indices),
+          ptr(vmap), ptr(nmap), id(band), ptr(band.ws4), float(u), float(v), float(minimal_loss), int(cluster_size),
+          ptr(ws.rows), ptr(ws.partials_frame), cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy)
+    cache = ws.__dict__.setdefault("frame_structs", {})
+    f = cache.get(ck) if not (jtj_events or solve_events or stage_events) else None
+    if f is None:
+        f = _build_frame_struct(sf, ed, J, n_cap, n_dev, order, vmap, nmap, cam, opt, ws, band, u, v, minimal_loss, cluster_size)
+        if not (jtj_events or solve_events or stage_events):
+            if len(cache) > 16:
+                cache.clear()
+            cache[ck] = f
     keep = []
     for name, evs in (("jtj", jtj_events), ("solve", solve_events), ("stage", stage_events)):
         if evs:
