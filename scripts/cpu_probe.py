@@ -14,9 +14,10 @@ dd = [torch.from_numpy(f["depth"]).cuda() for f in fr]
 dc = torch.from_numpy(fr[0]["color"]).cuda()
 K, iK = torch.from_numpy(fr[0]["K"]), torch.from_numpy(fr[0]["inv_K"])
 acc = {"lm_frame": 0.0, "refresh": 0.0, "n": 0}
+calls = []
 orig = lm.lm_frame
 def timed(*a, **k):
-    t0 = time.perf_counter(); r = orig(*a, **k); acc["lm_frame"] += time.perf_counter() - t0; acc["n"] += 1; return r
+    t0 = time.perf_counter(); r = orig(*a, **k); dt = time.perf_counter() - t0; acc["lm_frame"] += dt; calls.append(round(1e6 * dt)); acc["n"] += 1; return r
 lm.lm_frame = timed
 orig_rb = engine.Tracker._refresh_bound
 def timed_rb(self):
@@ -35,3 +36,4 @@ e1.record(); torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 print("frames 30: GPU ms/frame %.3f | wall ms/frame %.3f | host in sb_lm_frame (capture + update + launch) ms/frame %.3f | host waiting in _refresh_bound ms/frame %.3f"
       % (e0.elapsed_time(e1) / 30, 1e3 * wall / 30, 1e3 * acc["lm_frame"] / 30, 1e3 * acc["refresh"] / 30))
+print("host us per sb_lm_frame call, last 30 frames:", calls[-30:])
