@@ -150,6 +150,10 @@ int sb_lm_graph_destroy(void** cache);
  * this library (and nothing that synchronises) may be issued in between; abort_scope != 0 drops the capture. */
 int sb_graph_scope_begin(void** cache, void* stream, void** use_stream);
 int sb_graph_scope_end(void** cache, void* stream, int abort_scope);
+/* A non-blocking CUDA stream (one that does not synchronise implicitly with the legacy default stream): the side stream of the
+ * input prefetch (SuPer.prefetch). */
+int sb_stream_create(void** out);
+int sb_stream_destroy(void* stream);
 /* device-to-device copy of n ints on the stream (a memcpy node inside a scope) */
 int sb_copy_i32(int* dst, const int* src, int n, void* stream);
 

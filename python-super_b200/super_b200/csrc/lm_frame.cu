@@ -247,6 +247,15 @@ int sb_graph_scope_end(void** cache, void* stream, int abort_scope) {
     return graph_update_and_launch(gc, graph, (cudaStream_t)stream);
 }
 
+int sb_stream_create(void** out) {      // non-blocking: does not synchronise with the legacy default stream
+    if (!out) return SB_ERR_ARG;
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return SB_ERR_CUDA;
+    *out = (void*)s;
+    return SB_OK;
+}
+int sb_stream_destroy(void* s) { return (s && cudaStreamDestroy((cudaStream_t)s) == cudaSuccess) ? SB_OK : SB_ERR_ARG; }
+
 int sb_copy_i32(int* dst, const int* src, int n, void* stream) {
     if (!dst || !src || n <= 0) return SB_ERR_ARG;
     return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess

@@ -24,6 +24,9 @@ class SuPer(torch.nn.Module):
         self.sf = None
         self._frames = None
         self._fi = 0
+        self._prefetched = {}        # host data_ptr -> (device tensor, copy-done event, host tensor): prefetch()
+        self._copy_stream = None
+        self._frame_entered = None
         if opt.use_derived_gradient:
             from .LM import LM_Solver
             self.lm = LM_Solver(opt)
@@ -37,8 +40,46 @@ class SuPer(torch.nn.Module):
         self._fi ^= 1
         return self._frames[self._fi]
 
+    _HOST_KEYS = ("divterm", "K", "inv_K", "stereo_T", "time", "ID")
+
+    def prefetch(self, inputs):
+        """Start the host->device copies of a LATER frame's pinned image tensors on a side stream, so that they run under the
+        current frame's kernels; forward() picks the device copies up when it is handed the same host tensors.  (The
+        reference stages its inputs at the top of forward, super.py:31-34, i.e. serially in front of every frame.)
+        The side stream is NON-BLOCKING (sb_stream_create): a stream created through torch synchronises implicitly with the
+        legacy default stream the frame's launches go to, which serialises the copy behind the whole frame.  Three
+        persistent staging sets rotate (no allocation); a set is rewritten only after the frame that used it, two frames
+        back, has finished (the copy stream waits for the event recorded when the current frame was entered)."""
+        import ctypes
+        from .. import lib
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self._copy_stream is None:
+            h = ctypes.c_void_p()
+            lib.call("sb_stream_create", ctypes.byref(h))
+            self._copy_stream = torch.cuda.ExternalStream(h.value, device=dev)
+            self._stage, self._stage_i = [dict(), dict(), dict()], 0
+        self._stage_i = (self._stage_i + 1) % 3
+        slot = self._stage[self._stage_i]
+        todo = [(key, ipt) for key, ipt in inputs.items()
+                if torch.is_tensor(ipt) and key not in self._HOST_KEYS and ipt.device.type == "cpu" and ipt.is_pinned()]
+        for key, ipt in todo:                                   # first use of a set: allocate on the caller's stream
+            if key not in slot or slot[key].shape != ipt.shape or slot[key].dtype != ipt.dtype:
+                slot[key] = torch.empty(ipt.shape, dtype=ipt.dtype, device=dev)
+        if self._frame_entered is not None:
+            self._copy_stream.wait_event(self._frame_entered)
+        self._prefetched.clear()
+        with torch.cuda.stream(self._copy_stream):
+            for key, ipt in todo:
+                slot[key].copy_(ipt, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                self._prefetched[ipt.data_ptr()] = (slot[key], ev, ipt)
+
     def forward(self, models, inputs):
         dev = torch.device("cuda", torch.cuda.current_device())
+        if self._copy_stream is not None:
+            self._frame_entered = torch.cuda.Event()
+            self._frame_entered.record()
         staged = {}
         for key, ipt in inputs.items():                          # super.py:31-34
             if torch.is_tensor(ipt):
@@ -46,6 +87,10 @@ class SuPer(torch.nn.Module):
                     staged[key] = float(ipt.reshape(-1)[0])
                 elif key in ("K", "inv_K", "stereo_T", "time", "ID"):
                     staged[key] = ipt                            # small host-side parameters
+                elif ipt.device.type == "cpu" and ipt.data_ptr() in self._prefetched and self._prefetched[ipt.data_ptr()][2] is ipt:
+                    d, ev, _ = self._prefetched.pop(ipt.data_ptr())
+                    torch.cuda.current_stream().wait_event(ev)
+                    staged[key] = d
                 else:
                     staged[key] = ipt.to(dev, non_blocking=True)
             else:
