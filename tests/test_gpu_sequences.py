@@ -198,3 +198,52 @@ def test_frame_loop_equals_stepwise_loop(monkeypatch):
         assert np.abs(s0["loss"] - s1["loss"]).max() <= 1e-11 * s1["loss"].max()
         assert np.abs(s0["u_trace"] - s1["u_trace"]).max() == 0.0
         assert (b0 - b1).abs().max() < 1e-11
+
+
+def test_graph_replay_equals_stream_launches(monkeypatch):
+    """The LM loop and the frame tail replayed from CUDA graphs (sb_lm_frame's graph cache, lib.graph_scope /
+    Tracker.tail_scope) against the same launches issued one by one on the stream: bit-identical state, frame by frame."""
+    from super_b200 import engine, synth
+    H, W, step, frames = 480, 640, 32, 7
+
+    def run(graphs):
+        monkeypatch.setenv("SB_LM_GRAPH", "1" if graphs else "0")
+        monkeypatch.setenv("SB_TAIL_GRAPH", "1" if graphs else "0")
+        opt = so.default_opt(height=H, width=W, mesh_step_size=step)
+        trk = engine.Tracker(opt, device="cuda:0")
+        tex = synth.texture(H, W)
+        betas = []
+        for t in range(1, frames + 1):
+            fr = synth.frame_inputs(t, H, W, tex=tex)
+            b = trk.step(torch.from_numpy(fr["depth"]).cuda(), torch.from_numpy(fr["color"]).cuda(),
+                         torch.from_numpy(fr["K"]), torch.from_numpy(fr["inv_K"]), fr["time"])
+            if b is not None:
+                betas.append(b.clone())
+        return betas, trk.snapshot()
+
+    b1, s1 = run(True)
+    b0, s0 = run(False)
+    assert len(b1) == len(b0) == frames - 1
+    for x, y in zip(b1, b0):
+        assert torch.equal(x, y)
+    for k in s0:
+        assert torch.equal(s1[k], s0[k]), k
+
+
+@pytest.mark.parametrize("J,n", [(266, 50000), (35, 4097), (1209, 30000), (65535, 2000)])
+def test_tuple_order_groups_like_a_full_key_sort(J, n):
+    """sb_tuple_order (keys with ceil(log2(J+1)) bits per node id, radix sort over just those bits) against a stable sort
+    of the full (ascending node set) keys: same visiting order, rows beyond the device-side count last."""
+    from super_b200 import ops
+    g = torch.Generator().manual_seed(J + n)
+    idx = torch.stack([torch.randperm(J, generator=g)[:4] for _ in range(n)]).to(torch.int32)
+    # many equal node sets in different slot orders, as in the tracker
+    idx[n // 2:] = idx[: n - n // 2][:, torch.tensor([2, 0, 3, 1])]
+    n_live = n - 37
+    n_dev = torch.tensor([n_live], dtype=torch.int32, device="cuda")
+    pos = torch.arange(J, dtype=torch.int32, device="cuda")
+    order = ops.tuple_order(idx.cuda(), n_dev, pos, None).cpu().long()
+    srt = np.sort(idx.numpy().astype(np.int64), axis=1)[:n_live]
+    ref = torch.from_numpy(np.lexsort((srt[:, 3], srt[:, 2], srt[:, 1], srt[:, 0])))      # stable, first column primary
+    assert torch.equal(order[:n_live], ref)
+    assert sorted(order[n_live:].tolist()) == list(range(n_live, n))
