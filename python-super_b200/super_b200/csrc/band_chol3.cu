@@ -1231,7 +1231,11 @@ __device__ void role_U(const Args3& a, double* smem) {
 //   panel p, phase 2: the owner of (I,J), J > p, applies A(I,J) -= L(I,p) L(J,p)^T from the stored tiles (one product),
 //                     next block column first.
 // The only cross-CTA dependencies are diag_done[p] and rows_done[p] (+ the hot flag for P): no per-panel barrier.
-__device__ __forceinline__ int tile_owner(int I, int J, int NU) { return (int)(((unsigned)I * 7u + (unsigned)J * 13u) % (unsigned)NU); }
+// I + (WB+1) J is injective over a panel's trailing window (<= WB rows and columns), so a panel's tiles spread almost evenly
+// over the CTAs: worst CTA 4.5 tile-equivalents instead of 6.5 with the former 7 I + 13 J at bw 640 on 72 CTAs (mean 3.3)
+__device__ __forceinline__ int tile_owner(int I, int J, int NU, int WB) {
+    return (int)(((unsigned)I + (unsigned)(WB + 1) * (unsigned)J) % (unsigned)NU);
+}
 
 __device__ void role_U2(const Args3& a, double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1257,14 +1261,14 @@ __device__ void role_U2(const Args3& a, double* smem) {
         for (int c = tid; c < nrows * (nrows + 1) / 2 + nrows; c += THREADS) {
             if (c < nrows) {                                   // candidate row I = p+1+c of column p (row p+1 is P's)
                 const int I = p + 1 + c;
-                if (c >= 1 && tile_owner(I, p, NU) == ui) lst1[atomicAdd(&n1, 1)] = I;
+                if (c >= 1 && tile_owner(I, p, NU, WB) == ui) lst1[atomicAdd(&n1, 1)] = I;
             } else {
                 const int t = c - nrows;
                 int ri = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
                 while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
                 while (ri * (ri + 1) / 2 > t) --ri;
                 const int I = p + 1 + ri, J = p + 1 + (t - ri * (ri + 1) / 2);
-                if (t != 0 && NB * (I - J) - (NB - 1) <= bw && tile_owner(I, J, NU) == ui) lst2[atomicAdd(&n2, 1)] = (J << 16) | I;
+                if (t != 0 && NB * (I - J) - (NB - 1) <= bw && tile_owner(I, J, NU, WB) == ui) lst2[atomicAdd(&n2, 1)] = (J << 16) | I;
             }
         }
         __syncthreads();
@@ -1296,21 +1300,45 @@ __device__ void role_U2(const Args3& a, double* smem) {
         // ---- phase 2 ----
         if (m2 > 0) {
             cta_wait(rows_done + p, nrows);                     // every L(.,p) is stored
-            for (int x = 0; x < m2; ++x) {
+            // Software pipeline over this CTA's tiles: the operands of tile x+1 (two L tiles, 4 values per thread each, and
+            // the old values of its output fragments) are in flight in registers while tile x is multiplied; the role was
+            // bound by three dependent L2 round trips per tile (~2.5 k cycles) around ~1 k cycles of DMMA.
+            const int bi = warp >> 1, bj0 = 2 * (warp & 1);
+            double nI[4], nJ[4], nold[2][2];
+            auto fetch = [&](int x) {
                 const int I = lst2[x] & 0xffff, J = lst2[x] >> 16;
-                const bool diag = (I == J);
-                __syncthreads();
-                load_g_tile(lb_tile(a, I, I - p), LIs, S36, tid, THREADS);
-                if (!diag) load_g_tile(lb_tile(a, J, J - p), LJs, S36, tid, THREADS);
-                const int bi = warp >> 1, bj0 = 2 * (warp & 1);
-                double oldv[2][2];
+                const double* GI = lb_tile(a, I, I - p);
+                const double* GJ = lb_tile(a, J, J - p);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    nI[q] = __ldcg(GI + q * THREADS + tid);
+                    nJ[q] = (I != J) ? __ldcg(GJ + q * THREADS + tid) : 0.0;
+                }
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int i = NB * I + 8 * bi + fr, j = NB * J + 8 * (bj0 + q) + 2 * fc + e;
-                        oldv[q][e] = in_band(a, i, j) ? __ldcg(ab_at(a, i, j)) : 0.0;
+                        nold[q][e] = in_band(a, i, j) ? __ldcg(ab_at(a, i, j)) : 0.0;
                     }
+            };
+            fetch(0);
+            for (int x = 0; x < m2; ++x) {
+                const int I = lst2[x] & 0xffff, J = lst2[x] >> 16;
+                const bool diag = (I == J);
+                __syncthreads();                                // the previous tile's products are done with LIs / LJs
+                double oldv[2][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = q * THREADS + tid;
+                    LIs[(e >> 5) * S36 + (e & 31)] = nI[q];
+                    if (!diag) LJs[(e >> 5) * S36 + (e & 31)] = nJ[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) oldv[q][e] = nold[q][e];
+                if (x + 1 < m2) fetch(x + 1);
                 __syncthreads();
                 const double* Lb = diag ? LIs : LJs;
                 double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
