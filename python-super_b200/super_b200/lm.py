@@ -139,7 +139,9 @@ def lm_frame(sf, maps, cam, opt, ws, band, u=10.0, v=7.5, minimal_loss=1e10, ord
     # everything in front of the launch is time the device spends idle
     ck = (ptr(sf.points), ptr(sf.knn_indices), ptr(sf.knn_w), ptr(order), n_cap, ptr(n_dev), ptr(ed.points), ptr(ed.knn_indices),
           ptr(vmap), ptr(nmap), id(band), ptr(band.ws4), float(u), float(v), float(minimal_loss), int(cluster_size),
-          ptr(ws.rows), ptr(ws.partials_frame), cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy)
+          ptr(ws.rows), ptr(ws.partials_frame), cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy,
+          float(opt.sf_point_plane_weight), float(opt.mesh_arap_weight), float(opt.mesh_rot_weight), bool(opt.mesh_arap),
+          bool(opt.mesh_rot), int(opt.num_optimize_iterations), ptr(ws.beta), ptr(ws.state.buf))
     cache = ws.__dict__.setdefault("frame_structs", {})
     f = cache.get(ck) if not (jtj_events or solve_events or stage_events) else None
     if f is None:
