@@ -70,6 +70,10 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 #define GSTAMP(a, slot, p_) do { if ((DBGF(a) & 4) && (p_) >= 1 && (p_) <= (a).ke - 2) { \
     atomicAdd((unsigned long long*)(a).prof + 64 + (slot), gtime_ns()); atomicAdd((unsigned long long*)(a).prof + 69 + (slot), 1ull); } } while (0)
 
+// quiet-NaN test on the bit pattern: the polls of the by-value hand-over must not touch the FP64 pipe (DSETP) -- warp 4 of the
+// pivot CTA polls while it shares scheduler AND FP64 pipe with the pivot chain
+__device__ __forceinline__ bool is_qnan(double v) { return (__double2hiint(v) & 0x7ff80000) == 0x7ff80000; }
+
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -179,7 +183,7 @@ __device__ __forceinline__ void load_hot_tiles2(const Args3& a, const double* __
             const bool ok1 = (r0 + dr < NB) && (i1 + dr < a.n) && (d1 + dr >= 0) && (d1 + dr <= a.bw);
             v0[q] = ok0 ? __ldcg(H0 + (r0 + dr) * NB + c) : 0.0;
             v1[q] = ok1 ? __ldcg(H1 + (r0 + dr) * NB + c) : 0.0;
-            again = again || (v0[q] != v0[q]) || (v1[q] != v1[q]);
+            again = again || is_qnan(v0[q]) || is_qnan(v1[q]);
         }
         if (again && (++polls & 63) == 0) {
             if (*(volatile int*)a.info != 0) again = false;
@@ -227,7 +231,7 @@ __device__ __forceinline__ void load_g_tile_polled(const double* __restrict__ G,
             for (int q = 0; q < 4; ++q) {
                 const int e = base + q * nt + t;
                 v[q] = (e < T32) ? __ldcg(G + e) : 0.0;
-                again = again || (v[q] != v[q]);
+                again = again || is_qnan(v[q]);
             }
             if (again && (++polls & 63) == 0) {
                 if (*(volatile int*)info != 0) again = false;
