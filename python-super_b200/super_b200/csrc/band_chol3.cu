@@ -758,17 +758,20 @@ __device__ void role_P(const Args3& a, double* smem) {
                 double dq = T[31 * S36 + 31];
                 while (dq != dq && ++spins < (1 << 20)) dq = T[31 * S36 + 31];
                 asm volatile("" ::: "memory");
+                const long long f0 = (prof && warp == 3) ? clock64() : 0;
                 double y0 = 0.0, y1 = 0.0;
                 dmma884(y0, y1, a3[0], T[(24 + fr) * S36 + 24 + fc]);
                 dmma884(y0, y1, a3[1], T[(24 + fr) * S36 + 28 + fc]);
                 *reinterpret_cast<double2*>(Lx + (8 * rb + fr) * S36 + 24 + 2 * fc) = make_double2(y0, y1);
                 bar_sync(2, 128);                          // Y_3 of all four row blocks
+                if (prof && warp == 3 && *(volatile double*)Lx != 1.2345e300) tsacc[4] += clock64() - f0;
                 bar_arrive(1, 192);                        // I/O warps may store L(k,k-1)
                 double c0 = 0.0, c1 = 0.0;
                 dmma884(c0, c1, Lx[(8 * rb + fr) * S36 + 24 + fc], Lx[fr * S36 + 24 + fc]);
                 dmma884(c0, c1, Lx[(8 * rb + fr) * S36 + 28 + fc], Lx[fr * S36 + 28 + fc]);
                 v0 = dold[0] - (pre0[0] + c0);
                 v1 = dold[1] - (pre0[1] + c1);
+                if (prof && warp == 3 && v0 != 1.2345e300) tsacc[5] += clock64() - f0;
             } else {
                 bar_arrive(1, 192);
                 v0 = D[(8 * rb + fr) * S33 + 2 * fc];
@@ -910,6 +913,7 @@ __device__ void role_P(const Args3& a, double* smem) {
     if (prof && warp == 1 && lane == 0) for (int q = 0; q < 5; ++q) a.prof[31 + q] = wacc[q];
     if (prof && lane == 0 && warp == 1) for (int q = 0; q < 4; ++q) a.prof[44 + q] = tsacc[q];
     if (prof && lane == 0 && warp == 3) for (int q = 0; q < 4; ++q) a.prof[58 + q] = tsacc[q];
+    if (prof && lane == 0 && warp == 3) { a.prof[62] = tsacc[4]; a.prof[63] = tsacc[5]; }
     if (prof && lane == 0 && warp == 7) for (int q = 0; q < 2; ++q) a.prof[6 + q] = tsacc[q];
     if (prof && lane == 0) a.prof[36 + warp] = (warp == 1) ? arrive_acc : (tA_prev << 32) | arrive_acc;
     if (prof && tid == 0) for (int q = 4; q < 7; ++q) a.prof[44 + q] = tsacc[q];

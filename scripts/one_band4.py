@@ -74,6 +74,6 @@ if variant == 4 and os.environ.get("PROFP", "0") == "1":
           "\n   inverse builder: total", int(prof[30]) // m, "[wait cols<b, S products, wait T_b, M products, publish]", [int(v) // m for v in prof[31:36]],
           "| inverse builder's barrier-7 arrival after the Cholesky end", int(prof[37]) // m, "| warps 2..7: (panels in which they reached barrier 7 AFTER the Cholesky's end, mean delay)", [(int(v) >> 32, (int(v) & 0xffffffff) // max(1, int(v) >> 32)) for v in prof[38:44]], "| row b published since its own loop top", [int(v) // m for v in prof[44:48]],
           "\n   compute warp 3 since the panel's barrier [T_1 seen, arrived at the staging barrier, substitution loop done, T_2 seen]", [int(v) // m for v in prof[58:62]],
-          "| I/O warp 7 [staging begins, staged]", [int(v) // m for v in prof[6:8]],
+          "| final step in warp 3 since T_3 seen [all four Y_3 exchanged, D value ready]", [int(v) // m for v in prof[62:64]], "| I/O warp 7 [staging begins, staged]", [int(v) // m for v in prof[6:8]],
           "\n   U (rank 3; it owns a tile in few panels, so its waits are mostly idle time) [wait upd(p-1), operand loads, inverse tile by value, products + stores, signal, idle]:", [int(v) // m for v in prof[52:58]])
     l.sb_band3_debug(0)
