@@ -442,6 +442,14 @@ class Tracker:
         self._fi ^= 1
         return self.frames[self._fi]
 
+    def __del__(self):
+        try:                      # the instantiated graph of the frame tail (tail_scope)
+            h = getattr(self, "_tail_graph", None)
+            if h:
+                lib.load().sb_lm_graph_destroy(ctypes.byref(h))
+        except Exception:
+            pass
+
     def reset(self):
         """Forget the sequence but keep every allocation (surfel buffers, band stores, solver workspaces, Jacobian-row
         scratch): the next init_state() starts a new sequence of the same image size without touching the allocator --
