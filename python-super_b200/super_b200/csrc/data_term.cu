@@ -656,6 +656,14 @@ data_eval_decide_kernel(DataArgs a, double* __restrict__ partials, DecideArgs d,
         Eval ev;
         if (ROWS) {
             const int sid = a.order ? a.order[i] : i;
+            if (!a.order) {   // this thread's NEXT surfel (gathered arrays: consecutive rows) towards L1 while this one is evaluated
+                const size_t nx = (size_t)i + (size_t)((int)gridDim.x - rb) * BLOCK;
+                if (nx < (size_t)n) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.points + 3 * nx));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.knn_idx + 4 * nx));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.knn_w + 4 * nx));
+                }
+            }
             const bool ok = eval_surfel<true, true, NS>(a, sid, ev, ro.rows + i, ro.row_stride, nodes_s);
             if (ok) {
                 ro.rows[(size_t)28 * ro.row_stride + i] = ev.r;
