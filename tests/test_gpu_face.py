@@ -278,3 +278,38 @@ def test_surfels_face_methods(tmp_path):
         b3 = trk.step(torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["color"]).cuda(), torch.from_numpy(f["K"]),
                       torch.from_numpy(f["inv_K"]), f["time"], filename=f["filename"])
     assert b3 is not None and n > 0
+
+
+def test_super_forward_with_prefetch_equals_without():
+    """SuPer.prefetch (next frame's host->device copies on a non-blocking side stream, staged in rotating device buffers)
+    changes WHEN the inputs are copied, not what the tracker computes: bit-identical deformations over 5 frames."""
+    import bench
+    from super_b200.super.super import SuPer
+
+    def run(prefetch):
+        host = bench.frames_host(6, seed=3)
+        pin = []
+        for f in host:
+            pin.append({("depth", 0): torch.from_numpy(f["depth"])[None].pin_memory(),
+                        ("color", 0): torch.from_numpy(f["color"])[None].pin_memory(),
+                        "K": torch.from_numpy(f["K"])[None], "inv_K": torch.from_numpy(f["inv_K"])[None],
+                        "time": torch.tensor([f["time"]], dtype=torch.float64), "filename": [f["filename"]],
+                        "ID": torch.tensor([f["ID"]]), "divterm": torch.tensor([f["divterm"]], dtype=torch.float64)})
+        model = SuPer(bench.make_opt())
+        models = type("Models", (), {})()
+        models.super = model
+        out = []
+        if prefetch:
+            model.prefetch(pin[0])
+        for k in range(len(pin)):
+            beta = model(models, dict(pin[k]))
+            if prefetch and k + 1 < len(pin):
+                model.prefetch(pin[k + 1])
+            if beta is not None:
+                out.append(beta.clone().cpu())
+        return out
+
+    a, b = run(True), run(False)
+    assert len(a) == len(b) == 5
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
