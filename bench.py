@@ -297,6 +297,8 @@ def run_cuda(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     d2h = 0
+    ev_prev = None
+    beta_hosts = [beta_host, beta_host]
     use_prefetch = os.environ.get("SB_E2E_PREFETCH", "1") != "0"
     if use_prefetch:
         model.prefetch(pin[1 + Wm])      # like every later frame's: one frame ahead, under the previous frame's kernels
@@ -306,8 +308,19 @@ def run_cuda(args, rank, world, local_rank):
             model.prefetch(pin[1 + Wm + k + 1])                  # next frame's H2D copies on a side stream (SuPer.prefetch)
         if beta_host.shape != beta.shape:
             beta_host = torch.zeros(beta.shape, dtype=torch.float64).pin_memory()
-        beta_host.copy_(beta, non_blocking=False)            # D2H read of the step's result (synchronises)
+            beta_hosts = [beta_host, torch.zeros(beta.shape, dtype=torch.float64).pin_memory()]
+        # D2H read of the step's result into pinned memory, every step; the host waits for it ONE step later (a consumer that
+        # works one frame behind), so that issuing the next frame is not held up by the read -- all reads are complete before
+        # the timed region ends
+        beta_hosts[k & 1].copy_(beta, non_blocking=True)
+        ev_read = torch.cuda.Event()
+        ev_read.record()
+        if ev_prev is not None:
+            ev_prev.synchronize()
+        ev_prev = ev_read
         d2h = beta.numel() * 8
+    if ev_prev is not None:
+        ev_prev.synchronize()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -348,7 +361,7 @@ def run_cuda(args, rank, world, local_rank):
                    "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
         "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K,
-                "api": "super_b200.super.super.SuPer.forward(models, inputs) with pinned host depth+colour" + ("; SuPer.prefetch(next inputs) starts the next frame's host->device copies on a side stream, inside the timed region" if use_prefetch else "")},
+                "api": "super_b200.super.super.SuPer.forward(models, inputs) with pinned host depth+colour" + ("; SuPer.prefetch(next inputs) starts the next frame's host->device copies on a side stream, inside the timed region" if use_prefetch else "") + "; every step's result is copied to pinned host memory, the host waits for the copy one step later"},
         "gpu_launches": launches,
         "gpu_launches_per_lm_iteration": launches / (K * LM_ITERS),
         "clocks": clocks,

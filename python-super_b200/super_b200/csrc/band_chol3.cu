@@ -408,6 +408,129 @@ __device__ __forceinline__ bool warp_potrf_blocked(double* __restrict__ D, doubl
     return bad;
 }
 
+// ---- The same factorisation SPLIT between the chain warp and the helpers.  The chain warp above carries all 32 rows (own-row
+// solve interleaved with the replica: 224 FP64 instructions per 8 columns on a warp that issues one every 3.4 cycles) and, between
+// two blocks, updates the whole next block column.  Here it factors ONLY the 8x8 diagonal blocks (188 instructions) and, between
+// two blocks, forms L(b+1,b) = D(b+1,b) T_b^T and the next diagonal block D(b+1,b+1) -= L(b+1,b) L(b+1,b)^T (2 + 2 DMMAs);
+// the rows below, L(r,b) = D(r,b) T_b^T for r >= b+2, and every other trailing update are formed by the three helper warps one
+// block behind (helper_split), which have a whole block's chain (~700 cycles) for a handful of DMMAs.
+// lready[b] = tag once L(b+1,b) is in Lcol (T_b is in Ls before that): the helpers' and the other readers' flag.
+__device__ __forceinline__ bool warp_potrf_split(double* __restrict__ D, double* __restrict__ Lcol, double* __restrict__ dinvs,
+                                                 double* __restrict__ Ls, volatile int* lready, int tag, int lane,
+                                                 long long* ts = nullptr, long long tbase = 0) {
+    const int fr = lane >> 2, fc = lane & 3, jc = lane & 7;
+    bool bad = false;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 8 * b;
+        double d[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) d[i][j] = D[(c0 + i) * S33 + c0 + j];      // broadcast loads
+        double x[8];                                                                 // column jc of T_b = L_bb^-1
+        double myinv = 0.0;
+        long long q0 = 0, q1;
+        if (ts) { if (d[7][7] != 1.2345e300) q0 = clock64(); ts[4] += q0 - tbase; tbase = q0; }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double piv = d[c][c];
+            double s0 = (jc == c) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < c; ++t) {
+                if (t & 1) s1 = fma(-d[c][t], x[t], s1); else s0 = fma(-d[c][t], x[t], s0);
+            }
+            const double inv = rsqrt_pivot(piv);
+            x[c] = (s0 + s1) * inv;
+            bad = bad || !(piv > 0.0);
+#pragma unroll
+            for (int i = c + 1; i < 8; ++i) d[i][c] *= inv;
+#pragma unroll
+            for (int j = c + 1; j < 8; ++j)
+#pragma unroll
+                for (int i = j; i < 8; ++i) d[i][j] = fma(-d[i][c], d[j][c], d[i][j]);
+            if (lane == c) myinv = inv;
+        }
+        if (lane < 8) {
+            dinvs[c0 + lane] = myinv;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Ls[(c0 + i) * S36 + c0 + lane] = bad ? 0.0 : x[i];   // (7,7) last: T_b's ready flag
+        }
+        __syncwarp();
+        if (ts) { if (x[7] != 1.2345e300) q1 = clock64(); ts[5] += q1 - tbase; tbase = q1; }
+        if (b < 3) {
+            bar_sync(4 + b, 128);       // the helpers have applied every earlier block to D(b+1,b) and D(b+1,b+1)
+            const double a0 = D[(c0 + 8 + fr) * S33 + c0 + fc], a1 = D[(c0 + 8 + fr) * S33 + c0 + 4 + fc];
+            const double t0 = Ls[(c0 + fr) * S36 + c0 + fc], t1 = Ls[(c0 + fr) * S36 + c0 + 4 + fc];
+            double* dd = D + (c0 + 8 + fr) * S33 + c0 + 8 + 2 * fc;
+            const double dd0 = dd[0], dd1 = dd[1];
+            double l0 = 0.0, l1 = 0.0;
+            dmma884(l0, l1, a0, t0);
+            dmma884(l0, l1, a1, t1);
+            Lcol[(c0 + 2 * fc) * S36 + c0 + 8 + fr] = l0;
+            Lcol[(c0 + 2 * fc + 1) * S36 + c0 + 8 + fr] = l1;
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); lready[b] = tag; }
+            const double f0 = Lcol[(c0 + fc) * S36 + c0 + 8 + fr], f1 = Lcol[(c0 + 4 + fc) * S36 + c0 + 8 + fr];
+            double u0 = 0.0, u1 = 0.0;
+            dmma884(u0, u1, f0, f0);
+            dmma884(u0, u1, f1, f1);
+            dd[0] = dd0 - u0;
+            dd[1] = dd1 - u1;
+            __syncwarp();
+        }
+        if (ts) { q1 = clock64(); ts[6] += q1 - tbase; tbase = q1; }
+    }
+    return bad;
+}
+
+// helper h (0..2) behind block b of warp_potrf_split: rows r >= b+2 of block column b, then the updates of every block right of
+// it except the next diagonal one.  Barrier 11 among the three helpers.
+__device__ __forceinline__ void helper_split(double* __restrict__ D, double* __restrict__ Lcol, const double* __restrict__ Ls,
+                                             volatile int* lready, int tag, int b, int h, int lane) {
+    const int fr = lane >> 2, fc = lane & 3, c0 = 8 * b;
+    {
+        int spins = 0;
+        while (lready[b] != tag && ++spins < (1 << 20)) {}
+        asm volatile("" ::: "memory");
+    }
+    const volatile double* Lv = Lcol;
+    const volatile double* Tv = Ls;
+    const int r = b + 2 + h;
+    if (r <= 3) {
+        const double a0 = D[(8 * r + fr) * S33 + c0 + fc], a1 = D[(8 * r + fr) * S33 + c0 + 4 + fc];
+        double l0 = 0.0, l1 = 0.0;
+        dmma884(l0, l1, a0, Tv[(c0 + fr) * S36 + c0 + fc]);
+        dmma884(l0, l1, a1, Tv[(c0 + fr) * S36 + c0 + 4 + fc]);
+        Lcol[(c0 + 2 * fc) * S36 + 8 * r + fr] = l0;
+        Lcol[(c0 + 2 * fc + 1) * S36 + 8 * r + fr] = l1;
+    }
+    if (b >= 2) return;
+    bar_sync(11, 96);
+    // blocks (oi,oj): b = 0: h0 (2,1) (2,2) | h1 (3,1) (3,2) | h2 (3,3);  b = 1: h0 (3,2) | h1 (3,3)
+    int oi[2] = {-1, -1}, oj[2] = {-1, -1};
+    if (b == 0) {
+        if (h == 0) { oi[0] = 2; oj[0] = 1; oi[1] = 2; oj[1] = 2; }
+        else if (h == 1) { oi[0] = 3; oj[0] = 1; oi[1] = 3; oj[1] = 2; }
+        else { oi[0] = 3; oj[0] = 3; }
+    } else {
+        if (h == 0) { oi[0] = 3; oj[0] = 2; }
+        else if (h == 1) { oi[0] = 3; oj[0] = 3; }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (oi[q] < 0) continue;
+        double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            dmma884(u0, u1, Lv[(c0 + 4 * ks + fc) * S36 + 8 * oi[q] + fr], Lv[(c0 + 4 * ks + fc) * S36 + 8 * oj[q] + fr]);
+        double* dd = D + (8 * oi[q] + fr) * S33 + 8 * oj[q] + 2 * fc;
+        dd[0] -= u0;
+        dd[1] -= u1;
+    }
+    __syncwarp();
+}
+
 // ---- L^-1 behind the Cholesky, blocked by 8, on two warps.  With 8x8 blocks L_ik, T_b = L_bb^-1:
 //        M_bb = T_b,     M_bj = -T_b * S_bj,   S_bj = sum_{k=j}^{b-1} L_bk M_kj     (j < b)
 // Warp "T" (warp_tinv_trailing) inverts the diagonal blocks row by row right behind the pivot chain; warp "M"
@@ -885,6 +1008,7 @@ __device__ void role_P(const Args3& a, double* smem) {
                     // the NEXT block's accumulator first: it is the one the chain of the substitution waits for
 #pragma unroll
                     for (int uu = t + 1; uu < 4; ++uu) {
+
                         dmma884(acc[uu][0], acc[uu][1], ya, Lk[(8 * t + fc) * S36 + 8 * uu + fr]);
                         dmma884(acc[uu][0], acc[uu][1], yb, Lk[(8 * t + 4 + fc) * S36 + 8 * uu + fr]);
                     }
